@@ -1,0 +1,852 @@
+// liblba.so -- context, C ABI (include/lba.h) and the Levenberg-Marquardt driver.
+//
+// Replaces the scipy call at /root/reference/src/bundle_adjustment.py:319
+// (least_squares TRF + LSMR + finite differences) with
+//   fused residual/Jacobian kernel -> per-line / per-camera J^T J blocks ->
+//   Schur elimination of the line blocks -> block-Jacobi PCG on the reduced camera
+//   system (matrix-free) -> back-substitution -> trial evaluation -> accept / reject.
+// The same algorithm is restated in numpy in oracle/line_ba_oracle.py (test oracle).
+#include "../../include/lba.h"
+#include "lba_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lba;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(LBA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define CKR(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != LBA_OK) return r_; \
+  } while (0)
+
+// ---- NCCL through dlopen: single-GPU use never loads it ----------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return LBA_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(LBA_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(LBA_ERR_COMM, "libnccl is missing required symbols");
+  g_nccl.handle = h;
+  return LBA_OK;
+}
+
+// ---- device buffer ------------------------------------------------------------------------------
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n && p) return LBA_OK;
+    release();
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return fail(LBA_ERR_CUDA, "cudaMalloc(%zu B): %s", bytes, cudaGetErrorString(e)); }
+    n = count;
+    return LBA_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DBuf() { release(); }
+};
+
+struct lba_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_sm = 148;
+
+  // problem
+  int m = 0, nc = 0, nl = 0, ngroups = 0;
+  bool have_problem = false, have_eval = false, have_blocks = false, have_scaling = false;
+  bool sorted_input = true;
+  DBuf<int> obs_cam, obs_line, cam_pos, cam_perm, cam_ptr, line_ptr, group_line, orig_of;
+  DBuf<double> cst;
+
+  // state
+  DBuf<double> cams, cams_new, pts, pts_new, Gm, api_tmp;
+  DBuf<CamRec> recs, recs_new;
+  DBuf<double> r, r_new, jl, jc, w, wk, wr;
+  DBuf<double> V, gl, Vinv, y, Dl;
+  DBuf<double> U, gc, Dc, Mpart, bpart, Minv, b;
+  DBuf<double> cgx, cgr, cgz, cgp, tab, qpart;
+  DBuf<double> cost_partial, bs_partial;
+  DBuf<Scalars> scal;
+  DBuf<CgState> cgst;
+  DBuf<unsigned long long> gbits;
+  DBuf<int> clamped;
+  Scalars* h_scal = nullptr;   // pinned
+  CgState* h_cgst = nullptr;   // pinned
+  unsigned long long* h_gbits = nullptr;
+  int* h_clamped = nullptr;
+
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+
+  // instrumentation
+  int64_t launches = 0;
+  bool profiling = false;
+  double prof_ms[LBA_K_COUNT] = {0};
+  int64_t prof_n[LBA_K_COUNT] = {0};
+  int launch_err = 0;
+
+  void pre(int cls) {
+    ++launches;
+    if (profiling) cudaEventRecord(ev0, stream);
+    (void)cls;
+  }
+  void post(int cls) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !launch_err) {
+      launch_err = 1;
+      fail(LBA_ERR_CUDA, "kernel launch (class %d) failed: %s", cls, cudaGetErrorString(e));
+    }
+    if (profiling) {
+      cudaEventRecord(ev1, stream);
+      cudaEventSynchronize(ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev0, ev1);
+      prof_ms[cls] += ms;
+      prof_n[cls] += 1;
+    }
+  }
+};
+
+#define LAUNCH(ctx, cls, kern, grid, block, ...)                 \
+  do {                                                           \
+    (ctx)->pre(cls);                                             \
+    kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->post(cls);                                            \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static const char* kClassNames[LBA_K_COUNT] = {
+    "residual", "jacobian", "cam_blocks", "line_factor", "line_scalars", "cam_precond",
+    "pcg_line", "pcg_cam", "pcg_update", "backsub", "misc", "comm"};
+
+// ---- C ABI: lifecycle ---------------------------------------------------------------------------
+extern "C" const char* lba_last_error(void) { return g_err.c_str(); }
+extern "C" int lba_version(void) { return 100; }
+extern "C" const char* lba_kernel_class_name(int32_t k) { return (k >= 0 && k < LBA_K_COUNT) ? kClassNames[k] : "?"; }
+
+extern "C" void lba_default_options(lba_options* o) {
+  if (!o) return;
+  o->max_iter = 50;
+  o->pcg_max_iter = 200;
+  o->ftol = 1e-4;
+  o->xtol = 1e-8;
+  o->gtol = 1e-8;
+  o->lambda0 = 1e-4;
+  o->lambda_min = 1e-12;
+  o->lambda_max = 1e12;
+  o->pcg_tol = 1e-2;
+  o->min_ratio = 1e-4;
+  o->verbose = 0;
+  o->reserved = 0;
+}
+
+extern "C" int lba_create(int device, lba_ctx** out) {
+  if (!out) return fail(LBA_ERR_ARG, "lba_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(LBA_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count) return fail(LBA_ERR_ARG, "device %d out of range (count %d)", device, count);
+  CK(cudaSetDevice(device));
+  lba_ctx* c = new lba_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  CK(cudaMallocHost(&c->h_scal, sizeof(Scalars)));
+  CK(cudaMallocHost(&c->h_cgst, sizeof(CgState)));
+  CK(cudaMallocHost(&c->h_gbits, sizeof(unsigned long long)));
+  CK(cudaMallocHost(&c->h_clamped, sizeof(int)));
+  CKR(c->scal.alloc(1));
+  CKR(c->cgst.alloc(1));
+  CKR(c->gbits.alloc(1));
+  CKR(c->clamped.alloc(1));
+  CK(cudaMemsetAsync(c->scal.p, 0, sizeof(Scalars), c->stream));
+  CK(cudaMemsetAsync(c->clamped.p, 0, sizeof(int), c->stream));
+  *out = c;
+  return LBA_OK;
+}
+
+extern "C" int lba_comm_destroy(lba_ctx* ctx) {
+  if (ctx && ctx->comm) {
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+  }
+  return LBA_OK;
+}
+
+extern "C" int lba_destroy(lba_ctx* ctx) {
+  if (!ctx) return LBA_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  lba_comm_destroy(ctx);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  if (ctx->h_cgst) cudaFreeHost(ctx->h_cgst);
+  if (ctx->h_gbits) cudaFreeHost(ctx->h_gbits);
+  if (ctx->h_clamped) cudaFreeHost(ctx->h_clamped);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LBA_OK;
+}
+
+extern "C" int lba_set_stream(lba_ctx* ctx, void* s) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return LBA_OK;
+}
+
+extern "C" int lba_synchronize(lba_ctx* ctx) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->launch_err) return LBA_ERR_CUDA;
+  return LBA_OK;
+}
+
+extern "C" int64_t lba_launch_count(lba_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lba_set_profiling(lba_ctx* ctx, int32_t enable) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  ctx->profiling = enable != 0;
+  for (int k = 0; k < LBA_K_COUNT; ++k) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+  return LBA_OK;
+}
+
+extern "C" int lba_get_profile(lba_ctx* ctx, double* ms, int64_t* launches) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  for (int k = 0; k < LBA_K_COUNT; ++k) {
+    if (ms) ms[k] = ctx->prof_ms[k];
+    if (launches) launches[k] = ctx->prof_n[k];
+  }
+  return LBA_OK;
+}
+
+// ---- comm -----------------------------------------------------------------------------------------
+extern "C" int lba_comm_unique_id(void* id128) {
+  if (!id128) return fail(LBA_ERR_ARG, "id is NULL");
+  CKR(load_nccl());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(LBA_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  memcpy(id128, &id, 128);
+  return LBA_OK;
+}
+
+extern "C" int lba_comm_init(lba_ctx* ctx, const void* id128, int32_t rank, int32_t world) {
+  if (!ctx || !id128) return fail(LBA_ERR_ARG, "ctx or id is NULL");
+  if (world < 1 || rank < 0 || rank >= world) return fail(LBA_ERR_ARG, "bad rank %d / world %d", rank, world);
+  CKR(load_nccl());
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+  if (r != ncclSuccess) return fail(LBA_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->rank = rank;
+  ctx->world = world;
+  return LBA_OK;
+}
+
+static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+  if (c->world <= 1) return LBA_OK;
+  c->pre(LBA_K_COMM);
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, n, dt, op, c->comm, c->stream);
+  c->post(LBA_K_COMM);
+  --c->launches;  // a collective is not one of our kernels
+  if (r != ncclSuccess) return fail(LBA_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return LBA_OK;
+}
+static int allreduce_sum(lba_ctx* c, double* buf, size_t n) { return allreduce(c, buf, n, ncclDouble, ncclSum); }
+
+// ---- problem set-up -------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static int upload(lba_ctx* c, DBuf<T>& dst, const std::vector<T>& src) {
+  CKR(dst.alloc(src.size()));
+  if (!src.empty()) CK(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return LBA_OK;
+}
+
+extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t nl64, const int64_t* cam_idx,
+                               const int64_t* line_idx, const double* n, const double* p0, const double* p1) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (m64 < 0 || nc64 < 0 || nl64 < 0 || m64 > 0x7fffffffLL / 12 || nc64 > 0x7fffffffLL / 32 || nl64 > 0x7fffffffLL / 32)
+    return fail(LBA_ERR_ARG, "problem size out of range (m=%lld Nc=%lld Nl=%lld)", (long long)m64, (long long)nc64, (long long)nl64);
+  if (m64 > 0 && (!cam_idx || !line_idx || !n || !p0 || !p1)) return fail(LBA_ERR_ARG, "NULL input array");
+  CK(cudaSetDevice(ctx->device));
+  const int m = (int)m64, nc = (int)nc64, nl = (int)nl64;
+  ctx->have_problem = ctx->have_eval = ctx->have_blocks = ctx->have_scaling = false;
+
+  // indices to the host (they drive the one-time layout construction)
+  std::vector<int64_t> hc, hl;
+  const int64_t* pc = cam_idx;
+  const int64_t* pl = line_idx;
+  if (m > 0 && is_device_ptr(cam_idx)) { hc.resize(m); CK(cudaMemcpy(hc.data(), cam_idx, (size_t)m * 8, cudaMemcpyDeviceToHost)); pc = hc.data(); }
+  if (m > 0 && is_device_ptr(line_idx)) { hl.resize(m); CK(cudaMemcpy(hl.data(), line_idx, (size_t)m * 8, cudaMemcpyDeviceToHost)); pl = hl.data(); }
+
+  bool sorted = true;
+  std::vector<int> line_cnt((size_t)nl + 1, 0);
+  for (int i = 0; i < m; ++i) {
+    const int64_t c = pc[i], l = pl[i];
+    if (c < 0 || c >= nc) return fail(LBA_ERR_ARG, "camera_indices[%d]=%lld out of range [0,%d)", i, (long long)c, nc);
+    if (l < 0 || l >= nl) return fail(LBA_ERR_ARG, "lines_indices[%d]=%lld out of range [0,%d)", i, (long long)l, nl);
+    if (i > 0 && l < pl[i - 1]) sorted = false;
+    ++line_cnt[(size_t)l + 1];
+  }
+  std::vector<int> line_ptr((size_t)nl + 1, 0);
+  int kmax = 0;
+  for (int l = 0; l < nl; ++l) {
+    kmax = std::max(kmax, line_cnt[(size_t)l + 1]);
+    line_ptr[(size_t)l + 1] = line_ptr[l] + line_cnt[(size_t)l + 1];
+  }
+  if (kmax > LBA_MAX_OBS_PER_LINE)
+    return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
+
+  // line order: stable counting sort by line (identity when the input is already sorted)
+  std::vector<int> orig_of;
+  std::vector<int> obs_cam(m), obs_line(m);
+  if (sorted) {
+    for (int i = 0; i < m; ++i) { obs_cam[i] = (int)pc[i]; obs_line[i] = (int)pl[i]; }
+  } else {
+    orig_of.resize(m);
+    std::vector<int> cur(line_ptr.begin(), line_ptr.end() - 1);
+    for (int i = 0; i < m; ++i) orig_of[cur[pl[i]]++] = i;
+    for (int i = 0; i < m; ++i) { obs_cam[i] = (int)pc[orig_of[i]]; obs_line[i] = (int)pl[orig_of[i]]; }
+  }
+  // groups: whole lines, at most kTile observations
+  std::vector<int> group_line;
+  group_line.push_back(0);
+  {
+    int cur = 0;
+    for (int l = 0; l < nl; ++l) {
+      const int k = line_cnt[(size_t)l + 1];
+      if (cur + k > kTile || (l - group_line.back()) >= kTile) { group_line.push_back(l); cur = 0; }
+      cur += k;
+    }
+    if (nl > 0) group_line.push_back(nl);
+  }
+  const int ngroups = (int)group_line.size() - 1;
+  // camera order: stable counting sort of the line-ordered observations by camera
+  std::vector<int> cam_ptr((size_t)nc + 1, 0), cam_perm(m), cam_pos(m);
+  for (int i = 0; i < m; ++i) ++cam_ptr[(size_t)obs_cam[i] + 1];
+  for (int c = 0; c < nc; ++c) cam_ptr[(size_t)c + 1] += cam_ptr[c];
+  {
+    std::vector<int> cur(cam_ptr.begin(), cam_ptr.end() - 1);
+    for (int i = 0; i < m; ++i) { const int j = cur[obs_cam[i]]++; cam_perm[j] = i; cam_pos[i] = j; }
+  }
+
+  ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ngroups = std::max(ngroups, 0);
+  ctx->sorted_input = sorted;
+  CKR(upload(ctx, ctx->obs_cam, obs_cam));
+  CKR(upload(ctx, ctx->obs_line, obs_line));
+  CKR(upload(ctx, ctx->cam_pos, cam_pos));
+  CKR(upload(ctx, ctx->cam_perm, cam_perm));
+  CKR(upload(ctx, ctx->cam_ptr, cam_ptr));
+  CKR(upload(ctx, ctx->line_ptr, line_ptr));
+  CKR(upload(ctx, ctx->group_line, group_line));
+  if (!sorted) CKR(upload(ctx, ctx->orig_of, orig_of));
+
+  // observation constants: AoS (m,3) -> SoA, m_e = n x p_e
+  CKR(ctx->cst.alloc((size_t)9 * m));
+  if (m > 0) {
+    DBuf<double> tmp;
+    const double* src[3] = {n, p0, p1};
+    const double* dev[3];
+    size_t need = 0;
+    for (int k = 0; k < 3; ++k) if (!is_device_ptr(src[k])) need += (size_t)3 * m;
+    CKR(tmp.alloc(need));
+    size_t off = 0;
+    for (int k = 0; k < 3; ++k) {
+      if (is_device_ptr(src[k])) { dev[k] = src[k]; continue; }
+      CK(cudaMemcpyAsync(tmp.p + off, src[k], (size_t)3 * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+      dev[k] = tmp.p + off;
+      off += (size_t)3 * m;
+    }
+    LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(m, 256), 256, m, sorted ? nullptr : ctx->orig_of.p, dev[0], dev[1], dev[2], ctx->cst.p);
+    CK(cudaStreamSynchronize(ctx->stream));  // tmp and the host vectors go out of scope
+  } else {
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+
+  // state buffers
+  const size_t M = (size_t)m, NC = (size_t)nc, NL = (size_t)nl, NG = (size_t)ctx->ngroups;
+  CKR(ctx->cams.alloc(NC * 6)); CKR(ctx->cams_new.alloc(NC * 6)); CKR(ctx->api_tmp.alloc(std::max(NC * 6, (size_t)1)));
+  CKR(ctx->pts.alloc(NL * 6)); CKR(ctx->pts_new.alloc(NL * 6));
+  CKR(ctx->Gm.alloc(NC * 9)); CKR(ctx->recs.alloc(NC)); CKR(ctx->recs_new.alloc(NC));
+  CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * M));
+  CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M));
+  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6)); CKR(ctx->Vinv.alloc(NL * 21)); CKR(ctx->y.alloc(NL * 6)); CKR(ctx->Dl.alloc(NL * 6));
+  CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
+  CKR(ctx->Mpart.alloc(NC * 27)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
+  CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
+  CKR(ctx->tab.alloc(NC * 6)); CKR(ctx->qpart.alloc(NC * 6));
+  CKR(ctx->cost_partial.alloc(NG)); CKR(ctx->bs_partial.alloc(NG * 4));
+  ctx->have_problem = true;
+  if (ctx->launch_err) return LBA_ERR_CUDA;
+  return LBA_OK;
+}
+
+// U and gc (and Mpart/bpart) are stored back to back ([nc][21] then [nc][6]) so that one
+// all-reduce covers both.
+static inline double* gc_of(lba_ctx* c) { return c->U.p + (size_t)c->nc * 21; }
+static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc * 21; }
+
+static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
+  EvalArgs a;
+  a.m = c->m; a.group_line = c->group_line.p; a.line_ptr = c->line_ptr.p; a.obs_cam = c->obs_cam.p;
+  a.obs_line = c->obs_line.p; a.cam_pos = c->cam_pos.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
+  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p; a.cost_partial = c->cost_partial.p;
+  a.proj = nullptr; a.orig_of = c->sorted_input ? nullptr : c->orig_of.p;
+  return a;
+}
+
+static int load_state(lba_ctx* c, const double* cams_api, const double* pts_api) {
+  if (!c->have_problem) return fail(LBA_ERR_STATE, "lba_set_problem has not been called");
+  if (!cams_api || !pts_api) return fail(LBA_ERR_ARG, "NULL parameter array");
+  CK(cudaSetDevice(c->device));
+  if (c->nc > 0) {
+    CK(cudaMemcpyAsync(c->api_tmp.p, cams_api, (size_t)c->nc * 48, cudaMemcpyDefault, c->stream));
+    LAUNCH(c, LBA_K_MISC, k_cams_from_api, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->api_tmp.p, c->cams.p);
+    LAUNCH(c, LBA_K_MISC, k_cam_prepare, cdiv(c->nc, 128), 128, c->nc, c->cams.p, c->recs.p, c->Gm.p);
+  }
+  if (c->nl > 0) CK(cudaMemcpyAsync(c->pts.p, pts_api, (size_t)c->nl * 48, cudaMemcpyDefault, c->stream));
+  c->have_eval = c->have_blocks = false;
+  return LBA_OK;
+}
+
+static int store_state(lba_ctx* c, double* cams_api, double* pts_api) {
+  if (c->nc > 0) {
+    LAUNCH(c, LBA_K_MISC, k_cams_to_api, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->cams.p, c->api_tmp.p);
+    CK(cudaMemcpyAsync(cams_api, c->api_tmp.p, (size_t)c->nc * 48, cudaMemcpyDefault, c->stream));
+  }
+  if (c->nl > 0) CK(cudaMemcpyAsync(pts_api, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDefault, c->stream));
+  return LBA_OK;
+}
+
+// residual-only pass at (recs, pts) -> r_out, scal.cost (all-reduced)
+static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, double* r_out) {
+  if (c->ngroups > 0) {
+    EvalArgs a = eval_args(c, recs, pts, r_out);
+    LAUNCH(c, LBA_K_RESIDUAL, k_eval<false>, c->ngroups, kTile, a);
+  }
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
+  return LBA_OK;
+}
+
+// fused residual + Jacobian + line blocks at the current state -> r, jl, jc, V, gl, scal.cost
+static int run_jacobian(lba_ctx* c) {
+  if (c->ngroups > 0) {
+    EvalArgs a = eval_args(c, c->recs.p, c->pts.p, c->r.p);
+    LAUNCH(c, LBA_K_JACOBIAN, k_eval<true>, c->ngroups, kTile, a);
+  }
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
+  c->have_eval = true;
+  c->have_blocks = false;
+  return LBA_OK;
+}
+
+// camera blocks U_c, g_c (+ all-reduce), Marquardt scaling, gradient inf-norm
+static int run_blocks(lba_ctx* c, bool update_scaling) {
+  if (c->nc > 0) {
+    LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+           (const double*)nullptr, c->r.p, c->U.p, gc_of(c));
+    CKR(allreduce_sum(c, c->U.p, (size_t)c->nc * 27));
+    CK(cudaMemcpyAsync(c->gc.p, gc_of(c), (size_t)c->nc * 48, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (update_scaling) {
+    const int first = c->have_scaling ? 0 : 1;
+    if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_update_scaling, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, c->Dc.p, first);
+    if (c->nl > 0) LAUNCH(c, LBA_K_MISC, k_update_scaling, cdiv((long long)c->nl * 6, 256), 256, c->nl, c->V.p, c->Dl.p, first);
+    c->have_scaling = true;
+  }
+  CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
+  if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_absmax, std::min(cdiv((long long)c->nc * 6, 256), 4 * c->n_sm), 256, (size_t)c->nc * 6, c->gc.p, c->gbits.p);
+  if (c->nl > 0) LAUNCH(c, LBA_K_MISC, k_absmax, std::min(cdiv((long long)c->nl * 6, 256), 4 * c->n_sm), 256, (size_t)c->nl * 6, c->gl.p, c->gbits.p);
+  CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
+  c->have_blocks = true;
+  return LBA_OK;
+}
+
+// Solve the damped system for the resident evaluation: leaves dc in cgx, the candidate
+// parameters in cams_new / pts_new and the model-reduction sums in scal.
+static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
+                     int* breakdown_out) {
+  const int nc = c->nc, nl = c->nl, m = c->m;
+  if (nl > 0)
+    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, 128), 128, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p);
+  if (m > 0)
+    LAUNCH(c, LBA_K_LINE_SCALARS, k_line_scalars, cdiv(m, 256), 256, m, c->obs_line.p, c->jl.p, c->Vinv.p, c->y.p, c->wk.p, c->wr.p);
+  if (nc > 0) {
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+           (const double*)c->wk.p, c->wr.p, c->Mpart.p, bpart_of(c));
+    CKR(allreduce_sum(c, c->Mpart.p, (size_t)nc * 27));
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
+  }
+  CgArgs ca;
+  ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
+  ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
+  ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
+  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_init, 1, kCgThreads, ca);
+
+  LinePassArgs la;
+  la.m = m; la.group_line = c->group_line.p; la.line_ptr = c->line_ptr.p; la.obs_cam = c->obs_cam.p;
+  la.obs_line = c->obs_line.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
+  la.w = c->w.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p; la.partial = c->bs_partial.p; la.st = c->cgst.p;
+
+  int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
+  int issued = 0;
+  while (true) {
+    for (int q = 0; q < chunk && issued < pcg_max_iter; ++q, ++issued) {
+      if (c->ngroups > 0) LAUNCH(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->ngroups, kTile, la);
+      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, m, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
+      CKR(allreduce_sum(c, c->qpart.p, (size_t)nc * 6));
+      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_update, 1, kCgThreads, ca);
+    }
+    CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_cgst->done || issued >= pcg_max_iter) break;
+    chunk = 4;
+  }
+  *iters_out = c->h_cgst->k;
+  *breakdown_out = c->h_cgst->breakdown;
+  *chunk_hint = c->h_cgst->k + 1;
+
+  // back-substitution and candidate point
+  if (nc > 0) LAUNCH(c, LBA_K_MISC, k_make_table, cdiv(nc, 128), 128, nc, c->Gm.p, c->cams.p, c->cgx.p, c->tab.p);
+  if (c->ngroups > 0) LAUNCH(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->ngroups, kTile, la);
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 4, c->bs_partial.p, &c->scal.p->rjd, 1.0);
+  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, nc, c->cams.p, c->cgx.p, c->cams_new.p, &c->scal.p->dc2, &c->scal.p->x2_cams);
+  return LBA_OK;
+}
+
+static int fetch_scalars(lba_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_scal, c->scal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_gbits, c->gbits.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(c->h_clamped, c->clamped.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->launch_err) return LBA_ERR_CUDA;
+  return LBA_OK;
+}
+
+static double gnorm_host(lba_ctx* c) {
+  double g;
+  memcpy(&g, c->h_gbits, 8);
+  return g;
+}
+
+static int export_residuals(lba_ctx* c, const double* r_dev, double* out) {
+  if (!out || c->m == 0) return LBA_OK;
+  if (c->sorted_input) {
+    CK(cudaMemcpyAsync(out, r_dev, (size_t)c->m * 8, cudaMemcpyDefault, c->stream));
+  } else {
+    // un-sort into the caller's observation order (w is free outside the PCG loop)
+    LAUNCH(c, LBA_K_MISC, k_scatter_to_caller_order, cdiv(c->m, 256), 256, c->m, c->orig_of.p, r_dev, c->w.p);
+    CK(cudaMemcpyAsync(out, c->w.p, (size_t)c->m * 8, cudaMemcpyDefault, c->stream));
+  }
+  return LBA_OK;
+}
+
+// ---- C ABI: evaluation ---------------------------------------------------------------------------
+extern "C" int lba_point_wise_indices(lba_ctx* ctx, int64_t* cam_pt, int64_t* pt_idx) {
+  if (!ctx || !ctx->have_problem) return fail(LBA_ERR_STATE, "lba_set_problem has not been called");
+  if (!cam_pt || !pt_idx) return fail(LBA_ERR_ARG, "NULL output");
+  CK(cudaSetDevice(ctx->device));
+  const int m = ctx->m;
+  if (m == 0) return LBA_OK;
+  DBuf<long long> tmp;
+  CKR(tmp.alloc((size_t)4 * m));
+  LAUNCH(ctx, LBA_K_MISC, k_point_wise_indices, cdiv(m, 256), 256, m, ctx->sorted_input ? nullptr : ctx->orig_of.p,
+         ctx->obs_cam.p, ctx->obs_line.p, tmp.p, tmp.p + (size_t)2 * m);
+  CK(cudaMemcpyAsync(cam_pt, tmp.p, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
+  CK(cudaMemcpyAsync(pt_idx, tmp.p + (size_t)2 * m, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, double* proj) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (!proj) return fail(LBA_ERR_ARG, "NULL output");
+  CKR(load_state(ctx, cams, pts));
+  const int m = ctx->m;
+  if (m == 0) return LBA_OK;
+  DBuf<double> tmp;
+  CKR(tmp.alloc((size_t)6 * m));
+  EvalArgs a = eval_args(ctx, ctx->recs.p, ctx->pts.p, ctx->r.p);
+  a.proj = tmp.p;
+  LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(m, 256), 256, a);
+  CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+extern "C" int lba_residuals(lba_ctx* ctx, const double* cams, const double* pts, double* residuals, double* cost) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  CKR(load_state(ctx, cams, pts));
+  CKR(run_residual(ctx, ctx->recs.p, ctx->pts.p, ctx->r.p));
+  CKR(allreduce_sum(ctx, &ctx->scal.p->cost, 1));
+  CKR(export_residuals(ctx, ctx->r.p, residuals));
+  CKR(fetch_scalars(ctx));
+  if (cost) *cost = ctx->h_scal->cost;
+  return LBA_OK;
+}
+
+extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const double* pts, double* residuals,
+                                      double* jcam, double* jline) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  CKR(load_state(ctx, cams, pts));
+  CKR(run_jacobian(ctx));
+  CKR(export_residuals(ctx, ctx->r.p, residuals));
+  const int m = ctx->m;
+  if (m > 0 && (jcam || jline)) {
+    if (!jcam || !jline) return fail(LBA_ERR_ARG, "jcam and jline must both be given or both be NULL");
+    DBuf<double> tmp;
+    CKR(tmp.alloc((size_t)12 * m));
+    LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(m, 256), 256, m, ctx->sorted_input ? nullptr : ctx->orig_of.p,
+           ctx->cam_pos.p, ctx->jl.p, ctx->jc.p, tmp.p, tmp.p + (size_t)6 * m);
+    CK(cudaMemcpyAsync(jcam, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(jline, tmp.p + (size_t)6 * m, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double* V, double* gl) {
+  if (!ctx || !ctx->have_eval) return fail(LBA_ERR_STATE, "no resident evaluation: call lba_residuals_jacobian first");
+  CK(cudaSetDevice(ctx->device));
+  CKR(run_blocks(ctx, true));
+  if (U && ctx->nc) CK(cudaMemcpyAsync(U, ctx->U.p, (size_t)ctx->nc * 21 * 8, cudaMemcpyDefault, ctx->stream));
+  if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, ctx->gc.p, (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
+  if (V && ctx->nl) CK(cudaMemcpyAsync(V, ctx->V.p, (size_t)ctx->nl * 21 * 8, cudaMemcpyDefault, ctx->stream));
+  if (gl && ctx->nl) CK(cudaMemcpyAsync(gl, ctx->gl.p, (size_t)ctx->nl * 6 * 8, cudaMemcpyDefault, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+extern "C" int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int32_t pcg_max_iter, double* dcam,
+                               double* dpts, int32_t* pcg_iters) {
+  if (!ctx || !ctx->have_eval) return fail(LBA_ERR_STATE, "no resident evaluation: call lba_residuals_jacobian first");
+  if (!(lambda > 0.0)) return fail(LBA_ERR_ARG, "lambda must be positive");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_blocks) CKR(run_blocks(ctx, true));
+  int hint = 8, iters = 0, brk = 0;
+  CKR(run_solve(ctx, lambda, pcg_tol, pcg_max_iter, &hint, &iters, &brk));
+  if (pcg_iters) *pcg_iters = iters;
+  if (dcam && ctx->nc) CK(cudaMemcpyAsync(dcam, ctx->cgx.p, (size_t)ctx->nc * 48, cudaMemcpyDefault, ctx->stream));
+  if (dpts && ctx->nl) {
+    // dl = pts_new - pts (pts_new = pts + dl was written by the back-substitution pass); y is free after the solve
+    LAUNCH(ctx, LBA_K_MISC, k_sub, cdiv((long long)ctx->nl * 6, 256), 256, (size_t)ctx->nl * 6, ctx->pts_new.p, ctx->pts.p, ctx->y.p);
+    CK(cudaMemcpyAsync(dpts, ctx->y.p, (size_t)ctx->nl * 48, cudaMemcpyDefault, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+// ---- C ABI: the LM loop ---------------------------------------------------------------------------
+extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, const lba_options* opts_in,
+                            lba_report* rep, double* residuals) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  lba_options o;
+  if (opts_in) o = *opts_in; else lba_default_options(&o);
+  if (o.max_iter < 0 || o.pcg_max_iter < 1 || !(o.lambda0 > 0.0)) return fail(LBA_ERR_ARG, "bad options");
+  const auto t0 = std::chrono::steady_clock::now();
+  lba_report local;
+  if (!rep) rep = &local;
+  memset(rep, 0, sizeof(*rep));
+  lba_ctx* c = ctx;
+  CKR(load_state(c, cams_api, pts_api));
+  c->have_scaling = false;
+  CK(cudaMemsetAsync(c->clamped.p, 0, 4, c->stream));
+  CKR(run_jacobian(c));
+  rep->n_jac = 1;
+  CKR(allreduce_sum(c, &c->scal.p->cost, 1));
+  CKR(run_blocks(c, true));
+  CKR(fetch_scalars(c));
+  double cost = c->h_scal->cost;
+  rep->cost_init = cost;
+  if (!std::isfinite(cost)) return fail(LBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+  double g_norm = gnorm_host(c);
+  double lam = o.lambda0, nu = 2.0;
+  int status = 0, it = 0, chunk_hint = 8;
+  if (o.verbose >= 2)
+    printf("   Iteration     Total nfev        Cost      Cost reduction    Step norm     Optimality   \n");
+  while (it < o.max_iter) {
+    if (g_norm < o.gtol) { status = 1; break; }
+    int q = 0, brk = 0;
+    CKR(run_solve(c, lam, o.pcg_tol, o.pcg_max_iter, &chunk_hint, &q, &brk));
+    rep->pcg_iters_total += q;
+    // trial evaluation at x + delta
+    if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_cam_prepare, cdiv(c->nc, 128), 128, c->nc, c->cams_new.p, c->recs_new.p, (double*)nullptr);
+    // keep the pre-step cost: run_residual overwrites scal.cost with the trial cost
+    CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
+    rep->n_res += 1;
+    CKR(allreduce_sum(c, &c->scal.p->cost, 5));  // cost, rjd, jd2, dl2, x2_lines are contiguous
+    CKR(fetch_scalars(c));
+    const Scalars s = *c->h_scal;
+    const double cost_new = s.cost;
+    const double pred = -s.rjd - 0.5 * s.jd2;
+    const double step_norm = std::sqrt(s.dc2 + s.dl2);
+    const double x_norm = std::sqrt(s.x2_cams + s.x2_lines);
+    const double actual = cost - cost_new;
+    const bool finite = std::isfinite(cost_new);
+    const double ratio = (finite && pred > 0.0) ? actual / pred : -1.0;
+    const bool accepted = finite && ratio > o.min_ratio;
+    const bool ftol_ok = finite && (actual < o.ftol * cost) && (ratio > 0.25);
+    const bool xtol_ok = step_norm < o.xtol * (o.xtol + x_norm);
+    if (it < LBA_TRACE_MAX) {
+      rep->trace_pcg[it] = q; rep->trace_accepted[it] = accepted; rep->trace_cost[it] = cost;
+      rep->trace_cost_new[it] = cost_new; rep->trace_lambda[it] = lam; rep->trace_pred[it] = pred;
+      rep->trace_step_norm[it] = step_norm; rep->trace_g_norm[it] = g_norm;
+      rep->trace_len = it + 1;
+    }
+    if (o.verbose >= 2)
+      printf("   %6d        %6d        %.4e      %9.2e       %9.2e      %9.2e    (lam %.1e pcg %d %s)\n", it,
+             rep->n_jac + rep->n_res, accepted ? cost_new : cost, accepted ? actual : 0.0, step_norm, g_norm, lam, q,
+             accepted ? "ok" : "rej");
+    ++it;
+    if (accepted) {
+      std::swap(c->cams.p, c->cams_new.p); std::swap(c->cams.n, c->cams_new.n);
+      std::swap(c->pts.p, c->pts_new.p); std::swap(c->pts.n, c->pts_new.n);
+      cost = cost_new;
+      if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_cam_prepare, cdiv(c->nc, 128), 128, c->nc, c->cams.p, c->recs.p, c->Gm.p);
+      CKR(run_jacobian(c));
+      rep->n_jac += 1;
+      CKR(run_blocks(c, true));
+      CKR(fetch_scalars(c));
+      g_norm = gnorm_host(c);
+      lam = lam * std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * ratio - 1.0, 3.0));
+      lam = std::min(std::max(lam, o.lambda_min), o.lambda_max);
+      nu = 2.0;
+    } else {
+      lam = std::min(lam * nu, o.lambda_max);
+      nu *= 2.0;
+    }
+    if (ftol_ok && xtol_ok) status = 4;
+    else if (ftol_ok) status = 2;
+    else if (xtol_ok) status = 3;
+    if (status) break;
+  }
+  rep->iterations = it;
+  rep->status = status;
+  rep->cost = cost;
+  rep->chol_clamped = *c->h_clamped;
+  CKR(store_state(c, cams_api, pts_api));
+  CKR(export_residuals(c, c->r.p, residuals));
+  CK(cudaStreamSynchronize(c->stream));
+  rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return c->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+// ---- microbenchmarks --------------------------------------------------------------------------------
+extern "C" int lba_measure_fp64_peak(lba_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return fail(LBA_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  const int blocks = ctx->n_sm * 8, threads = 256, iters = 20000;
+  DBuf<double> out;
+  CKR(out.alloc((size_t)blocks * threads));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ++ctx->launches;
+    k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(out.p, iters);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  *tflops = best;
+  return LBA_OK;
+}
+
+extern "C" int lba_measure_copy_bandwidth(lba_ctx* ctx, int64_t bytes, double* gbs) {
+  if (!ctx || !gbs || bytes < 1024) return fail(LBA_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n2 = (size_t)bytes / 16;
+  DBuf<double2> a, b;
+  CKR(a.alloc(n2)); CKR(b.alloc(n2));
+  CK(cudaMemsetAsync(a.p, 0, n2 * 16, ctx->stream));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ++ctx->launches;
+    k_stream_copy<<<ctx->n_sm * 16, 256, 0, ctx->stream>>>(n2, a.p, b.p);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    best = std::max(best, 2.0 * n2 * 16 / (ms * 1e-3) / 1e9);
+  }
+  *gbs = best;
+  return LBA_OK;
+}

@@ -1,0 +1,805 @@
+// Hand-written sm_100a kernels for the line bundle-adjustment hot path.
+//
+// Data layout in HBM (all fp64 / int32, structure-of-arrays over observations):
+//   line order  (observations sorted by 3D line, the reference's own order,
+//                seq_utils.py:188-195):  cst[9][m] = n, m0 = n x p0, m1 = n x p1;
+//                obs_cam[m], obs_line[m], cam_pos[m]; r[m]; jl[6][m]; w[m] ...
+//   camera order (stable counting sort of the same observations by camera):
+//                jc[6][m]; cam_perm[m] (camera-order slot -> line-order index);
+//                cam_ptr[Nc+1]
+//   per line:    pts[Nl][6] = [X0,X1]; V[Nl][21]; gl[Nl][6]; Vinv[Nl][21]; y[Nl][6]; Dl[Nl][6]
+//   per camera:  cams[Nc][6] = [w,c]; CamRec[Nc]; G[Nc][9]; U[Nc][21]; gc[Nc][6]; Dc[Nc][6];
+//                Minv[Nc][21]; CG vectors [Nc][6]; tab[Nc][6]
+//
+// Each residual is a scalar, so a Jacobian row is (jc_i in R^6, jl_i in R^6) and every
+// coupling block W_{c,l} = jc_i jl_i^T is rank one: only ONE scalar per observation
+// (s_i, w_i) ever crosses between the line-ordered and the camera-ordered halves of a
+// pass.  Line-side reductions are segmented sums over contiguous runs inside one CTA
+// tile ("group" = whole lines, <= 256 observations) staged in shared memory; camera-side
+// reductions run one CTA per camera over the camera-ordered copy with warp-shuffle
+// reductions.  No atomics on the data path: every sum has a fixed order, so results
+// are bit-reproducible run to run.
+#pragma once
+#include "lba_geometry.cuh"
+
+namespace lba {
+
+constexpr int kTile = 256;      // threads per line-order CTA == max observations per group
+constexpr int kCamThreads = 128;
+constexpr int kCgThreads = 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block sum; result valid in thread 0 (and broadcast through smem slot).
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/32 doubles */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = (l < THREADS / 32) ? red[l] : 0.0;
+    t = warp_sum(t);
+    if (l == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+__device__ __forceinline__ void load_camrec(const CamRec* __restrict__ recs, int cam, double w[3], double c[3],
+                                            double& A, double& B, double& C) {
+  const double* p = reinterpret_cast<const double*>(recs + cam);
+  const double2 v0 = ldg2(p), v1 = ldg2(p + 2), v2 = ldg2(p + 4), v3 = ldg2(p + 6), v4 = ldg2(p + 8);
+  w[0] = v0.x; w[1] = v0.y; w[2] = v1.x;
+  c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
+  A = v3.x; B = v3.y; C = v4.x;
+}
+
+__device__ __forceinline__ void load6(const double* __restrict__ p, double v[6]) {
+  const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+
+// ---------------------------------------------------------------------------------
+// setup kernels
+// ---------------------------------------------------------------------------------
+
+// AoS (m,3) n/p0/p1 in caller order -> SoA cst[9][m] in line order, with m_e = n x p_e
+// (np.cross at bundle_adjustment.py:126,133, hoisted out of the evaluation loop).
+__global__ void k_setup_constants(int m, const int* __restrict__ orig_of, const double* __restrict__ n,
+                                  const double* __restrict__ p0, const double* __restrict__ p1,
+                                  double* __restrict__ cst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t s = orig_of ? (size_t)orig_of[i] : (size_t)i;
+  const double nx = n[3 * s], ny = n[3 * s + 1], nz = n[3 * s + 2];
+  const double ax = p0[3 * s], ay = p0[3 * s + 1], az = p0[3 * s + 2];
+  const double bx = p1[3 * s], by = p1[3 * s + 1], bz = p1[3 * s + 2];
+  const size_t M = (size_t)m;
+  cst[0 * M + i] = nx; cst[1 * M + i] = ny; cst[2 * M + i] = nz;
+  cst[3 * M + i] = ny * az - nz * ay; cst[4 * M + i] = nz * ax - nx * az; cst[5 * M + i] = nx * ay - ny * ax;
+  cst[6 * M + i] = ny * bz - nz * by; cst[7 * M + i] = nz * bx - nx * bz; cst[8 * M + i] = nx * by - ny * bx;
+}
+
+// (Nc,6) interleaved [w0,c0,w1,c1,w2,c2] <-> internal [w,c]
+__global__ void k_cams_from_api(int nc, const double* __restrict__ api, double* __restrict__ cams) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * 6) return;
+  const int c = t / 6, k = t % 6;  // k = 2*axis + {0: w, 1: centre}
+  cams[c * 6 + (k & 1) * 3 + (k >> 1)] = api[t];
+}
+__global__ void k_cams_to_api(int nc, const double* __restrict__ cams, double* __restrict__ api) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * 6) return;
+  const int c = t / 6, k = t % 6;
+  api[t] = cams[c * 6 + (k & 1) * 3 + (k >> 1)];
+}
+
+__global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* __restrict__ recs,
+                              double* __restrict__ Gm) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  CamRec rec;
+  for (int k = 0; k < 3; ++k) { rec.w[k] = cams[c * 6 + k]; rec.c[k] = cams[c * 6 + 3 + k]; }
+  rodrigues_coeffs(rec.w, rec.A, rec.B, rec.C);
+  rec.pad = 0.0;
+  recs[c] = rec;
+  if (Gm) {
+    double G[9];
+    build_G(rec.w, rec.B, rec.C, G);
+    for (int k = 0; k < 9; ++k) Gm[c * 9 + k] = G[k];
+  }
+}
+
+// point_wise_input (:235-243) integer expansion, in the caller's observation order.
+__global__ void k_point_wise_indices(int m, const int* __restrict__ orig_of, const int* __restrict__ obs_cam,
+                                     const int* __restrict__ obs_line, long long* __restrict__ cam_pt,
+                                     long long* __restrict__ pt_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t o = orig_of ? (size_t)orig_of[i] : (size_t)i;
+  const long long c = obs_cam[i], l = obs_line[i];
+  cam_pt[2 * o] = c; cam_pt[2 * o + 1] = c;
+  pt_idx[2 * o] = 2 * l; pt_idx[2 * o + 1] = 2 * l + 1;
+}
+
+// ---------------------------------------------------------------------------------
+// K1/K2/K3 (line side): residuals, Jacobian rows, per-line blocks V_l, g_l
+// ---------------------------------------------------------------------------------
+struct EvalArgs {
+  int m;
+  const int* group_line;   // [ngroups+1] first line of each group
+  const int* line_ptr;     // [nl+1]
+  const int* obs_cam;
+  const int* obs_line;
+  const int* cam_pos;
+  const double* cst;       // [9][m]
+  const CamRec* recs;
+  const double* pts;       // [nl][6]
+  double* r;               // [m]
+  double* jl;              // [6][m] line order
+  double* jc;              // [6][m] camera order
+  double* V;               // [nl][21]
+  double* gl;              // [nl][6]
+  double* cost_partial;    // [ngroups]
+  double* proj;            // optional (2m,3) p_hat output in caller order (lba_project)
+  const int* orig_of;
+};
+
+__constant__ int c_sym_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ int c_sym_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+constexpr int kStagePad = kTile + 2;  // row stride of the smem staging rows (bank spread)
+
+template <bool WITH_JAC>
+__global__ void __launch_bounds__(kTile, WITH_JAC ? 2 : 3) k_eval(const EvalArgs a) {
+  __shared__ double red[kTile / 32];
+  __shared__ double stage[WITH_JAC ? 7 * kStagePad : 1];
+  const int g = blockIdx.x;
+  const int l0 = a.group_line[g], l1 = a.group_line[g + 1];
+  const int o0 = a.line_ptr[l0], o1 = a.line_ptr[l1];
+  const int i = o0 + threadIdx.x;
+  const bool active = i < o1;
+  const size_t M = (size_t)a.m;
+  double r = 0.0;
+  double jl[6] = {0, 0, 0, 0, 0, 0};
+  if (active) {
+    const int cam = a.obs_cam[i];
+    const int line = a.obs_line[i];
+    double n[3], m0[3], m1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      n[k] = __ldg(a.cst + (size_t)k * M + i);
+      m0[k] = __ldg(a.cst + (size_t)(3 + k) * M + i);
+      m1[k] = __ldg(a.cst + (size_t)(6 + k) * M + i);
+    }
+    double w[3], c[3], A, B, C;
+    load_camrec(a.recs, cam, w, c, A, B, C);
+    double X[6];
+    load6(a.pts + (size_t)line * 6, X);
+    double R[9];
+    build_R(w, A, B, R);
+    double tq[3] = {0, 0, 0};
+    const double e0 = endpoint_term<WITH_JAC>(R, c, X, n, m0, jl, tq);
+    const double e1 = endpoint_term<WITH_JAC>(R, c, X + 3, n, m1, jl + 3, tq);
+    r = e0 + e1;
+    a.r[i] = r;
+    if (WITH_JAC) {
+      double G[9];
+      build_G(w, B, C, G);
+      const int pos = a.cam_pos[i];
+      // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1)
+      a.jc[0 * M + pos] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
+      a.jc[1 * M + pos] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
+      a.jc[2 * M + pos] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
+      a.jc[3 * M + pos] = -(jl[0] + jl[3]);
+      a.jc[4 * M + pos] = -(jl[1] + jl[4]);
+      a.jc[5 * M + pos] = -(jl[2] + jl[5]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.jl[(size_t)k * M + i] = jl[k];
+    }
+  }
+  if (WITH_JAC) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) stage[k * kStagePad + threadIdx.x] = jl[k];
+    stage[6 * kStagePad + threadIdx.x] = r;
+  }
+  const double cs = block_sum<kTile>(r * r, red);  // contains the barrier that publishes `stage`
+  if (threadIdx.x == 0) a.cost_partial[g] = cs;
+  if (WITH_JAC) {
+    // segmented sums: one work item per (line of the group, block entry); fixed order.
+    const int nwork = (l1 - l0) * 27;
+    for (int wi = threadIdx.x; wi < nwork; wi += kTile) {
+      const int ll = wi / 27, e = wi - ll * 27;
+      const int line = l0 + ll;
+      const int s0 = a.line_ptr[line] - o0, s1 = a.line_ptr[line + 1] - o0;
+      double acc = 0.0;
+      if (e < 21) {
+        const double* ra = stage + c_sym_a[e] * kStagePad;
+        const double* rb = stage + c_sym_b[e] * kStagePad;
+        for (int s = s0; s < s1; ++s) acc += ra[s] * rb[s];
+        a.V[(size_t)line * 21 + e] = acc;
+      } else {
+        const double* ra = stage + (e - 21) * kStagePad;
+        const double* rr = stage + 6 * kStagePad;
+        for (int s = s0; s < s1; ++s) acc += ra[s] * rr[s];
+        a.gl[(size_t)line * 6 + (e - 21)] = acc;
+      }
+    }
+  }
+}
+
+// project(): p_hat rows 2i+e in the caller's observation order (API parity only; cold path)
+__global__ void k_project(const EvalArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.m) return;
+  const int cam = a.obs_cam[i], line = a.obs_line[i];
+  double w[3], c[3], A, B, C;
+  load_camrec(a.recs, cam, w, c, A, B, C);
+  double X[6];
+  load6(a.pts + (size_t)line * 6, X);
+  double R[9];
+  build_R(w, A, B, R);
+  const size_t o = a.orig_of ? (size_t)a.orig_of[i] : (size_t)i;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const double d0 = X[3 * e] - c[0], d1 = X[3 * e + 1] - c[1], d2 = X[3 * e + 2] - c[2];
+    const double x0 = R[0] * d0 + R[1] * d1 + R[2] * d2;
+    const double x1 = R[3] * d0 + R[4] * d1 + R[5] * d2;
+    const double x2 = R[6] * d0 + R[7] * d1 + R[8] * d2;
+    const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+    a.proj[(2 * o + e) * 3 + 0] = x0 * inv;
+    a.proj[(2 * o + e) * 3 + 1] = x1 * inv;
+    a.proj[(2 * o + e) * 3 + 2] = x2 * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K3 (camera side): per-camera sums  S_c = sum_j wa_j jc_j jc_j^T (21),  v_c = sum_j wb_j jc_j (6)
+// over the camera-ordered Jacobian copy.  wa == nullptr means weight 1.
+// One CTA per camera; 27 register accumulators per thread, warp-shuffle + smem reduce.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCamThreads) k_cam_accum(int m, const int* __restrict__ cam_ptr,
+                                                            const int* __restrict__ cam_perm,
+                                                            const double* __restrict__ jc,
+                                                            const double* __restrict__ wa,
+                                                            const double* __restrict__ wb,
+                                                            double* __restrict__ S, double* __restrict__ v) {
+  __shared__ double sm[kCamThreads / 32][27];
+  const int c = blockIdx.x;
+  const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
+  const size_t M = (size_t)m;
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+    const int i = cam_perm[j];
+    double x[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = __ldg(jc + (size_t)k * M + j);
+    const double a = wa ? __ldg(wa + i) : 1.0;
+    const double b = __ldg(wb + i);
+    int e = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      const double ax = a * x[p];
+#pragma unroll
+      for (int q = p; q < 6; ++q) acc[e++] += ax * x[q];
+    }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc[21 + p] += b * x[p];
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (l == 0) sm[w][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+    if (threadIdx.x < 21) S[(size_t)c * 21 + threadIdx.x] = s;
+    else v[(size_t)c * 6 + threadIdx.x - 21] = s;
+  }
+}
+
+// Marquardt scaling D = diag(J^T J), zeros -> 1, running max
+// (scipy compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at :319).
+__global__ void k_update_scaling(int nblocks, const double* __restrict__ S /*[n][21]*/, double* __restrict__ D,
+                                 int first) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblocks * 6) return;
+  const int b = t / 6, k = t % 6;
+  double d = S[(size_t)b * 21 + sym_idx(k, k)];
+  if (d == 0.0) d = 1.0;
+  D[t] = first ? d : fmax(D[t], d);
+}
+
+// ---------------------------------------------------------------------------------
+// K4: Schur elimination pieces
+// ---------------------------------------------------------------------------------
+// per line: Vinv = (V + lam Dl)^-1, y = Vinv gl
+__global__ void __launch_bounds__(128) k_line_factor(int nl, double lam, const double* __restrict__ V,
+                                                      const double* __restrict__ Dl, const double* __restrict__ gl,
+                                                      double* __restrict__ Vinv, double* __restrict__ y,
+                                                      int* __restrict__ clamped) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nl) return;
+  double S[21];
+#pragma unroll
+  for (int e = 0; e < 21; ++e) S[e] = V[(size_t)l * 21 + e];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * Dl[(size_t)l * 6 + k];
+  const int cl = spd6_inverse(S);
+  if (cl) atomicAdd(clamped, cl);
+  double g[6], yy[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g[k] = gl[(size_t)l * 6 + k];
+  sym6_matvec(S, g, yy);
+#pragma unroll
+  for (int e = 0; e < 21; ++e) Vinv[(size_t)l * 21 + e] = S[e];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) y[(size_t)l * 6 + k] = yy[k];
+}
+
+// per observation: wk[i] = 1 - jl_i^T Vinv jl_i (block-Jacobi weight), wr[i] = jl_i . y_l (Schur rhs weight)
+__global__ void __launch_bounds__(256) k_line_scalars(int m, const int* __restrict__ obs_line,
+                                                       const double* __restrict__ jl, const double* __restrict__ Vinv,
+                                                       const double* __restrict__ y, double* __restrict__ wk,
+                                                       double* __restrict__ wr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t M = (size_t)m;
+  const int l = obs_line[i];
+  double x[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[k] = __ldg(jl + (size_t)k * M + i);
+  const double* S = Vinv + (size_t)l * 21;
+  double q = 0.0;
+  int e = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    q += __ldg(S + e) * x[p] * x[p];
+    ++e;
+#pragma unroll
+    for (int s = p + 1; s < 6; ++s) { q += 2.0 * __ldg(S + e) * x[p] * x[s]; ++e; }
+  }
+  double d = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d += x[k] * __ldg(y + (size_t)l * 6 + k);
+  wk[i] = 1.0 - q;
+  wr[i] = d;
+}
+
+// per camera: Minv = (lam Dc + Mpart)^-1 (block-Jacobi), b = -gc + bpart (Schur rhs)
+__global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const double* __restrict__ Mpart,
+                                                     const double* __restrict__ Dc, const double* __restrict__ gc,
+                                                     const double* __restrict__ bpart, double* __restrict__ Minv,
+                                                     double* __restrict__ b, int* __restrict__ clamped) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double S[21];
+#pragma unroll
+  for (int e = 0; e < 21; ++e) S[e] = Mpart[(size_t)c * 21 + e];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * Dc[(size_t)c * 6 + k];
+  const int cl = spd6_inverse(S);
+  if (cl) atomicAdd(clamped, cl);
+#pragma unroll
+  for (int e = 0; e < 21; ++e) Minv[(size_t)c * 21 + e] = S[e];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b[(size_t)c * 6 + k] = bpart[(size_t)c * 6 + k] - gc[(size_t)c * 6 + k];
+}
+
+// ---------------------------------------------------------------------------------
+// K5: matrix-free Schur product and PCG
+// ---------------------------------------------------------------------------------
+struct CgState {
+  double rz, rz0, pq;
+  int k, done, breakdown, pad;
+};
+
+// per camera gather table for a camera-space vector v:  a = G v_w,  h = a x c + v_c, so that
+// jc_i . v_c = sum_e jl_e . (a x X_e - h)   (jc is never read in line order).
+__device__ __forceinline__ void make_tab_entry(const double* __restrict__ G, const double* __restrict__ cam,
+                                               const double v[6], double* __restrict__ tab) {
+  const double a0 = G[0] * v[0] + G[1] * v[1] + G[2] * v[2];
+  const double a1 = G[3] * v[0] + G[4] * v[1] + G[5] * v[2];
+  const double a2 = G[6] * v[0] + G[7] * v[1] + G[8] * v[2];
+  const double c0 = cam[3], c1 = cam[4], c2 = cam[5];
+  tab[0] = a0; tab[1] = a1; tab[2] = a2;
+  tab[3] = a1 * c2 - a2 * c1 + v[3];
+  tab[4] = a2 * c0 - a0 * c2 + v[4];
+  tab[5] = a0 * c1 - a1 * c0 + v[5];
+}
+
+__global__ void k_make_table(int nc, const double* __restrict__ Gm, const double* __restrict__ cams,
+                             const double* __restrict__ v, double* __restrict__ tab) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double vv[6];
+  for (int k = 0; k < 6; ++k) vv[k] = v[(size_t)c * 6 + k];
+  make_tab_entry(Gm + (size_t)c * 9, cams + (size_t)c * 6, vv, tab + (size_t)c * 6);
+}
+
+struct LinePassArgs {
+  int m;
+  const int* group_line;
+  const int* line_ptr;
+  const int* obs_cam;
+  const int* obs_line;
+  const double* jl;      // [6][m]
+  const double* pts;     // [nl][6]
+  const double* tab;     // [nc][6]
+  const double* Vinv;    // [nl][21]
+  double* w;             // MATVEC out [m]
+  // BACKSUB only
+  const double* gl;      // [nl][6]
+  const double* r;       // [m]
+  double* pts_new;       // [nl][6]
+  double* partial;       // [ngroups][4]: r.jd, jd.jd, |dl|^2, |pts|^2
+  const CgState* st;     // MATVEC: early exit when done
+};
+
+enum { kModeMatvec = 0, kModeBacksub = 1 };
+
+// Line-ordered half of S*p (MATVEC) and the back-substitution (BACKSUB).
+//   s_i = jc_i . v_{c_i} (via the table),  t_l = sum_{i in l} jl_i s_i,
+//   MATVEC:  u_l = Vinv_l t_l,           w_i = s_i - jl_i . u_l
+//   BACKSUB: dl  = -Vinv_l (gl_l + t_l), (J delta)_i = s_i + jl_i . dl
+template <int MODE>
+__global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
+  __shared__ double stage[6 * kStagePad];
+  __shared__ double ul[kTile * 6];
+  __shared__ double red[kTile / 32];
+  if (MODE == kModeMatvec && a.st->done) return;
+  const int g = blockIdx.x;
+  const int l0 = a.group_line[g], l1 = a.group_line[g + 1];
+  const int o0 = a.line_ptr[l0], o1 = a.line_ptr[l1];
+  const int i = o0 + threadIdx.x;
+  const bool active = i < o1;
+  const size_t M = (size_t)a.m;
+  double jl[6] = {0, 0, 0, 0, 0, 0};
+  double s = 0.0;
+  int ll = 0;
+  if (active) {
+    const int cam = a.obs_cam[i];
+    const int line = a.obs_line[i];
+    ll = line - l0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) jl[k] = __ldg(a.jl + (size_t)k * M + i);
+    double t[6], X[6];
+    load6(a.tab + (size_t)cam * 6, t);
+    load6(a.pts + (size_t)line * 6, X);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double* Xe = X + 3 * e;
+      const double v0 = t[1] * Xe[2] - t[2] * Xe[1] - t[3];
+      const double v1 = t[2] * Xe[0] - t[0] * Xe[2] - t[4];
+      const double v2 = t[0] * Xe[1] - t[1] * Xe[0] - t[5];
+      s += jl[3 * e] * v0 + jl[3 * e + 1] * v1 + jl[3 * e + 2] * v2;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) stage[k * kStagePad + threadIdx.x] = jl[k] * s;
+  __syncthreads();
+  // 8 lanes per line: lane b < 6 sums component b, then the 6x6 product by shuffles.
+  {
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const int nlg = l1 - l0;
+    const int rounds = (nlg + (kTile / 8) - 1) / (kTile / 8);
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int lx = rd * (kTile / 8) + grp;
+      const bool have = lx < nlg;
+      const int line = l0 + (have ? lx : 0);
+      double tb = 0.0;
+      if (have && sub < 6) {
+        const int s0 = a.line_ptr[line] - o0, s1 = a.line_ptr[line + 1] - o0;
+        const double* row = stage + sub * kStagePad;
+        for (int q = s0; q < s1; ++q) tb += row[q];
+        if (MODE == kModeBacksub) tb += a.gl[(size_t)line * 6 + sub];
+      }
+      double u = 0.0;
+      const double* S = a.Vinv + (size_t)line * 21;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const double tv = __shfl_sync(0xffffffffu, tb, (threadIdx.x & 24) + b);
+        if (have && sub < 6) u += __ldg(S + sym_idx(sub < b ? sub : b, sub < b ? b : sub)) * tv;
+      }
+      if (have && sub < 6) {
+        if (MODE == kModeBacksub) {
+          u = -u;
+          const double x = a.pts[(size_t)line * 6 + sub];
+          a.pts_new[(size_t)line * 6 + sub] = x + u;
+        }
+        ul[lx * 6 + sub] = u;
+      }
+    }
+  }
+  __syncthreads();
+  double d = 0.0;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d += jl[k] * ul[ll * 6 + k];
+  }
+  if (MODE == kModeMatvec) {
+    if (active) a.w[i] = s - d;
+  } else {
+    const double jd = active ? s + d : 0.0;
+    const double rr = active ? __ldg(a.r + i) : 0.0;
+    // per-group partial sums for the model reduction and the step / parameter norms
+    double dl2 = 0.0, x2 = 0.0;
+    const int nlg = l1 - l0;
+    for (int q = threadIdx.x; q < nlg * 6; q += kTile) {
+      const double u = ul[q];
+      const double x = a.pts[(size_t)l0 * 6 + q];
+      dl2 += u * u;
+      x2 += x * x;
+    }
+    const double s0 = block_sum<kTile>(rr * jd, red);
+    const double s1 = block_sum<kTile>(jd * jd, red);
+    const double s2 = block_sum<kTile>(dl2, red);
+    const double s3 = block_sum<kTile>(x2, red);
+    if (threadIdx.x == 0) {
+      a.partial[(size_t)g * 4 + 0] = s0;
+      a.partial[(size_t)g * 4 + 1] = s1;
+      a.partial[(size_t)g * 4 + 2] = s2;
+      a.partial[(size_t)g * 4 + 3] = s3;
+    }
+  }
+}
+
+// Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}
+__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int m, const int* __restrict__ cam_ptr,
+                                                          const int* __restrict__ cam_perm,
+                                                          const double* __restrict__ jc, const double* __restrict__ w,
+                                                          double* __restrict__ qpart, const CgState* __restrict__ st) {
+  __shared__ double sm[kCamThreads / 32][6];
+  if (st->done) return;
+  const int c = blockIdx.x;
+  const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
+  const size_t M = (size_t)m;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+    const double wi = __ldg(w + cam_perm[j]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] += wi * __ldg(jc + (size_t)k * M + j);
+  }
+  const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (l == 0) sm[wp][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+    qpart[(size_t)c * 6 + threadIdx.x] = s;
+  }
+}
+
+struct CgArgs {
+  int nc;
+  double lam, tol2;
+  int max_iter;
+  const double* Dc;     // [nc][6]
+  const double* Minv;   // [nc][21]
+  const double* Gm;     // [nc][9]
+  const double* cams;   // [nc][6]
+  const double* b;      // [nc][6]
+  const double* qpart;  // [nc][6] (all-reduced partial S p without the damping term)
+  double* x; double* r; double* z; double* p; double* tab;
+  CgState* st;
+};
+
+// x = 0, r = b, z = Minv r, p = z, rz0 = r.z ; table(p).   One CTA.
+__global__ void __launch_bounds__(kCgThreads) k_cg_init(const CgArgs a) {
+  __shared__ double red[kCgThreads / 32];
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
+    double rr[6], zz[6], S[21];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rr[k] = a.b[(size_t)c * 6 + k];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) S[e] = a.Minv[(size_t)c * 21 + e];
+    sym6_matvec(S, rr, zz);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      a.x[(size_t)c * 6 + k] = 0.0;
+      a.r[(size_t)c * 6 + k] = rr[k];
+      a.z[(size_t)c * 6 + k] = zz[k];
+      a.p[(size_t)c * 6 + k] = zz[k];
+      acc += rr[k] * zz[k];
+    }
+    make_tab_entry(a.Gm + (size_t)c * 9, a.cams + (size_t)c * 6, zz, a.tab + (size_t)c * 6);
+  }
+  const double rz = block_sum<kCgThreads>(acc, red);
+  if (threadIdx.x == 0) {
+    a.st->rz = rz; a.st->rz0 = rz; a.st->pq = 0.0; a.st->k = 0;
+    a.st->breakdown = 0;
+    a.st->done = !(rz > 0.0);
+  }
+}
+
+// One CG step after q = S p is available (q = qpart + lam Dc p).   One CTA.
+__global__ void __launch_bounds__(kCgThreads) k_cg_update(const CgArgs a) {
+  __shared__ double red[kCgThreads / 32];
+  if (a.st->done) return;
+  const double rz = a.st->rz;
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const size_t t = (size_t)c * 6 + k;
+      const double pp = a.p[t];
+      const double q = a.qpart[t] + a.lam * a.Dc[t] * pp;
+      a.z[t] = q;  // z is free until the preconditioner is applied below; reuse it to keep q
+      acc += pp * q;
+    }
+  }
+  const double pq = block_sum<kCgThreads>(acc, red);
+  const bool ok = pq > 0.0;
+  const double alpha = ok ? rz / pq : 0.0;
+  acc = 0.0;
+  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
+    double rr[6], zz[6], S[21];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const size_t t = (size_t)c * 6 + k;
+      a.x[t] += alpha * a.p[t];
+      rr[k] = a.r[t] - alpha * a.z[t];
+      a.r[t] = rr[k];
+    }
+#pragma unroll
+    for (int e = 0; e < 21; ++e) S[e] = a.Minv[(size_t)c * 21 + e];
+    sym6_matvec(S, rr, zz);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      a.z[(size_t)c * 6 + k] = zz[k];
+      acc += rr[k] * zz[k];
+    }
+  }
+  const double rz_new = block_sum<kCgThreads>(acc, red);
+  const int k_new = a.st->k + 1;
+  const bool stop = !ok || rz_new <= a.tol2 * a.st->rz0 || k_new >= a.max_iter;
+  __syncthreads();
+  if (!stop) {
+    const double beta = rz_new / rz;
+    for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
+      double pn[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const size_t t = (size_t)c * 6 + k;
+        pn[k] = a.z[t] + beta * a.p[t];
+        a.p[t] = pn[k];
+      }
+      make_tab_entry(a.Gm + (size_t)c * 9, a.cams + (size_t)c * 6, pn, a.tab + (size_t)c * 6);
+    }
+  }
+  if (threadIdx.x == 0) {
+    a.st->pq = pq;
+    a.st->k = k_new;
+    a.st->rz = rz_new;
+    if (!ok) a.st->breakdown = 1;
+    if (stop) a.st->done = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------
+struct Scalars {            // device-resident LM scalars, copied to the host once per iteration
+  double cost;              // 0.5 sum r^2 of the last evaluation
+  double rjd, jd2;          // sum r (J delta), sum (J delta)^2
+  double dl2, x2_lines;     // |delta_lines|^2, |pts|^2
+  double dc2, x2_cams;      // |delta_cams|^2, |cams|^2
+  double gnorm;             // inf-norm of the gradient
+  int pcg_iters, pcg_breakdown;
+  int clamped, pad;
+};
+
+// out[col] = sum_g partial[g][col] (fixed order); one CTA.
+__global__ void __launch_bounds__(1024) k_reduce_partials(int n, int ncols, const double* __restrict__ partial,
+                                                           double* __restrict__ out, double scale) {
+  __shared__ double red[32];
+  for (int col = 0; col < ncols; ++col) {
+    double acc = 0.0;
+    for (int g = threadIdx.x; g < n; g += 1024) acc += partial[(size_t)g * ncols + col];
+    const double s = block_sum<1024>(acc, red);
+    if (threadIdx.x == 0) out[col] = s * scale;
+    __syncthreads();
+  }
+}
+
+// cams_new = cams + dc ; norms.  One CTA.
+__global__ void __launch_bounds__(1024) k_cam_step(int nc, const double* __restrict__ cams,
+                                                    const double* __restrict__ dc, double* __restrict__ cams_new,
+                                                    double* __restrict__ out_dc2, double* __restrict__ out_x2) {
+  __shared__ double red[32];
+  double d2 = 0.0, x2 = 0.0;
+  for (int t = threadIdx.x; t < nc * 6; t += 1024) {
+    const double x = cams[t], d = dc[t];
+    cams_new[t] = x + d;
+    d2 += d * d;
+    x2 += x * x;
+  }
+  const double s0 = block_sum<1024>(d2, red);
+  const double s1 = block_sum<1024>(x2, red);
+  if (threadIdx.x == 0) { *out_dc2 = s0; *out_x2 = s1; }
+}
+
+// inf-norm via order-preserving integer max on non-negative doubles (exact, order independent)
+__global__ void k_absmax(size_t n, const double* __restrict__ v, unsigned long long* __restrict__ out) {
+  double mx = 0.0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const double a = fabs(v[t]);
+    mx = (a > mx || a != a) ? a : mx;  // NaN propagates
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (other > mx || other != other) ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+
+__global__ void k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = a[t] - b[t];
+}
+
+__global__ void k_scatter_to_caller_order(int m, const int* __restrict__ orig_of, const double* __restrict__ src,
+                                          double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  dst[orig_of[i]] = src[i];
+}
+
+// Jacobian rows in API layout: jcam (m,6) interleaved [w0,c0,w1,c1,w2,c2], jline (m,6); caller order.
+__global__ void k_export_jacobian(int m, const int* __restrict__ orig_of, const int* __restrict__ cam_pos,
+                                  const double* __restrict__ jl, const double* __restrict__ jc,
+                                  double* __restrict__ jcam, double* __restrict__ jline) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const size_t M = (size_t)m;
+  const size_t o = orig_of ? (size_t)orig_of[i] : (size_t)i;
+  const int pos = cam_pos[i];
+  for (int k = 0; k < 3; ++k) {
+    jcam[o * 6 + 2 * k] = jc[(size_t)k * M + pos];
+    jcam[o * 6 + 2 * k + 1] = jc[(size_t)(3 + k) * M + pos];
+  }
+  for (int k = 0; k < 6; ++k) jline[o * 6 + k] = jl[(size_t)k * M + i];
+}
+
+// ---------------------------------------------------------------------------------
+// microbenchmarks for the roofline denominators
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) k_stream_copy(size_t n2, const double2* __restrict__ src,
+                                                      double2* __restrict__ dst) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x)
+    dst[t] = src[t];
+}
+
+}  // namespace lba

@@ -1,0 +1,233 @@
+"""Array-native host API over liblba.so: one ``LineBA`` object per GPU.
+
+This is the fast path below the drop-in ``run_bundle_adjustment`` (which only has to
+flatten the reference's Python objects first).  Arrays use the reference's layouts
+(see include/lba.h); numpy arrays and torch tensors (CPU or CUDA) are accepted
+wherever a pointer is expected, so device-resident data is never copied to the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import LbaOptions, LbaReport, check
+
+STATUS_TEXT = {
+    0: "The maximum number of iterations is exceeded.",
+    1: "`gtol` termination condition is satisfied.",
+    2: "`ftol` termination condition is satisfied.",
+    3: "`xtol` termination condition is satisfied.",
+    4: "Both `ftol` and `xtol` termination conditions are satisfied.",
+}
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _as_ptr(x, np_dtype, torch_dtype_name, shape_size=None):
+    """Return (address, keepalive) for a C-contiguous numpy array or torch tensor."""
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        import torch
+        want = getattr(torch, torch_dtype_name)
+        t = x if (x.dtype == want and x.is_contiguous()) else x.to(want).contiguous()
+        if shape_size is not None and t.numel() != shape_size:
+            raise ValueError(f"expected {shape_size} elements, got {t.numel()}")
+        return t.data_ptr(), t
+    a = np.ascontiguousarray(x, dtype=np_dtype)
+    if shape_size is not None and a.size != shape_size:
+        raise ValueError(f"expected {shape_size} elements, got {a.size}")
+    return a.ctypes.data, a
+
+
+@dataclass
+class LMResult:
+    camera_params: np.ndarray
+    points_3d: np.ndarray
+    residuals: np.ndarray | None
+    iterations: int
+    status: int
+    message: str
+    n_jac: int
+    n_res: int
+    pcg_iters_total: int
+    chol_clamped: int
+    cost_init: float
+    cost: float
+    seconds: float
+    trace: list = field(default_factory=list)
+
+
+class LineBA:
+    """One bundle-adjustment context bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.lba_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.m = self.n_cameras = self.n_lines = 0
+        self.rank, self.world = 0, 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- problem ------------------------------------------------------------------
+    def set_problem(self, n_cameras, n_lines, camera_indices, lines_indices, n, p0, p1):
+        m = int(camera_indices.shape[0])
+        pc, k0 = _as_ptr(camera_indices, np.int64, "int64", m)
+        pl, k1 = _as_ptr(lines_indices, np.int64, "int64", m)
+        pn, k2 = _as_ptr(n, np.float64, "float64", 3 * m)
+        pa, k3 = _as_ptr(p0, np.float64, "float64", 3 * m)
+        pb, k4 = _as_ptr(p1, np.float64, "float64", 3 * m)
+        check(self._lib.lba_set_problem(self._h, m, int(n_cameras), int(n_lines), pc, pl, pn, pa, pb))
+        self.m, self.n_cameras, self.n_lines = m, int(n_cameras), int(n_lines)
+        return self
+
+    def _params(self, camera_params, points_3d):
+        pc, kc = _as_ptr(camera_params, np.float64, "float64", 6 * self.n_cameras)
+        pp, kp = _as_ptr(points_3d, np.float64, "float64", 6 * self.n_lines)
+        return pc, pp, (kc, kp)
+
+    def point_wise_indices(self):
+        cam_pt = np.empty(2 * self.m, dtype=np.int64)
+        pt_idx = np.empty(2 * self.m, dtype=np.int64)
+        check(self._lib.lba_point_wise_indices(self._h, cam_pt.ctypes.data, pt_idx.ctypes.data))
+        return cam_pt, pt_idx
+
+    # -- evaluation -----------------------------------------------------------------
+    def project(self, camera_params, points_3d):
+        pc, pp, keep = self._params(camera_params, points_3d)
+        out = np.empty((2 * self.m, 3), dtype=np.float64)
+        check(self._lib.lba_project(self._h, pc, pp, out.ctypes.data))
+        return out
+
+    def residuals(self, camera_params, points_3d, want_residuals=True):
+        pc, pp, keep = self._params(camera_params, points_3d)
+        r = np.empty(self.m, dtype=np.float64) if want_residuals else None
+        cost = C.c_double()
+        check(self._lib.lba_residuals(self._h, pc, pp, r.ctypes.data if r is not None else None, C.byref(cost)))
+        return r, cost.value
+
+    def residuals_jacobian(self, camera_params, points_3d, want_jacobian=True):
+        pc, pp, keep = self._params(camera_params, points_3d)
+        r = np.empty(self.m, dtype=np.float64)
+        jc = np.empty((self.m, 6), dtype=np.float64) if want_jacobian else None
+        jl = np.empty((self.m, 6), dtype=np.float64) if want_jacobian else None
+        check(self._lib.lba_residuals_jacobian(self._h, pc, pp, r.ctypes.data,
+                                               jc.ctypes.data if want_jacobian else None,
+                                               jl.ctypes.data if want_jacobian else None))
+        return r, jc, jl
+
+    def normal_equations(self):
+        U = np.empty((self.n_cameras, 21)); gc = np.empty((self.n_cameras, 6))
+        V = np.empty((self.n_lines, 21)); gl = np.empty((self.n_lines, 6))
+        check(self._lib.lba_normal_equations(self._h, U.ctypes.data, gc.ctypes.data, V.ctypes.data, gl.ctypes.data))
+        return U, gc, V, gl
+
+    def schur_solve(self, lam, pcg_tol=1e-2, pcg_max_iter=200):
+        dc = np.empty((self.n_cameras, 6)); dl = np.empty((self.n_lines, 6))
+        it = C.c_int32()
+        check(self._lib.lba_schur_solve(self._h, float(lam), float(pcg_tol), int(pcg_max_iter),
+                                        dc.ctypes.data, dl.ctypes.data, C.byref(it)))
+        return dc, dl, it.value
+
+    # -- LM -----------------------------------------------------------------------------
+    def default_options(self, **kw) -> LbaOptions:
+        o = LbaOptions()
+        self._lib.lba_default_options(C.byref(o))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown option {k!r}")
+            setattr(o, k, v)
+        return o
+
+    def lm_solve(self, camera_params, points_3d, want_residuals=True, out=None, **options) -> LMResult:
+        """Optimise cameras and 3D lines.  ``camera_params`` (Nc,6) interleaved and
+        ``points_3d`` (2Nl,3) are not modified; optimised copies are returned (host numpy),
+        unless ``out=(cams_buf, pts_buf)`` gives buffers (numpy or torch, any device) that
+        are read as the initial guess and overwritten in place."""
+        o = self.default_options(**options)
+        if out is None:
+            cams = np.array(camera_params, dtype=np.float64, order="C", copy=True).reshape(self.n_cameras, 6)
+            pts = np.array(points_3d, dtype=np.float64, order="C", copy=True).reshape(2 * self.n_lines, 3)
+            pc, pp = cams.ctypes.data, pts.ctypes.data
+        else:
+            cams, pts = out
+            pc, _k0 = _as_ptr(cams, np.float64, "float64", 6 * self.n_cameras)
+            pp, _k1 = _as_ptr(pts, np.float64, "float64", 6 * self.n_lines)
+            if (_k0 is not cams) or (_k1 is not pts):
+                raise ValueError("out buffers must be contiguous float64")
+        r = np.empty(self.m, dtype=np.float64) if want_residuals else None
+        rep = LbaReport()
+        check(self._lib.lba_lm_solve(self._h, pc, pp, C.byref(o), C.byref(rep),
+                                     r.ctypes.data if r is not None else None))
+        n = rep.trace_len
+        trace = [dict(it=i, cost=rep.trace_cost[i], cost_new=rep.trace_cost_new[i], lam=rep.trace_lambda[i],
+                      pcg=rep.trace_pcg[i], pred=rep.trace_pred[i], accepted=bool(rep.trace_accepted[i]),
+                      step_norm=rep.trace_step_norm[i], g_norm=rep.trace_g_norm[i]) for i in range(n)]
+        return LMResult(cams, pts, r, rep.iterations, rep.status, STATUS_TEXT.get(rep.status, "?"), rep.n_jac,
+                        rep.n_res, rep.pcg_iters_total, rep.chol_clamped, rep.cost_init, rep.cost, rep.seconds, trace)
+
+    # -- multi-GPU --------------------------------------------------------------------------
+    def init_comm(self, rank=None, world=None, group=None):
+        """Attach an NCCL communicator; the unique id travels over torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        if world == 1:
+            return self
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(self._lib.lba_comm_unique_id(buf))
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(self.device)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
+        check(self._lib.lba_comm_init(self._h, buf2, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+        return self
+
+    # -- instrumentation ------------------------------------------------------------------
+    def synchronize(self):
+        check(self._lib.lba_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.lba_launch_count(self._h))
+
+    def set_profiling(self, enable: bool):
+        check(self._lib.lba_set_profiling(self._h, 1 if enable else 0))
+
+    def get_profile(self):
+        ms = (C.c_double * _lib.LBA_K_COUNT)()
+        n = (C.c_int64 * _lib.LBA_K_COUNT)()
+        check(self._lib.lba_get_profile(self._h, ms, n))
+        return {self._lib.lba_kernel_class_name(k).decode(): dict(ms=ms[k], launches=int(n[k]))
+                for k in range(_lib.LBA_K_COUNT)}
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        check(self._lib.lba_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_copy_bandwidth(self, nbytes=1 << 30) -> float:
+        v = C.c_double()
+        check(self._lib.lba_measure_copy_bandwidth(self._h, int(nbytes), C.byref(v)))
+        return v.value

@@ -1,0 +1,280 @@
+#!/usr/bin/env python3
+"""Benchmark of the line bundle-adjustment hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # CPU port of the reference's scipy path
+    torchrun --nproc-per-node N bench.py --gpus N ...         # observations sharded over N GPUs
+
+A "step" is one Levenberg-Marquardt iteration (solve of the damped normal equations by Schur
+elimination + PCG, trial evaluation, accept/reject, and -- when accepted -- the next fused
+residual+Jacobian pass) on BASELINE.json's synthetic scene.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lm_iterations_per_sec"
+UNIT = "LM iterations/s"
+
+# BASELINE.json configs: [3] = 1k cameras / 200k lines / 2M observations (1 GPU),
+# [4] = 10k cameras / 2M lines / 20M observations (sharded).  Per-GPU work is fixed as N grows
+# ("weak" scaling): N GPUs solve a scene with N x the lines and observations of config [3].
+PER_GPU_LINES = 200_000
+OBS_PER_LINE = 10
+N_CAMERAS = 1000
+
+# algorithmic HBM bytes per observation (fp64, int32 indices)
+BYTES_PER_OBS = {
+    "residual": 72 + 8 + 8 + 4.8,                 # constants, indices, r out, line endpoints (48 B / 10 obs)
+    "jacobian": 72 + 12 + 8 + 96 + 4.8 + 21.6,    # + cam_pos, J row out (12 doubles), V_l,g_l out (27*8/10)
+    "pcg_line": 48 + 8 + 4.8 + 16.8 + 8,          # jl, indices, endpoints, Vinv (21*8/10), w out
+    "pcg_cam": 48 + 4 + 8,                        # jc, cam_perm, w gather
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_scene(n_gpus, scale=1.0, seed=0):
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    n_lines = int(PER_GPU_LINES * n_gpus * scale)
+    n_cams = max(OBS_PER_LINE, int(N_CAMERAS * n_gpus * scale))
+    return make_synthetic_scene(n_cams, n_lines, OBS_PER_LINE, seed=seed, variant="A")
+
+
+def cpu_reference_run(steps, warmup, full_obs, mode="analytic"):
+    """The reference's scipy path (bundle_adjustment.py:319) with `fun` vectorised, on a bounded
+    1/10-scale sample of the workload; iterations/s are scaled to the full observation count."""
+    from oracle import line_ba_oracle as orc
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    s = make_synthetic_scene(100, 20_000, OBS_PER_LINE, seed=0, variant="A")
+    orc.scipy_reference_port(*s.arrays(), mode=mode, max_nfev=max(1, min(warmup, 2)))   # warm numpy/scipy paths
+    t0 = time.perf_counter()
+    out = orc.scipy_reference_port(*s.arrays(), mode=mode, max_nfev=max(steps, 2))
+    dt = time.perf_counter() - t0
+    iters = max(1, out[3].nfev - 1)
+    v = iters / dt * (s.n_obs / full_obs)
+    cores = 1
+    return dict(value=v, unit=UNIT, cores=cores, kind="port",
+                sample=f"scipy least_squares(trf, lsmr, x_scale='jac', {mode} Jacobian) with numpy-vectorised fun on "
+                       f"{s.n_cameras} cams/{s.n_lines} lines/{s.n_obs} obs: {iters} TRF iterations in {dt:.1f} s, "
+                       f"scaled by {s.n_obs}/{full_obs} observations; host has {os.cpu_count()} cores, path is single-threaded"), dt / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the scene")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-mode", default="analytic", choices=["analytic", "as_shipped"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    full_obs = int(PER_GPU_LINES * args.gpus * args.scale) * OBS_PER_LINE
+    n_cams_total = max(OBS_PER_LINE, int(N_CAMERAS * args.gpus * args.scale))
+    workload = (f"synthetic line-SfM scene, {n_cams_total} cameras / {full_obs // OBS_PER_LINE} 3D lines / {full_obs} "
+                f"line observations (10 views per line, uniform random visibility), seed 0")
+    config = {"workload": workload, "obs_per_gpu": full_obs // max(args.gpus, 1), "parallelism": f"obs-shard x{args.gpus}",
+              "l2": "working set per LM iteration (~0.5 GB/GPU) exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, sec_per_it = cpu_reference_run(args.steps, warmup, full_obs, mode=args.ref_mode)
+        line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from amuya_sfm_lines_beta_b200 import LineBA
+    from amuya_sfm_lines_beta_b200.sharding import plan_shards, local_problem
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    s = make_scene(args.gpus, args.scale)
+    shard = plan_shards(s.lines_indices, s.n_lines, world)[rank]
+    ci, li, n, p0, p1, pts_local = local_problem(shard, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1, s.points_3d)
+    m_local = ci.shape[0]
+
+    # pinned host copies: the e2e leg copies from these inside the timed region
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory()
+    h = dict(ci=pin(ci), li=pin(li), n=pin(n), p0=pin(p0), p1=pin(p1), cams=pin(s.camera_params), pts=pin(pts_local))
+
+    stream = torch.cuda.Stream()
+    ba = LineBA(local_rank)
+    from amuya_sfm_lines_beta_b200._lib import check
+    check(ba._lib.lba_set_stream(ba._h, stream.cuda_stream))
+    if world > 1:
+        ba.init_comm(rank, world)
+    ba.set_problem(s.n_cameras, shard.n_lines, h["ci"], h["li"], h["n"], h["p0"], h["p1"])
+    lm_kw = dict(ftol=0.0, xtol=0.0, gtol=0.0, verbose=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            out = fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    cams_buf = h["cams"].clone().cuda()
+    pts_buf = h["pts"].clone().cuda()
+
+    def reset_state():
+        cams_buf.copy_(h["cams"]); pts_buf.copy_(h["pts"])
+        torch.cuda.synchronize()
+
+    # -- warm-up: W untimed LM iterations --------------------------------------------------------------
+    reset_state()
+    ba.lm_solve(None, None, out=(cams_buf, pts_buf), want_residuals=False, max_iter=warmup, **lm_kw)
+
+    # -- value: K LM iterations, observations and parameters already resident in HBM ----------------------
+    reset_state()
+    n0 = ba.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms, res = timed(lambda: ba.lm_solve(None, None, out=(cams_buf, pts_buf), want_residuals=False,
+                                            max_iter=args.steps, **lm_kw))
+    launches = ba.launch_count() - n0
+    steps_done = res.iterations
+    value = steps_done / (ms * 1e-3)
+
+    # -- e2e: host buffers in, host results out, through the public array API ------------------------------
+    out_c = torch.empty_like(h["cams"]).pin_memory()
+    out_p = torch.empty_like(h["pts"]).pin_memory()
+
+    def e2e_call():
+        ba.set_problem(s.n_cameras, shard.n_lines, h["ci"], h["li"], h["n"], h["p0"], h["p1"])
+        out_c.copy_(h["cams"]); out_p.copy_(h["pts"])
+        return ba.lm_solve(None, None, out=(out_c, out_p), want_residuals=True, max_iter=args.steps, **lm_kw)
+    e2e_call()  # warm
+    ms_e2e, res_e2e = timed(e2e_call)
+    e2e_value = res_e2e.iterations / (ms_e2e * 1e-3)
+    h2d = sum(h[k].numel() * h[k].element_size() for k in ("ci", "li", "n", "p0", "p1", "cams", "pts"))
+    d2h = out_c.numel() * 8 + out_p.numel() * 8 + m_local * 8
+
+    # -- roofline: per-kernel-class device time from CUDA events on the launching stream ---------------------
+    reset_state()
+    ba.set_profiling(True)
+    ba.lm_solve(None, None, out=(cams_buf, pts_buf), want_residuals=False, max_iter=min(args.steps, 10), **lm_kw)
+    prof = ba.get_profile()
+    ba.set_profiling(False)
+    peak, peak_src = read_peaks()
+    tot = sum(v["ms"] for v in prof.values()) or 1.0
+    shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["launches"]}
+    dom = max((k for k in BYTES_PER_OBS if prof.get(k, {}).get("launches")), key=lambda k: prof[k]["ms"], default=None)
+    roof = None
+    per_kernel = {}
+    for k, bpo in BYTES_PER_OBS.items():
+        if prof.get(k, {}).get("launches"):
+            avg_ms = prof[k]["ms"] / prof[k]["launches"]
+            per_kernel[k] = {"avg_us": round(avg_ms * 1e3, 2), "GBps": round(bpo * m_local / (avg_ms * 1e-3) / 1e9, 1),
+                             "frac": round(bpo * m_local / (avg_ms * 1e-3) / 1e9 / peak, 4), "launches": prof[k]["launches"]}
+    if dom:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_obs": BYTES_PER_OBS[dom], "per_kernel": per_kernel, "time_shares": shares}
+
+    fp64_tf = ba.measure_fp64_peak()
+    copy_gbs = ba.measure_copy_bandwidth(1 << 30)
+
+    if rank == 0:
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_reference_run(3, 1, full_obs, mode=args.ref_mode)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+                "warmup": warmup, "ms_per_step": ms / max(steps_done, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(res_e2e.iterations, 1),
+                        "d2h_bytes_per_step": d2h / max(res_e2e.iterations, 1), "ms_total": ms_e2e,
+                        "note": "one call = lba_set_problem from pinned host arrays + K LM iterations + results to host"},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cb,
+                "lm": {"cost_init": res.cost_init, "cost_final": res.cost, "pcg_iters_total": res.pcg_iters_total,
+                       "pcg_iters_per_lm": res.pcg_iters_total / max(steps_done, 1), "n_jac": res.n_jac, "n_res": res.n_res,
+                       "obs_per_sec": m_local * world * (res.n_jac + res.n_res) / (ms * 1e-3)},
+                "device_peaks": {"fp64_tflops_measured": round(fp64_tf, 2), "copy_gbs_measured": round(copy_gbs, 1)}}
+        print(json.dumps(line))
+    ba.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,374 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle and the
+golden fixtures generated from the reference itself.  Parity ladder of SURVEY.md 8c:
+
+P0 indexing bit-exact | P1 residuals <= 1e-9 rel | P2 Jacobian vs oracle / vs FD of the reference fun
+P3 normal equations, Schur solve | P4 LM trajectory vs the oracle | P5 final cost vs the reference's run
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+RTOL_RESIDUAL = 1e-9       # north_star: per-residual values within 1e-9 relative in fp64
+RTOL_FINAL = 1e-6          # north_star: final cost and parameters within 1e-6 relative
+RTOL_TRAJ = 1e-9           # per-iteration cost against the oracle running the same algorithm
+
+
+def residual_tol(r_ref):
+    # 1e-9 relative plus the fp64 floor of the formula itself: r = (2a)^2 + b^2 + ... with a, b dot
+    # products of unit vectors (|da| ~ eps), so |dr| <~ 8 eps sqrt(r).
+    return RTOL_RESIDUAL * np.abs(r_ref) + 16 * EPS * np.sqrt(np.abs(r_ref)) + 64 * EPS * EPS
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import line_ba_oracle
+    return line_ba_oracle
+
+
+@pytest.fixture(scope="module")
+def LineBA():
+    from amuya_sfm_lines_beta_b200 import LineBA as cls
+    return cls
+
+
+def make_ctx(LineBA, s):
+    ba = LineBA(0)
+    ba.set_problem(s.n_cameras, s.n_lines, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1)
+    return ba
+
+
+def load(name):
+    from amuya_sfm_lines_beta_b200.scenes import scene_from_npz
+    return scene_from_npz(os.path.join(GOLDEN, name + ".npz")), np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def synth(*a, **k):
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    return make_synthetic_scene(*a, **k)
+
+
+# ---------------------------------------------------------------- P0
+@pytest.mark.parametrize("name", golden_names())
+def test_p0_indexing_bit_exact(LineBA, name):
+    s, q = load(name)
+    ba = make_ctx(LineBA, s)
+    cam_pt, pt_idx = ba.point_wise_indices()
+    assert np.array_equal(cam_pt, q["ref_camera_indices_pt"])
+    assert np.array_equal(pt_idx, q["ref_pt_indices"])
+    ba.close()
+
+
+# ---------------------------------------------------------------- P1
+@pytest.mark.parametrize("name", golden_names())
+def test_p1_residuals_vs_reference_fun(LineBA, name):
+    s, q = load(name)
+    ba = make_ctx(LineBA, s)
+    nc = s.n_cameras
+    for xk, fk in (("ref_x0", "ref_fun_x0"), ("ref_x1", "ref_fun_x1")):
+        x = q[xk]
+        r, cost = ba.residuals(x[:6 * nc].reshape(nc, 6), x[6 * nc:].reshape(-1, 3))
+        assert np.all(np.abs(r - q[fk]) <= residual_tol(q[fk]))
+        assert abs(cost - 0.5 * np.sum(q[fk] ** 2)) <= 1e-12 * cost
+    ba.close()
+
+
+@pytest.mark.parametrize("name", ["toy1_lv2", "toy2_lv2"])
+def test_p1_project_vs_reference(LineBA, name):
+    s, q = load(name)
+    ba = make_ctx(LineBA, s)
+    ph = ba.project(s.camera_params, s.points_3d)
+    assert np.max(np.abs(ph - q["ref_project_x0"])) < 1e-14
+    ba.close()
+
+
+def test_p1_dropin_fun_and_project(LineBA):
+    """The module-level mirrors of the reference helpers."""
+    from amuya_sfm_lines_beta_b200 import bundle_adjustment as mod
+    from test_cabi_and_host import _objects_from_golden
+    s, q = load("toy1_lv2")
+    lines_3d, lines_2d = _objects_from_golden(q)
+    pts, p2d, cam_pt, pt_idx = mod.point_wise_input(lines_3d, lines_2d, q["camera_indices"], q["lines_indices"])
+    r = mod.fun(q["ref_x0"], s.n_cameras, pts.shape[0], cam_pt, pt_idx, p2d, lines_2d)
+    assert np.all(np.abs(r - q["ref_fun_x0"]) <= residual_tol(q["ref_fun_x0"]))
+    x0 = q["ref_x0"]; nc = s.n_cameras
+    ph = mod.project(x0[6 * nc:].reshape(-1, 3)[pt_idx], x0[:6 * nc].reshape(nc, 3, 2)[cam_pt])
+    assert np.max(np.abs(ph - q["ref_project_x0"])) < 1e-14
+
+
+def test_p1_residuals_synthetic_32k(LineBA, orc):
+    s = synth(64, 3200, 10, seed=0)
+    ba = make_ctx(LineBA, s)
+    r, cost = ba.residuals(s.camera_params, s.points_3d)
+    ref = orc.residuals(*s.arrays())
+    assert np.all(np.abs(r - ref) <= residual_tol(ref))
+    assert abs(cost - 0.5 * ref @ ref) <= 1e-12 * cost
+    ba.close()
+
+
+# ---------------------------------------------------------------- P2
+def _oracle_jac(orc, s, cams=None, pts=None):
+    cams = s.camera_params if cams is None else cams
+    pts = s.points_3d if pts is None else pts
+    om, ce = orc.split_camera_params(cams)
+    return orc.residuals_jacobian(om, ce, pts.reshape(-1, 6), s.camera_indices, s.lines_indices, s.n,
+                                  np.cross(s.n, s.p0), np.cross(s.n, s.p1))
+
+
+def _interleave(jc):
+    out = np.empty_like(jc)
+    out[:, 0::2] = jc[:, 0:3]
+    out[:, 1::2] = jc[:, 3:6]
+    return out
+
+
+@pytest.mark.parametrize("name", ["toy1_lv2", "toy1_lv5", "toy2_lv2"])
+def test_p2_jacobian_vs_reference_fd_and_oracle(LineBA, orc, name):
+    s, q = load(name)
+    nc = s.n_cameras
+    x1 = q["ref_x1"]
+    cams, pts = x1[:6 * nc].reshape(nc, 6), x1[6 * nc:].reshape(-1, 3)
+    ba = make_ctx(LineBA, s)
+    r, jcam, jline = ba.residuals_jacobian(cams, pts)
+    r_o, jc_o, jl_o = _oracle_jac(orc, s, cams, pts)
+    scale = max(np.abs(jc_o).max(), np.abs(jl_o).max())
+    assert np.max(np.abs(jcam - _interleave(jc_o))) < 1e-12 * scale
+    assert np.max(np.abs(jline - jl_o)) < 1e-12 * scale
+    # against central finite differences of the REFERENCE fun
+    J = np.zeros((s.n_obs, 6 * nc + 6 * s.n_lines))
+    rows = np.arange(s.n_obs)
+    for k in range(6):
+        J[rows, 6 * s.camera_indices + k] = jcam[:, k]
+        J[rows, 6 * nc + 6 * s.lines_indices + k] = jline[:, k]
+    Ja = J[np.ix_(q["ref_fd_rows"], q["ref_fd_cols"])]
+    assert np.max(np.abs(Ja - q["ref_fd_jac_x1"])) < 1e-7 * max(1.0, np.abs(Ja).max())
+    ba.close()
+
+
+# ---------------------------------------------------------------- P3
+def _unpack21(P):
+    M = np.empty((P.shape[0], 6, 6))
+    k = 0
+    for a in range(6):
+        for b in range(a, 6):
+            M[:, a, b] = P[:, k]; M[:, b, a] = P[:, k]; k += 1
+    return M
+
+
+@pytest.mark.parametrize("scene", ["toy1_lv9", "synth"])
+def test_p3_normal_equations_and_schur_solve(LineBA, orc, scene):
+    s = load(scene)[0] if scene != "synth" else synth(40, 1500, 8, seed=2)
+    ba = make_ctx(LineBA, s)
+    r, jcam, jline = ba.residuals_jacobian(s.camera_params, s.points_3d)
+    U, gc, V, gl = ba.normal_equations()
+    r_o, jc_o, jl_o = _oracle_jac(orc, s)
+    Uo, gco, Vo, glo = orc.normal_equations(r_o, jc_o, jl_o, s.camera_indices, s.lines_indices, s.n_cameras, s.n_lines)
+    for got, ref in ((_unpack21(U), Uo), (gc, gco), (_unpack21(V), Vo), (gl, glo)):
+        assert np.max(np.abs(got - ref)) <= 1e-10 * np.max(np.abs(ref))
+    idx = np.arange(6)
+    Dc = orc.update_scaling(None, Uo[:, idx, idx]); Dl = orc.update_scaling(None, Vo[:, idx, idx])
+    for lam in (1e-2, 1e-4):
+        sysm = orc.SchurSystem(r_o, jc_o, jl_o, s.camera_indices, s.lines_indices, Uo, gco, Vo, glo, Dc, Dl, lam)
+        dco, qo = sysm.pcg(1e-10, 500)
+        dlo, _ = sysm.back_substitute(dco)
+        dc, dl, qd = ba.schur_solve(lam, pcg_tol=1e-10, pcg_max_iter=500)
+        assert np.max(np.abs(dc - dco)) <= 1e-7 * np.max(np.abs(dco))
+        assert np.max(np.abs(dl - dlo)) <= 1e-7 * np.max(np.abs(dlo))
+        assert abs(qd - qo) <= 2
+    ba.close()
+
+
+# ---------------------------------------------------------------- P4
+def _traj(res):
+    return np.array([t["cost_new"] for t in res.trace]), [t["accepted"] for t in res.trace], [t["pcg"] for t in res.trace]
+
+
+@pytest.mark.parametrize("scene,iters", [("toy1_lv2", 12), ("toy1_lv9", 12), ("toy2_lv2", 12), ("manual3", 10),
+                                         ("synth_small", 12), ("synth_mid", 8)])
+def test_p4_lm_trajectory_matches_oracle(LineBA, orc, scene, iters):
+    if scene == "synth_small":
+        s = synth(12, 200, 5, seed=1)
+    elif scene == "synth_mid":
+        s = synth(50, 2000, 10, seed=0)
+    else:
+        s = load(scene)[0]
+    kw = dict(max_iter=iters, ftol=0.0, xtol=0.0, gtol=0.0)
+    ba = make_ctx(LineBA, s)
+    res = ba.lm_solve(s.camera_params, s.points_3d, **kw)
+    cams_o, pts_o, r_o, rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(**kw))
+    assert res.iterations == rep.iterations == iters
+    cost_d, acc_d, pcg_d = _traj(res)
+    cost_o = np.array([t["cost_new"] for t in rep.trace])
+    assert acc_d == [t["accepted"] for t in rep.trace]
+    assert pcg_d == [t["pcg"] for t in rep.trace]
+    assert np.all(np.abs(cost_d - cost_o) <= RTOL_TRAJ * np.abs(cost_o))
+    assert abs(res.cost - rep.cost) <= RTOL_FINAL * rep.cost
+    assert np.max(np.abs(res.camera_params - cams_o)) <= RTOL_FINAL * np.max(np.abs(cams_o))
+    assert np.max(np.abs(res.points_3d - pts_o)) <= RTOL_FINAL * np.max(np.abs(pts_o))
+    assert np.all(np.abs(res.residuals - r_o) <= 1e-6 * np.abs(r_o) + 1e-6 * np.abs(r_o).max())
+    # the returned residual is fun at the returned parameters (bundle_adjustment.py:332)
+    r_chk = orc.residuals(res.camera_params, res.points_3d, *s.arrays()[2:])
+    assert np.all(np.abs(res.residuals - r_chk) <= residual_tol(r_chk))
+    assert res.chol_clamped == 0
+    ba.close()
+
+
+def test_p4_termination_rules_match_oracle(LineBA, orc):
+    """Default tolerances (ftol=1e-4 as the reference call site, xtol=gtol=1e-8)."""
+    s = synth(12, 200, 5, seed=1)
+    ba = make_ctx(LineBA, s)
+    res = ba.lm_solve(s.camera_params, s.points_3d, max_iter=60)
+    rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(max_iter=60))[3]
+    assert (res.iterations, res.status) == (rep.iterations, rep.status)
+    assert abs(res.cost - rep.cost) <= RTOL_FINAL * rep.cost
+    ba.close()
+
+
+# ---------------------------------------------------------------- P5
+def test_p5_dropin_beats_reference_run(LineBA, capsys):
+    """run_bundle_adjustment on the scene whose reference output was recorded: same returned shapes
+    and layouts; final cost below the reference's (its as-shipped pattern stalls)."""
+    from amuya_sfm_lines_beta_b200.bundle_adjustment import run_bundle_adjustment
+    from test_cabi_and_host import _objects_from_golden
+    s, q = load("toy1_lv2")
+    lines_3d, lines_2d = _objects_from_golden(q)
+    inp = {"camera_params": q["camera_params"], "Lines_3d": lines_3d, "camera_indices": q["camera_indices"],
+           "lines_indices": q["lines_indices"], "lines_2d": lines_2d}
+    cams_before = q["camera_params"].copy()
+    opc, opp, res = run_bundle_adjustment(inp, "linear")
+    out = capsys.readouterr().out
+    assert out.splitlines()[0] == str(q["ref_ba_stdout_head"]).splitlines()[0]      # same banner
+    assert out.splitlines()[1:6] == str(q["ref_ba_stdout_head"]).splitlines()[1:6]  # same size lines
+    assert "Optimization took" in out
+    assert opc.shape == q["ref_ba_op_camera_params"].shape and opc.dtype == np.float64
+    assert opp.shape == q["ref_ba_op_points_3d"].shape and opp.dtype == np.float64
+    assert res.shape == q["ref_ba_residual"].shape
+    assert np.array_equal(inp["camera_params"], cams_before)                        # inputs not mutated
+    ref_cost = 0.5 * float(np.sum(q["ref_ba_residual"] ** 2))
+    assert 0.5 * float(res @ res) < ref_cost
+
+
+# ---------------------------------------------------------------- edge cases
+def test_unsorted_observations_give_identical_results(LineBA):
+    s = synth(10, 150, 5, seed=7)
+    perm = np.random.default_rng(0).permutation(s.n_obs)
+    ba = make_ctx(LineBA, s)
+    r0, c0 = ba.residuals(s.camera_params, s.points_3d)
+    res0 = ba.lm_solve(s.camera_params, s.points_3d, max_iter=5, ftol=0.0)
+    ba2 = LineBA(0)
+    ba2.set_problem(s.n_cameras, s.n_lines, s.camera_indices[perm], s.lines_indices[perm], s.n[perm], s.p0[perm], s.p1[perm])
+    r1, c1 = ba2.residuals(s.camera_params, s.points_3d)
+    assert np.array_equal(r1, r0[perm])
+    cam_pt, pt_idx = ba2.point_wise_indices()
+    assert np.array_equal(cam_pt, np.repeat(s.camera_indices[perm], 2))
+    assert np.array_equal(pt_idx[0::2], 2 * s.lines_indices[perm])
+    # a stable sort by line keeps the per-line order only if the permutation did; costs agree to rounding
+    res1 = ba2.lm_solve(s.camera_params, s.points_3d, max_iter=5, ftol=0.0)
+    assert abs(res1.cost - res0.cost) <= 1e-9 * res0.cost
+    assert np.allclose(res1.residuals, res0.residuals[perm], rtol=1e-7, atol=1e-12)
+    ba.close(); ba2.close()
+
+
+def test_bitwise_reproducible(LineBA):
+    s = synth(30, 800, 8, seed=3)
+    ba = make_ctx(LineBA, s)
+    a = ba.lm_solve(s.camera_params, s.points_3d, max_iter=6, ftol=0.0)
+    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=6, ftol=0.0)
+    assert np.array_equal(a.camera_params, b.camera_params) and np.array_equal(a.points_3d, b.points_3d)
+    assert a.cost == b.cost
+    ba.close()
+
+
+def test_lines_and_cameras_without_observations(LineBA, orc):
+    s = synth(8, 60, 4, seed=11)
+    # append two 3D lines and one camera that nothing observes (Lines_3d holds ALL lines, seq_utils.py:198)
+    pts = np.vstack([s.points_3d, np.array([[1., 2, 3], [4, 5, 6], [0, 0, 1], [1, 1, 1]])])
+    cams = np.vstack([s.camera_params, np.array([[0.1, 5, 0.2, 6, 0.3, 7]])])
+    ba = LineBA(0)
+    ba.set_problem(9, 62, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1)
+    res = ba.lm_solve(cams, pts, max_iter=6, ftol=0.0)
+    ref = orc.lm_solve(cams, pts, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1,
+                       opts=orc.LMOptions(max_iter=6, ftol=0.0))
+    assert abs(res.cost - ref[3].cost) <= RTOL_FINAL * ref[3].cost
+    assert np.array_equal(res.points_3d[-4:], pts[-4:])      # untouched
+    assert np.array_equal(res.camera_params[-1], cams[-1])
+    ba.close()
+
+
+def test_empty_problem(LineBA):
+    ba = LineBA(0)
+    z3 = np.zeros((0, 3))
+    ba.set_problem(2, 3, np.zeros(0, np.int64), np.zeros(0, np.int64), z3, z3, z3)
+    r, cost = ba.residuals(np.zeros((2, 6)), np.ones((6, 3)))
+    assert r.shape == (0,) and cost == 0.0
+    res = ba.lm_solve(np.zeros((2, 6)), np.ones((6, 3)), max_iter=3)
+    assert res.cost == 0.0 and res.status == 1          # gradient is zero: gtol
+    ba.close()
+
+
+def test_error_paths(LineBA):
+    from amuya_sfm_lines_beta_b200._lib import LbaError, LBA_ERR_ARG, LBA_ERR_UNSUPPORTED, LBA_ERR_NONFINITE, LBA_ERR_STATE
+    ba = LineBA(0)
+    with pytest.raises(LbaError) as e:
+        ba.residuals(np.zeros((1, 6)), np.zeros((2, 3)))
+    assert e.value.code == LBA_ERR_STATE
+    one = np.array([[0.0, 0.0, 1.0]])
+    with pytest.raises(LbaError) as e:
+        ba.set_problem(1, 1, np.array([1]), np.array([0]), one, one, one)
+    assert e.value.code == LBA_ERR_ARG
+    k = 300                                               # more than LBA_MAX_OBS_PER_LINE views of one line
+    rep = np.tile(one, (k, 1))
+    with pytest.raises(LbaError) as e:
+        ba.set_problem(k, 1, np.arange(k), np.zeros(k, np.int64), rep, rep, rep)
+    assert e.value.code == LBA_ERR_UNSUPPORTED
+    s = synth(4, 10, 3, seed=0)
+    ba.set_problem(s.n_cameras, s.n_lines, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1)
+    bad = s.points_3d.copy(); bad[0, 0] = np.nan
+    with pytest.raises(LbaError, match="not finite in the initial point") as e:
+        ba.lm_solve(s.camera_params, bad)
+    assert e.value.code == LBA_ERR_NONFINITE
+    ba.close()
+
+
+def test_device_resident_inputs(LineBA):
+    """torch CUDA tensors are consumed in place (no host round trip of the observation arrays)."""
+    import torch
+    s = synth(10, 150, 5, seed=7)
+    ba = make_ctx(LineBA, s)
+    r0, _ = ba.residuals(s.camera_params, s.points_3d)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ba2 = LineBA(0)
+    ba2.set_problem(s.n_cameras, s.n_lines, t(s.camera_indices), t(s.lines_indices), t(s.n), t(s.p0), t(s.p1))
+    r1, _ = ba2.residuals(t(s.camera_params), t(s.points_3d))
+    assert np.array_equal(r0, r1)
+    ba.close(); ba2.close()
+
+
+# ---------------------------------------------------------------- full size (config 4) properties
+@pytest.mark.parametrize("variant", ["A"])
+def test_config4_full_size_properties(LineBA, orc, variant):
+    """1k cameras / 200k lines / 2M observations: residuals checked against the oracle on the whole
+    scene (vectorised numpy), cost monotone over accepted steps, bit-reproducible, launches counted."""
+    s = synth(1000, 200_000, 10, seed=0, variant=variant)
+    ba = make_ctx(LineBA, s)
+    r, cost = ba.residuals(s.camera_params, s.points_3d)
+    ref = orc.residuals(*s.arrays())
+    assert np.all(np.abs(r - ref) <= residual_tol(ref))
+    n0 = ba.launch_count()
+    a = ba.lm_solve(s.camera_params, s.points_3d, max_iter=6, ftol=0.0)
+    assert ba.launch_count() > n0
+    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=6, ftol=0.0)
+    assert a.cost == b.cost and np.array_equal(a.points_3d, b.points_3d)
+    costs = [t["cost_new"] for t in a.trace if t["accepted"]]
+    assert all(x > y for x, y in zip([a.cost_init] + costs[:-1], costs))
+    assert a.cost < 0.5 * a.cost_init
+    r_fin = orc.residuals(a.camera_params, a.points_3d, *s.arrays()[2:])
+    assert np.all(np.abs(a.residuals - r_fin) <= residual_tol(r_fin))
+    assert abs(a.cost - 0.5 * r_fin @ r_fin) <= 1e-10 * a.cost
+    ba.close()

@@ -1,0 +1,185 @@
+"""CPU: the numpy oracle against the fixtures generated from the reference itself
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import line_ba_oracle as orc
+from conftest import GOLDEN, golden_names
+
+EPS = np.finfo(np.float64).eps
+
+
+def residual_tol(r_ref):
+    """1e-9 relative, plus the floor any fp64 evaluation has: r = sum (2a)^2 + b^2 with a, b dot
+    products of unit vectors carrying ~eps absolute error, so |dr| <~ 8 eps sqrt(r)."""
+    return 1e-9 * np.abs(r_ref) + 16 * EPS * np.sqrt(np.abs(r_ref)) + 64 * EPS * EPS
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_indexing_bit_exact(name):
+    q = np.load(os.path.join(GOLDEN, name + ".npz"))
+    pts, cam_pt, pt_idx = orc.point_wise_input_arrays(q["points_3d_raw"], q["camera_indices"], q["lines_indices"])
+    assert np.array_equal(cam_pt, q["ref_camera_indices_pt"])
+    assert np.array_equal(pt_idx, q["ref_pt_indices"])
+    assert cam_pt.dtype == q["ref_camera_indices_pt"].dtype and pt_idx.dtype == q["ref_pt_indices"].dtype
+    assert np.array_equal(pts, q["ref_points_3d"].astype(np.float64))
+    # x0 packing (bundle_adjustment.py:311)
+    assert np.array_equal(orc._x_pack(q["camera_params"], q["points_3d_raw"]), q["ref_x0"])
+    # observation order is track-major, view-ascending (seq_utils.py:190)
+    li, ci = q["lines_indices"], q["camera_indices"]
+    assert np.all(np.diff(li) >= 0)
+    same = np.diff(li) == 0
+    assert np.all(np.diff(ci)[same] > 0)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_residuals_match_reference_fun(name):
+    q = np.load(os.path.join(GOLDEN, name + ".npz"))
+    nc = q["camera_params"].shape[0]
+    for xk, fk in (("ref_x0", "ref_fun_x0"), ("ref_x1", "ref_fun_x1")):
+        x = q[xk]
+        r = orc.residuals(x[:6 * nc].reshape(nc, 6), x[6 * nc:].reshape(-1, 3), q["camera_indices"],
+                          q["lines_indices"], q["n"], q["p0"], q["p1"])
+        assert np.all(np.abs(r - q[fk]) <= residual_tol(q[fk]))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_project_matches_reference(name):
+    q = np.load(os.path.join(GOLDEN, name + ".npz"))
+    om, ce = orc.split_camera_params(q["camera_params"])
+    pts = q["ref_points_3d"].astype(np.float64)
+    cam_pt, pt_idx = q["ref_camera_indices_pt"], q["ref_pt_indices"]
+    ph = orc.project(pts[pt_idx], om[cam_pt], ce[cam_pt])
+    assert np.max(np.abs(ph - q["ref_project_x0"])) < 1e-14
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sparsity_columns_as_shipped(name):
+    q = np.load(os.path.join(GOLDEN, name + ".npz"))
+    nc = q["camera_params"].shape[0]
+    cols = orc.bundle_adjustment_sparsity_columns(nc, q["camera_indices"], q["lines_indices"])
+    indptr, indices = q["ref_sparsity_indptr"], q["ref_sparsity_indices"]
+    for i in range(cols.shape[0]):
+        assert np.array_equal(np.sort(cols[i]), indices[indptr[i]:indptr[i + 1]])
+
+
+@pytest.mark.parametrize("name", ["toy1_lv2", "toy1_lv5", "toy2_lv2"])
+def test_analytic_jacobian_vs_reference_fd(name):
+    q = np.load(os.path.join(GOLDEN, name + ".npz"))
+    nc = q["camera_params"].shape[0]
+    x1 = q["ref_x1"]
+    om, ce = orc.split_camera_params(x1[:6 * nc].reshape(nc, 6))
+    pts = x1[6 * nc:].reshape(-1, 6)
+    ci, li, n = q["camera_indices"], q["lines_indices"], q["n"]
+    r, jc, jl = orc.residuals_jacobian(om, ce, pts, ci, li, n, np.cross(n, q["p0"]), np.cross(n, q["p1"]))
+    J = orc.dense_jacobian_reference_layout(jc, jl, ci, li, nc, pts.shape[0])
+    assert ((J != 0).sum(axis=1) <= 12).all()
+    Ja = J[np.ix_(q["ref_fd_rows"], q["ref_fd_cols"])]
+    assert np.max(np.abs(Ja - q["ref_fd_jac_x1"])) < 1e-7 * max(1.0, np.abs(Ja).max())
+    # no non-zero outside the columns the FD probe covered
+    mask = np.ones(J.shape[1], bool); mask[q["ref_fd_cols"]] = False
+    assert np.all(J[np.ix_(q["ref_fd_rows"], np.nonzero(mask)[0])] == 0)
+
+
+def test_rodrigues_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    w = np.vstack([rng.normal(0, 1.0, (200, 3)), np.zeros((1, 3)), rng.normal(0, 1e-9, (5, 3)),
+                   rng.normal(0, 1e-3, (5, 3))])
+    R = orc.rodrigues(w)
+    for k in range(w.shape[0]):
+        assert np.max(np.abs(R[k] - cv2.Rodrigues(w[k])[0])) < 4e-15
+
+
+def test_right_jacobian_against_finite_differences():
+    rng = np.random.default_rng(1)
+    for scale in (1.0, 0.05, 1e-4, 0.0):
+        w = rng.normal(0, 1, 3) * scale
+        d = rng.normal(0, 1, 3)
+        G = orc.so3_right_jacobian(w[None])[0]
+        R = orc.rodrigues(w[None])[0]
+        dK = np.array([[0, -d[2], d[1]], [d[2], 0, -d[0]], [-d[1], d[0], 0]])
+        ana = -R @ dK @ G
+        h = 1e-6
+        fd = np.stack([(orc.rodrigues((w + h * e)[None])[0] @ d - orc.rodrigues((w - h * e)[None])[0] @ d) / (2 * h)
+                       for e in np.eye(3)], axis=1)
+        assert np.max(np.abs(ana - fd)) < 1e-8
+
+
+def test_table_identity_for_camera_dot():
+    """jc_i . v == sum_e jl_e . (a x X_e - h) with a = G v_w, h = a x c + v_c -- the identity the
+    line-ordered PCG kernel relies on (it never reads jc)."""
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    s = make_synthetic_scene(7, 40, 4, seed=5)
+    om, ce = orc.split_camera_params(s.camera_params)
+    pts = s.points_3d.reshape(-1, 6)
+    ci, li = s.camera_indices, s.lines_indices
+    r, jc, jl = orc.residuals_jacobian(om, ce, pts, ci, li, s.n, np.cross(s.n, s.p0), np.cross(s.n, s.p1))
+    v = np.random.default_rng(2).normal(size=(7, 6))
+    G = orc.so3_right_jacobian(om)
+    a = np.einsum('cij,cj->ci', G, v[:, :3])
+    h = np.cross(a, ce) + v[:, 3:]
+    s_tab = sum(np.einsum('ni,ni->n', jl[:, 3 * e:3 * e + 3], np.cross(a[ci], pts[li, 3 * e:3 * e + 3]) - h[ci])
+                for e in (0, 1))
+    s_dir = np.einsum('ni,ni->n', jc, v[ci])
+    assert np.max(np.abs(s_tab - s_dir)) < 1e-12 * max(1.0, np.abs(s_dir).max())
+
+
+def test_schur_pcg_solves_the_damped_normal_equations():
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    s = make_synthetic_scene(6, 30, 4, seed=9)
+    om, ce = orc.split_camera_params(s.camera_params)
+    pts = s.points_3d.reshape(-1, 6)
+    ci, li = s.camera_indices, s.lines_indices
+    r, jc, jl = orc.residuals_jacobian(om, ce, pts, ci, li, s.n, np.cross(s.n, s.p0), np.cross(s.n, s.p1))
+    nc, nl = 6, 30
+    U, gc, V, gl = orc.normal_equations(r, jc, jl, ci, li, nc, nl)
+    idx = np.arange(6)
+    Dc = orc.update_scaling(None, U[:, idx, idx]); Dl = orc.update_scaling(None, V[:, idx, idx])
+    lam = 1e-3
+    sysm = orc.SchurSystem(r, jc, jl, ci, li, U, gc, V, gl, Dc, Dl, lam)
+    dc, q = sysm.pcg(1e-12, 500)
+    dl, jd = sysm.back_substitute(dc)
+    # dense check
+    J = np.zeros((len(r), 6 * nc + 6 * nl))
+    for i in range(len(r)):
+        J[i, 6 * ci[i]:6 * ci[i] + 6] = jc[i]
+        J[i, 6 * nc + 6 * li[i]:6 * nc + 6 * li[i] + 6] = jl[i]
+    H = J.T @ J + lam * np.diag(np.concatenate([Dc.ravel(), Dl.ravel()]))
+    ref = np.linalg.solve(H, -J.T @ r)
+    got = np.concatenate([dc.ravel(), dl.ravel()])
+    assert np.max(np.abs(got - ref)) < 1e-8 * np.max(np.abs(ref))
+    assert np.allclose(jd, J @ got, rtol=1e-10, atol=1e-14)
+
+
+def test_lm_oracle_beats_the_reference_as_shipped():
+    """P5: on the scene where the reference's own run_bundle_adjustment output was recorded, the LM
+    restatement ends below the reference's final cost (the as-shipped pattern stalls, finding F4)."""
+    q = np.load(os.path.join(GOLDEN, "toy1_lv2.npz"))
+    ref_cost = 0.5 * float(np.sum(q["ref_ba_residual"] ** 2))
+    out = orc.lm_solve(q["camera_params"], q["points_3d_raw"].astype(np.float64), q["camera_indices"],
+                       q["lines_indices"], q["n"], q["p0"], q["p1"], opts=orc.LMOptions(max_iter=15))
+    assert out[3].cost < ref_cost
+    assert out[3].cost < 0.05 * out[3].cost_init
+    # returned layouts: (Nc,6) interleaved, (2Nl,3), (m,)
+    assert out[0].shape == q["ref_ba_op_camera_params"].shape
+    assert out[1].shape == q["ref_ba_op_points_3d"].shape
+    assert out[2].shape == q["ref_ba_residual"].shape
+
+
+def test_reference_port_reproduces_as_shipped_behaviour():
+    """Finding F2: with the shipped sparsity pattern only the first half of the endpoint rows can
+    move.  The vectorised port of the reference call shows the same signature as the recorded run."""
+    q = np.load(os.path.join(GOLDEN, "toy1_lv2.npz"))
+    pts0 = q["points_3d_raw"].astype(np.float64)
+    moved_ref = np.any(q["ref_ba_op_points_3d"] != pts0, axis=1)
+    op_cam, op_pts, res, sres, dt = orc.scipy_reference_port(
+        q["camera_params"], pts0, q["camera_indices"], q["lines_indices"], q["n"], q["p0"], q["p1"])
+    moved = np.any(op_pts != pts0, axis=1)
+    half = pts0.shape[0] // 2
+    assert moved_ref[:half].all() and not moved_ref[half:].any()
+    assert moved[:half].all() and not moved[half:].any()
+    ref_cost = 0.5 * float(np.sum(q["ref_ba_residual"] ** 2))
+    assert abs(sres.cost - ref_cost) < 0.2 * ref_cost
