@@ -185,8 +185,8 @@ extern "C" void lba_default_options(lba_options* o) {
   o->ftol = 1e-4;
   o->xtol = 1e-8;
   o->gtol = 1e-8;
-  o->lambda0 = 1e-4;
-  o->lambda_min = 1e-12;
+  o->lambda0 = 1e-2;
+  o->lambda_min = 1e-6;
   o->lambda_max = 1e12;
   o->pcg_tol = 1e-2;
   o->min_ratio = 1e-4;

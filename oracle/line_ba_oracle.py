@@ -285,8 +285,8 @@ class LMOptions:
     ftol: float = 1e-4       # reference call site bundle_adjustment.py:319
     xtol: float = 1e-8       # scipy default
     gtol: float = 1e-8       # scipy default
-    lambda0: float = 1e-4
-    lambda_min: float = 1e-12
+    lambda0: float = 1e-2
+    lambda_min: float = 1e-6
     lambda_max: float = 1e12
     pcg_tol: float = 1e-2    # eta: stop when |r|_Minv <= eta |r0|_Minv
     pcg_max_iter: int = 200

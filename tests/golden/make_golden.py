@@ -186,56 +186,58 @@ def reference_quantities(ref, inp, seed, fd_rows=None, run_ba=False):
 
 
 def manual_annotation_scene(ref, seed=7):
-    """Config-3 stand-in (the natural JPEGs are missing): 3 views x 234 hand-annotated
-    segments (input/manual_line_annotation/*_csv.csv, row i <-> same line), K from
-    main.py:24, bearings as Domain.spherical_representation (domain.py:338-351)
-    computes them.  Poses come from a seeded synthetic rig; 3D endpoints from a seeded
-    back-projection (the reference cannot produce them without the pixels)."""
+    """Config-3 stand-in (the natural JPEGs are missing, so LSD + matching cannot run): natural-image
+    SIZE and 2D-segment statistics from the 3 x 234 hand-annotated segments
+    (input/manual_line_annotation/*_csv.csv), K from main.py:24, bearings exactly as
+    Domain.spherical_representation computes them (domain.py:338-351).
+    View 0 uses the real annotated segments; their 3D endpoints are back-projected at seeded depths;
+    views 1-2 (true poses unknown without the pixels) observe those 3D segments from a seeded rig with
+    endpoint sliding and 1e-3 bearing noise.  Initial cameras/endpoints are seeded perturbations."""
     import csv
     K = np.array([[3.47133831e+03, 0, 2.81264921e+03], [0, 3.46595620e+03, 1.84437179e+03], [0, 0, 1]])
-    segs = []
-    for name in ("DSC_0342", "DSC_0345", "DSC_0347"):
-        rows = []
-        with open(os.path.join(REF, "input", "manual_line_annotation", name + "_csv.csv")) as fp:
-            for row in csv.DictReader(fp):
-                sh = json.loads(row["region_shape_attributes"])
-                if "all_points_x" in sh and len(sh["all_points_x"]) >= 2:
-                    rows.append([sh["all_points_x"][0], sh["all_points_y"][0],
-                                 sh["all_points_x"][1], sh["all_points_y"][1]])
-        segs.append(np.array(rows, dtype=np.float64))
-    nl_all = min(len(s) for s in segs)
+    rows = []
+    with open(os.path.join(REF, "input", "manual_line_annotation", "DSC_0342_csv.csv")) as fp:
+        for row in csv.DictReader(fp):
+            sh = json.loads(row["region_shape_attributes"])
+            if "all_points_x" in sh and len(sh["all_points_x"]) >= 2:
+                rows.append([sh["all_points_x"][0], sh["all_points_y"][0], sh["all_points_x"][1], sh["all_points_y"][1]])
+    seg = np.array(rows, dtype=np.float64)
     cen = K[:2, 2]
-
-    def bearings(s):
-        q0 = np.concatenate((s[0:2] - cen, [K[0, 0]])); q0 /= np.linalg.norm(q0)
-        q1 = np.concatenate((s[2:4] - cen, [K[0, 0]])); q1 /= np.linalg.norm(q1)
-        return q0, q1, np.cross(q0, q1)
-
-    keep = [L for L in range(nl_all)
-            if all(np.linalg.norm(bearings(segs[v][L])[2]) > 0 for v in range(3))]
-    nl = len(keep)
-    n_l, p0_l, p1_l, ci, li = [], [], [], [], []
-    for Lnew, L in enumerate(keep):
-        for v in range(3):
-            q0, q1, nn = bearings(segs[v][L])
-            n_l.append(nn / np.linalg.norm(nn)); p0_l.append(q0); p1_l.append(q1); ci.append(v); li.append(Lnew)
+    q0 = np.concatenate((seg[:, 0:2] - cen, np.full((len(seg), 1), K[0, 0])), axis=1)
+    q1 = np.concatenate((seg[:, 2:4] - cen, np.full((len(seg), 1), K[0, 0])), axis=1)
+    q0 /= np.linalg.norm(q0, axis=1)[:, None]; q1 /= np.linalg.norm(q1, axis=1)[:, None]
+    keep = np.linalg.norm(np.cross(q0, q1), axis=1) > 1e-6
+    q0, q1 = q0[keep], q1[keep]
+    nl = len(q0)
     rng = np.random.default_rng(seed)
-    cams = np.zeros((3, 3, 2))
-    cams[1, :, 0] = [0.02, -0.15, 0.01]; cams[1, :, 1] = [1.0, 0.05, 0.1]
-    cams[2, :, 0] = [-0.01, -0.3, 0.02]; cams[2, :, 1] = [2.0, -0.05, 0.3]
-    p0a = np.array(p0_l); p1a = np.array(p1_l); cia = np.array(ci); lia = np.array(li)
-    pts = np.zeros((2 * nl, 3), dtype=np.float32)
     depth = rng.uniform(6, 12, nl)
-    first = {}
-    for i, L in enumerate(lia):
-        if cia[i] == 0:
-            first[L] = i
+    X0 = q0 * (depth / q0[:, 2])[:, None]
+    X1 = q1 * ((depth + rng.normal(0, 0.3, nl)) / q1[:, 2])[:, None]
+    cams = np.zeros((3, 3, 2))
+    cams[1, :, 0] = [0.02, -0.12, 0.01]; cams[1, :, 1] = [1.2, 0.05, 0.1]
+    cams[2, :, 0] = [-0.01, -0.25, 0.02]; cams[2, :, 1] = [2.4, -0.05, 0.3]
+    import cv2
+    n_l, p0_l, p1_l, ci, li = [], [], [], [], []
     for L in range(nl):
-        i = first[L]
-        pts[2 * L] = (p0a[i] * depth[L] / p0a[i][2]).astype(np.float32)
-        pts[2 * L + 1] = (p1a[i] * depth[L] / p1a[i][2]).astype(np.float32)
-    return dict(camera_params=cams.reshape(3, 6), points_3d_raw=pts, camera_indices=cia.astype(np.int64),
-                lines_indices=lia.astype(np.int64), n=np.array(n_l), p0=p0a, p1=p1a)
+        for v in range(3):
+            if v == 0:
+                a, b = q0[L], q1[L]
+            else:
+                R = cv2.Rodrigues(cams[v, :, 0])[0]
+                c = cams[v, :, 1]
+                s0, s1 = rng.uniform(-0.1, 0.1, 2)
+                dX = X1[L] - X0[L]
+                a = R @ (X0[L] + s0 * dX - c); b = R @ (X1[L] - s1 * dX - c)
+                a = a / np.linalg.norm(a) + rng.normal(0, 1e-3, 3); b = b / np.linalg.norm(b) + rng.normal(0, 1e-3, 3)
+                a /= np.linalg.norm(a); b /= np.linalg.norm(b)
+            nn = np.cross(a, b)
+            n_l.append(nn / np.linalg.norm(nn)); p0_l.append(a); p1_l.append(b); ci.append(v); li.append(L)
+    cams0 = cams.copy()
+    cams0[:, :, 0] += rng.normal(0, 5e-3, (3, 3)); cams0[:, :, 1] += rng.normal(0, 1e-2, (3, 3))
+    pts = np.empty((2 * nl, 3)); pts[0::2] = X0; pts[1::2] = X1
+    pts = (pts + rng.normal(0, 2e-2, pts.shape)).astype(np.float32)   # float32 like the reference's triangulation
+    return dict(camera_params=cams0.reshape(3, 6), points_3d_raw=pts, camera_indices=np.array(ci, dtype=np.int64),
+                lines_indices=np.array(li, dtype=np.int64), n=np.array(n_l), p0=np.array(p0_l), p1=np.array(p1_l))
 
 
 def main():

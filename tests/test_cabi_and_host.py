@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     lib.lba_default_options(ctypes.byref(o))
     assert (o.max_iter, o.pcg_max_iter) == (50, 200)
     assert (o.ftol, o.xtol, o.gtol) == (1e-4, 1e-8, 1e-8)   # reference call site :319 + scipy defaults
-    assert o.lambda0 == 1e-4 and o.pcg_tol == 1e-2 and o.min_ratio == 1e-4
+    assert o.lambda0 == 1e-2 and o.lambda_min == 1e-6 and o.pcg_tol == 1e-2 and o.min_ratio == 1e-4
     assert ctypes.sizeof(_lib.LbaOptions) == 2 * 4 + 8 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.LbaReport) == 6 * 4 + 3 * 8 + 8 + 2 * 4 * 512 + 6 * 8 * 512
 
