@@ -104,11 +104,15 @@ struct lba_ctx {
   int n_sm = 148;
 
   // problem
-  int m = 0, nc = 0, nl = 0, ngroups = 0;
+  int m = 0, nc = 0, nl = 0, ntiles = 0, Mp = 0, lmax = 8;
   bool have_problem = false, have_eval = false, have_blocks = false, have_scaling = false;
-  bool sorted_input = true;
-  DBuf<int> obs_cam, obs_line, cam_pos, cam_perm, cam_ptr, line_ptr, group_line, orig_of;
-  DBuf<double> cst;
+  DBuf<int> obs_cam, cam_pos, cam_perm, cam_ptr, slot_src;
+  DBuf<unsigned char> obs_ll;
+  DBuf<TileMeta> meta;
+  DBuf<double> cst, dense_tmp;
+  // persistent-grid sizes and dynamic shared memory of the pipelined line-order kernels
+  int grid_eval_j = 1, grid_eval_r = 1, grid_lp[3] = {1, 1, 1};
+  int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
 
   // state
   DBuf<double> cams, cams_new, pts, pts_new, Gm, api_tmp;
@@ -372,51 +376,76 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
 
   // line order: stable counting sort by line (identity when the input is already sorted)
-  std::vector<int> orig_of;
-  std::vector<int> obs_cam(m), obs_line(m);
+  std::vector<int> order(m);   // line-sorted position -> caller's observation index
   if (sorted) {
-    for (int i = 0; i < m; ++i) { obs_cam[i] = (int)pc[i]; obs_line[i] = (int)pl[i]; }
+    for (int i = 0; i < m; ++i) order[i] = i;
   } else {
-    orig_of.resize(m);
     std::vector<int> cur(line_ptr.begin(), line_ptr.end() - 1);
-    for (int i = 0; i < m; ++i) orig_of[cur[pl[i]]++] = i;
-    for (int i = 0; i < m; ++i) { obs_cam[i] = (int)pc[orig_of[i]]; obs_line[i] = (int)pl[orig_of[i]]; }
+    for (int i = 0; i < m; ++i) order[cur[pl[i]]++] = i;
   }
-  // groups: whole lines, at most kTile observations
-  std::vector<int> group_line;
-  group_line.push_back(0);
+  // tiles: whole lines, at most kTile observations and kMaxLinesPerTile lines each
+  std::vector<TileMeta> meta;
   {
-    int cur = 0;
+    TileMeta cur;
+    memset(&cur, 0, sizeof cur);
+    bool open = false;
     for (int l = 0; l < nl; ++l) {
       const int k = line_cnt[(size_t)l + 1];
-      if (cur + k > kTile || (l - group_line.back()) >= kTile) { group_line.push_back(l); cur = 0; }
-      cur += k;
+      if (open && (cur.nobs + k > kTile || cur.nl >= kMaxLinesPerTile)) { meta.push_back(cur); open = false; }
+      if (!open) { memset(&cur, 0, sizeof cur); cur.l0 = l; open = true; }
+      cur.nobs += k;
+      cur.lend[cur.nl++] = (unsigned short)cur.nobs;
     }
-    if (nl > 0) group_line.push_back(nl);
+    if (open) meta.push_back(cur);
   }
-  const int ngroups = (int)group_line.size() - 1;
+  const int ntiles = (int)meta.size();
+  const long long Mp64 = (long long)ntiles * kTile;
+  if (Mp64 > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "padded observation count out of range");
+  const int Mp = (int)Mp64;
+  int lmax = 8;
+  for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 7) & ~7);
+  std::vector<int> obs_cam((size_t)Mp, -1), slot_src((size_t)Mp, -1), slot_of_sorted(m);
+  std::vector<unsigned char> obs_ll((size_t)Mp, 0);
+  for (int g = 0; g < ntiles; ++g) {
+    const TileMeta& t = meta[g];
+    int sorted_pos = line_ptr[t.l0];
+    for (int ll = 0; ll < t.nl; ++ll) {
+      const int s0 = ll ? t.lend[ll - 1] : 0, s1 = t.lend[ll];
+      for (int sl = s0; sl < s1; ++sl, ++sorted_pos) {
+        const size_t slot = (size_t)g * kTile + sl;
+        const int src = order[sorted_pos];
+        obs_cam[slot] = (int)pc[src];
+        obs_ll[slot] = (unsigned char)ll;
+        slot_src[slot] = src;
+        slot_of_sorted[sorted_pos] = (int)slot;
+      }
+    }
+  }
   // camera order: stable counting sort of the line-ordered observations by camera
-  std::vector<int> cam_ptr((size_t)nc + 1, 0), cam_perm(m), cam_pos(m);
-  for (int i = 0; i < m; ++i) ++cam_ptr[(size_t)obs_cam[i] + 1];
+  std::vector<int> cam_ptr((size_t)nc + 1, 0), cam_perm(m), cam_pos((size_t)Mp, 0);
+  for (int i = 0; i < m; ++i) ++cam_ptr[(size_t)pc[i] + 1];
   for (int c = 0; c < nc; ++c) cam_ptr[(size_t)c + 1] += cam_ptr[c];
   {
     std::vector<int> cur(cam_ptr.begin(), cam_ptr.end() - 1);
-    for (int i = 0; i < m; ++i) { const int j = cur[obs_cam[i]]++; cam_perm[j] = i; cam_pos[i] = j; }
+    for (int i = 0; i < m; ++i) {
+      const int slot = slot_of_sorted[i];
+      const int j = cur[obs_cam[slot]]++;
+      cam_perm[j] = slot;
+      cam_pos[slot] = j;
+    }
   }
 
-  ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ngroups = std::max(ngroups, 0);
-  ctx->sorted_input = sorted;
+  ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ntiles = ntiles; ctx->Mp = Mp; ctx->lmax = lmax;
   CKR(upload(ctx, ctx->obs_cam, obs_cam));
-  CKR(upload(ctx, ctx->obs_line, obs_line));
+  CKR(upload(ctx, ctx->obs_ll, obs_ll));
   CKR(upload(ctx, ctx->cam_pos, cam_pos));
   CKR(upload(ctx, ctx->cam_perm, cam_perm));
   CKR(upload(ctx, ctx->cam_ptr, cam_ptr));
-  CKR(upload(ctx, ctx->line_ptr, line_ptr));
-  CKR(upload(ctx, ctx->group_line, group_line));
-  if (!sorted) CKR(upload(ctx, ctx->orig_of, orig_of));
+  CKR(upload(ctx, ctx->slot_src, slot_src));
+  CKR(upload(ctx, ctx->meta, meta));
 
-  // observation constants: AoS (m,3) -> SoA, m_e = n x p_e
-  CKR(ctx->cst.alloc((size_t)9 * m));
+  // observation constants: AoS (m,3) -> SoA over slots, m_e = n x p_e
+  CKR(ctx->cst.alloc((size_t)9 * Mp));
   if (m > 0) {
     DBuf<double> tmp;
     const double* src[3] = {n, p0, p1};
@@ -431,20 +460,44 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       dev[k] = tmp.p + off;
       off += (size_t)3 * m;
     }
-    LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(m, 256), 256, m, sorted ? nullptr : ctx->orig_of.p, dev[0], dev[1], dev[2], ctx->cst.p);
+    LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(Mp, 256), 256, Mp, ctx->slot_src.p, dev[0], dev[1], dev[2], ctx->cst.p);
     CK(cudaStreamSynchronize(ctx->stream));  // tmp and the host vectors go out of scope
   } else {
     CK(cudaStreamSynchronize(ctx->stream));
   }
 
+  // persistent grids: SMs x resident CTAs for each pipelined kernel at this problem's stage size
+  {
+    auto plan = [&](auto kern, int smem, int* grid) -> int {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTile, (size_t)smem));
+      if (nb < 1) return fail(LBA_ERR_UNSUPPORTED, "line-order kernel does not fit on an SM (%d B shared memory)", smem);
+      *grid = std::max(1, std::min(ntiles, nb * ctx->n_sm));
+      return LBA_OK;
+    };
+    ctx->smem_eval_j = eval_smem_bytes(lmax, true);
+    ctx->smem_eval_r = eval_smem_bytes(lmax, false);
+    CKR(plan(k_eval<true>, ctx->smem_eval_j, &ctx->grid_eval_j));
+    CKR(plan(k_eval<false>, ctx->smem_eval_r, &ctx->grid_eval_r));
+    ctx->smem_lp[0] = lp_smem_bytes(lmax, kModeMatvec);
+    ctx->smem_lp[1] = lp_smem_bytes(lmax, kModeBacksub);
+    ctx->smem_lp[2] = lp_smem_bytes(lmax, kModeScalars);
+    CKR(plan(k_line_pass<kModeMatvec>, ctx->smem_lp[0], &ctx->grid_lp[0]));
+    CKR(plan(k_line_pass<kModeBacksub>, ctx->smem_lp[1], &ctx->grid_lp[1]));
+    CKR(plan(k_line_pass<kModeScalars>, ctx->smem_lp[2], &ctx->grid_lp[2]));
+  }
+
   // state buffers
-  const size_t M = (size_t)m, NC = (size_t)nc, NL = (size_t)nl, NG = (size_t)ctx->ngroups;
+  const size_t M = (size_t)Mp, NC = (size_t)nc, NL = (size_t)nl;
+  const size_t NG = (size_t)std::max({ctx->grid_eval_j, ctx->grid_eval_r, ctx->grid_lp[1], 1});
   CKR(ctx->cams.alloc(NC * 6)); CKR(ctx->cams_new.alloc(NC * 6)); CKR(ctx->api_tmp.alloc(std::max(NC * 6, (size_t)1)));
-  CKR(ctx->pts.alloc(NL * 6)); CKR(ctx->pts_new.alloc(NL * 6));
+  CKR(ctx->pts.alloc(NL * 6 + 2)); CKR(ctx->pts_new.alloc(NL * 6 + 2));
   CKR(ctx->Gm.alloc(NC * 9)); CKR(ctx->recs.alloc(NC)); CKR(ctx->recs_new.alloc(NC));
-  CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * M));
-  CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M));
-  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6)); CKR(ctx->Vinv.alloc(NL * 21)); CKR(ctx->y.alloc(NL * 6)); CKR(ctx->Dl.alloc(NL * 6));
+  CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * (size_t)m));
+  CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M)); CKR(ctx->dense_tmp.alloc((size_t)m));
+  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
+  CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6));
   CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
   CKR(ctx->Mpart.alloc(NC * 27)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
   CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
@@ -462,12 +515,19 @@ static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc *
 
 static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
   EvalArgs a;
-  a.m = c->m; a.group_line = c->group_line.p; a.line_ptr = c->line_ptr.p; a.obs_cam = c->obs_cam.p;
-  a.obs_line = c->obs_line.p; a.cam_pos = c->cam_pos.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
-  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p; a.cost_partial = c->cost_partial.p;
-  a.proj = nullptr; a.orig_of = c->sorted_input ? nullptr : c->orig_of.p;
+  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.meta = c->meta.p; a.obs_cam = c->obs_cam.p;
+  a.obs_ll = c->obs_ll.p; a.cam_pos = c->cam_pos.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
+  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.m = (size_t)c->m; a.V = c->V.p; a.gl = c->gl.p;
+  a.cost_partial = c->cost_partial.p;
   return a;
 }
+
+#define LAUNCH_DYN(ctx, cls, kern, grid, block, smem, ...)            \
+  do {                                                                \
+    (ctx)->pre(cls);                                                  \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->post(cls);                                                 \
+  } while (0)
 
 static int load_state(lba_ctx* c, const double* cams_api, const double* pts_api) {
   if (!c->have_problem) return fail(LBA_ERR_STATE, "lba_set_problem has not been called");
@@ -494,21 +554,25 @@ static int store_state(lba_ctx* c, double* cams_api, double* pts_api) {
 
 // residual-only pass at (recs, pts) -> r_out, scal.cost (all-reduced)
 static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, double* r_out) {
-  if (c->ngroups > 0) {
+  int ng = 0;
+  if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, recs, pts, r_out);
-    LAUNCH(c, LBA_K_RESIDUAL, k_eval<false>, c->ngroups, kTile, a);
+    ng = c->grid_eval_r;
+    LAUNCH_DYN(c, LBA_K_RESIDUAL, k_eval<false>, ng, kTile, c->smem_eval_r, a);
   }
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ng, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
   return LBA_OK;
 }
 
 // fused residual + Jacobian + line blocks at the current state -> r, jl, jc, V, gl, scal.cost
 static int run_jacobian(lba_ctx* c) {
-  if (c->ngroups > 0) {
+  int ng = 0;
+  if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, c->recs.p, c->pts.p, c->r.p);
-    LAUNCH(c, LBA_K_JACOBIAN, k_eval<true>, c->ngroups, kTile, a);
+    ng = c->grid_eval_j;
+    LAUNCH_DYN(c, LBA_K_JACOBIAN, k_eval<true>, ng, kTile, c->smem_eval_j, a);
   }
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ng, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
   c->have_eval = true;
   c->have_blocks = false;
   return LBA_OK;
@@ -517,7 +581,7 @@ static int run_jacobian(lba_ctx* c) {
 // camera blocks U_c, g_c (+ all-reduce), Marquardt scaling, gradient inf-norm
 static int run_blocks(lba_ctx* c, bool update_scaling) {
   if (c->nc > 0) {
-    LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+    LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, (size_t)c->m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
            (const double*)nullptr, c->r.p, c->U.p, gc_of(c));
     CKR(allreduce_sum(c, c->U.p, (size_t)c->nc * 27));
     CK(cudaMemcpyAsync(c->gc.p, gc_of(c), (size_t)c->nc * 48, cudaMemcpyDeviceToDevice, c->stream));
@@ -543,10 +607,16 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   const int nc = c->nc, nl = c->nl, m = c->m;
   if (nl > 0)
     LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, 128), 128, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p);
-  if (m > 0)
-    LAUNCH(c, LBA_K_LINE_SCALARS, k_line_scalars, cdiv(m, 256), 256, m, c->obs_line.p, c->jl.p, c->Vinv.p, c->y.p, c->wk.p, c->wr.p);
+  LinePassArgs la;
+  la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.meta = c->meta.p; la.obs_cam = c->obs_cam.p;
+  la.obs_ll = c->obs_ll.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
+  la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p;
+  la.partial = c->bs_partial.p; la.st = c->cgst.p;
+  if (c->ntiles > 0)
+    LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
+  la.w = c->w.p;
   if (nc > 0) {
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, (size_t)m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
            (const double*)c->wk.p, c->wr.p, c->Mpart.p, bpart_of(c));
     CKR(allreduce_sum(c, c->Mpart.p, (size_t)nc * 27));
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
@@ -557,17 +627,12 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
   LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_init, 1, kCgThreads, ca);
 
-  LinePassArgs la;
-  la.m = m; la.group_line = c->group_line.p; la.line_ptr = c->line_ptr.p; la.obs_cam = c->obs_cam.p;
-  la.obs_line = c->obs_line.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
-  la.w = c->w.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p; la.partial = c->bs_partial.p; la.st = c->cgst.p;
-
   int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
   int issued = 0;
   while (true) {
     for (int q = 0; q < chunk && issued < pcg_max_iter; ++q, ++issued) {
-      if (c->ngroups > 0) LAUNCH(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->ngroups, kTile, la);
-      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, m, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
+      if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], la);
+      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, (size_t)m, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
       CKR(allreduce_sum(c, c->qpart.p, (size_t)nc * 6));
       LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_update, 1, kCgThreads, ca);
     }
@@ -582,8 +647,14 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
 
   // back-substitution and candidate point
   if (nc > 0) LAUNCH(c, LBA_K_MISC, k_make_table, cdiv(nc, 128), 128, nc, c->Gm.p, c->cams.p, c->cgx.p, c->tab.p);
-  if (c->ngroups > 0) LAUNCH(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->ngroups, kTile, la);
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, c->ngroups, 4, c->bs_partial.p, &c->scal.p->rjd, 1.0);
+  int ngb = 0;
+  if (c->ntiles > 0) {
+    ngb = c->grid_lp[1];
+    LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, ngb, kTile, c->smem_lp[1], la);
+  } else if (nl > 0) {
+    CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)nl * 48, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ngb, 4, c->bs_partial.p, &c->scal.p->rjd, 1.0);
   LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, nc, c->cams.p, c->cgx.p, c->cams_new.p, &c->scal.p->dc2, &c->scal.p->x2_cams);
   return LBA_OK;
 }
@@ -605,13 +676,9 @@ static double gnorm_host(lba_ctx* c) {
 
 static int export_residuals(lba_ctx* c, const double* r_dev, double* out) {
   if (!out || c->m == 0) return LBA_OK;
-  if (c->sorted_input) {
-    CK(cudaMemcpyAsync(out, r_dev, (size_t)c->m * 8, cudaMemcpyDefault, c->stream));
-  } else {
-    // un-sort into the caller's observation order (w is free outside the PCG loop)
-    LAUNCH(c, LBA_K_MISC, k_scatter_to_caller_order, cdiv(c->m, 256), 256, c->m, c->orig_of.p, r_dev, c->w.p);
-    CK(cudaMemcpyAsync(out, c->w.p, (size_t)c->m * 8, cudaMemcpyDefault, c->stream));
-  }
+  // slot order -> the caller's observation order
+  LAUNCH(c, LBA_K_MISC, k_slots_to_caller, cdiv(c->Mp, 256), 256, c->Mp, c->slot_src.p, r_dev, c->dense_tmp.p);
+  CK(cudaMemcpyAsync(out, c->dense_tmp.p, (size_t)c->m * 8, cudaMemcpyDefault, c->stream));
   return LBA_OK;
 }
 
@@ -624,8 +691,8 @@ extern "C" int lba_point_wise_indices(lba_ctx* ctx, int64_t* cam_pt, int64_t* pt
   if (m == 0) return LBA_OK;
   DBuf<long long> tmp;
   CKR(tmp.alloc((size_t)4 * m));
-  LAUNCH(ctx, LBA_K_MISC, k_point_wise_indices, cdiv(m, 256), 256, m, ctx->sorted_input ? nullptr : ctx->orig_of.p,
-         ctx->obs_cam.p, ctx->obs_line.p, tmp.p, tmp.p + (size_t)2 * m);
+  LAUNCH(ctx, LBA_K_MISC, k_point_wise_indices, cdiv(ctx->Mp, 256), 256, ctx->Mp, ctx->slot_src.p, ctx->obs_cam.p,
+         ctx->obs_ll.p, ctx->meta.p, tmp.p, tmp.p + (size_t)2 * m);
   CK(cudaMemcpyAsync(cam_pt, tmp.p, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(pt_idx, tmp.p + (size_t)2 * m, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -640,9 +707,10 @@ extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, 
   if (m == 0) return LBA_OK;
   DBuf<double> tmp;
   CKR(tmp.alloc((size_t)6 * m));
-  EvalArgs a = eval_args(ctx, ctx->recs.p, ctx->pts.p, ctx->r.p);
-  a.proj = tmp.p;
-  LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(m, 256), 256, a);
+  ProjectArgs a;
+  a.Mp = ctx->Mp; a.slot_src = ctx->slot_src.p; a.obs_cam = ctx->obs_cam.p; a.obs_ll = ctx->obs_ll.p;
+  a.meta = ctx->meta.p; a.recs = ctx->recs.p; a.pts = ctx->pts.p; a.proj = tmp.p;
+  LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(ctx->Mp, 256), 256, a);
   CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
@@ -670,7 +738,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
     if (!jcam || !jline) return fail(LBA_ERR_ARG, "jcam and jline must both be given or both be NULL");
     DBuf<double> tmp;
     CKR(tmp.alloc((size_t)12 * m));
-    LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(m, 256), 256, m, ctx->sorted_input ? nullptr : ctx->orig_of.p,
+    LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(ctx->Mp, 256), 256, ctx->Mp, (size_t)m, ctx->slot_src.p,
            ctx->cam_pos.p, ctx->jl.p, ctx->jc.p, tmp.p, tmp.p + (size_t)6 * m);
     CK(cudaMemcpyAsync(jcam, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaMemcpyAsync(jline, tmp.p + (size_t)6 * m, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));

@@ -1,32 +1,85 @@
 // Hand-written sm_100a kernels for the line bundle-adjustment hot path.
 //
-// Data layout in HBM (all fp64 / int32, structure-of-arrays over observations):
-//   line order  (observations sorted by 3D line, the reference's own order,
-//                seq_utils.py:188-195):  cst[9][m] = n, m0 = n x p0, m1 = n x p1;
-//                obs_cam[m], obs_line[m], cam_pos[m]; r[m]; jl[6][m]; w[m] ...
-//   camera order (stable counting sort of the same observations by camera):
-//                jc[6][m]; cam_perm[m] (camera-order slot -> line-order index);
-//                cam_ptr[Nc+1]
-//   per line:    pts[Nl][6] = [X0,X1]; V[Nl][21]; gl[Nl][6]; Vinv[Nl][21]; y[Nl][6]; Dl[Nl][6]
-//   per camera:  cams[Nc][6] = [w,c]; CamRec[Nc]; G[Nc][9]; U[Nc][21]; gc[Nc][6]; Dc[Nc][6];
-//                Minv[Nc][21]; CG vectors [Nc][6]; tab[Nc][6]
+// Data layout in HBM (all fp64 / int32, structure-of-arrays over observations)
+// -------------------------------------------------------------------------
+// LINE ORDER, tile-aligned "slots".  Observations are sorted by 3D line (the reference's own
+//   order, seq_utils.py:188-195) and packed into tiles of kTile = 256 slots; a tile holds whole
+//   lines only (<= kMaxLinesPerTile), the unused tail slots are padding (obs_cam = -1).  Every
+//   per-observation array has Mp = ntiles*256 entries, so tile g of any array is the aligned
+//   2 KB block [g*256, (g+1)*256) and can be moved by ONE bulk-async copy (TMA, cp.async.bulk):
+//     cst[9][Mp] = n, m0 = n x p0, m1 = n x p1;  obs_cam[Mp]; obs_ll[Mp] (local line id, u8);
+//     cam_pos[Mp]; r[Mp]; jl[6][Mp]; w[Mp]; wk[Mp]; wr[Mp];  TileMeta[ntiles]
+// CAMERA ORDER (stable counting sort of the same observations by camera), dense m entries:
+//     jc[6][m]; cam_perm[m] (camera-order position -> slot); cam_ptr[Nc+1]
+// per line:   pts[Nl][6] = [X0,X1]; V[Nl][21]; gl[Nl][6]; Vinv[Nl][22] (21 + pad: 16 B aligned
+//             rows); y[Nl][6]; Dl[Nl][6]
+// per camera: cams[Nc][6] = [w,c]; CamRec[Nc]; G[Nc][9]; U[Nc][21]; gc[Nc][6]; Dc[Nc][6];
+//             Minv[Nc][21]; CG vectors [Nc][6]; tab[Nc][6]
 //
-// Each residual is a scalar, so a Jacobian row is (jc_i in R^6, jl_i in R^6) and every
-// coupling block W_{c,l} = jc_i jl_i^T is rank one: only ONE scalar per observation
-// (s_i, w_i) ever crosses between the line-ordered and the camera-ordered halves of a
-// pass.  Line-side reductions are segmented sums over contiguous runs inside one CTA
-// tile ("group" = whole lines, <= 256 observations) staged in shared memory; camera-side
-// reductions run one CTA per camera over the camera-ordered copy with warp-shuffle
-// reductions.  No atomics on the data path: every sum has a fixed order, so results
-// are bit-reproducible run to run.
+// Each residual is a scalar, so a Jacobian row is (jc_i in R^6, jl_i in R^6) and every coupling
+// block W_{c,l} = jc_i jl_i^T is rank one: only ONE scalar per observation (s_i, w_i) ever
+// crosses between the line-ordered and the camera-ordered halves of a pass.
+//
+// Execution model
+// ---------------
+// Line-ordered kernels are persistent CTAs (grid = SMs x resident CTAs) that walk the tiles with
+// a 3-stage bulk-async (TMA) -> shared-memory pipeline synchronised by mbarriers: one elected
+// thread issues the copies for tile t+3 while the 8 warps work on tile t, so HBM latency is
+// covered by bytes in flight rather than by occupancy.  Segmented (per-line) sums run on the
+// staged tile in shared memory with warp shuffles; camera-side sums run one CTA per camera over
+// the camera-ordered copy with warp-shuffle reductions.  There are no floating-point atomics:
+// every sum has a fixed order, so results are bit-reproducible run to run.
 #pragma once
 #include "lba_geometry.cuh"
+#include <stdint.h>
 
 namespace lba {
 
-constexpr int kTile = 256;      // threads per line-order CTA == max observations per group
+constexpr int kTile = 256;             // slots per tile == threads per line-order CTA
+constexpr int kMaxLinesPerTile = 128;
+constexpr int kStages = 3;      // k_eval pipeline depth (2 CTAs/SM)
+constexpr int kLpStages = 2;    // k_line_pass pipeline depth (3 CTAs/SM)
 constexpr int kCamThreads = 128;
 constexpr int kCgThreads = 1024;
+constexpr int kVinvStride = 22;        // 21 packed entries + 1 pad -> 176 B rows (16 B aligned)
+
+struct __align__(16) TileMeta {
+  int l0;      // first global line of the tile
+  int nl;      // lines in the tile
+  int nobs;    // real observations (slots [0,nobs) are used)
+  int pad;
+  unsigned short lend[kMaxLinesPerTile];  // exclusive end slot of local line ll (start = lend[ll-1] or 0)
+};
+static_assert(sizeof(TileMeta) % 16 == 0, "TileMeta must be bulk-copyable");
+
+// ---- bulk-async (TMA) + mbarrier primitives ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; 16 B aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -34,7 +87,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Deterministic block sum; result valid in thread 0 (and broadcast through smem slot).
+// Deterministic block sum, returned to every thread.
 template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/32 doubles */) {
   v = warp_sum(v);
@@ -72,18 +125,24 @@ __device__ __forceinline__ void load6(const double* __restrict__ p, double v[6])
 // setup kernels
 // ---------------------------------------------------------------------------------
 
-// AoS (m,3) n/p0/p1 in caller order -> SoA cst[9][m] in line order, with m_e = n x p_e
+// AoS (m,3) n/p0/p1 in caller order -> SoA cst[9][Mp] in slot order, with m_e = n x p_e
 // (np.cross at bundle_adjustment.py:126,133, hoisted out of the evaluation loop).
-__global__ void k_setup_constants(int m, const int* __restrict__ orig_of, const double* __restrict__ n,
+__global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, const double* __restrict__ n,
                                   const double* __restrict__ p0, const double* __restrict__ p1,
                                   double* __restrict__ cst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const size_t s = orig_of ? (size_t)orig_of[i] : (size_t)i;
+  if (i >= Mp) return;
+  const int src = slot_src[i];
+  const size_t M = (size_t)Mp;
+  if (src < 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cst[(size_t)k * M + i] = 0.0;
+    return;
+  }
+  const size_t s = (size_t)src;
   const double nx = n[3 * s], ny = n[3 * s + 1], nz = n[3 * s + 2];
   const double ax = p0[3 * s], ay = p0[3 * s + 1], az = p0[3 * s + 2];
   const double bx = p1[3 * s], by = p1[3 * s + 1], bz = p1[3 * s + 2];
-  const size_t M = (size_t)m;
   cst[0 * M + i] = nx; cst[1 * M + i] = ny; cst[2 * M + i] = nz;
   cst[3 * M + i] = ny * az - nz * ay; cst[4 * M + i] = nz * ax - nx * az; cst[5 * M + i] = nx * ay - ny * ax;
   cst[6 * M + i] = ny * bz - nz * by; cst[7 * M + i] = nz * bx - nx * bz; cst[8 * M + i] = nx * by - ny * bx;
@@ -120,13 +179,15 @@ __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* _
 }
 
 // point_wise_input (:235-243) integer expansion, in the caller's observation order.
-__global__ void k_point_wise_indices(int m, const int* __restrict__ orig_of, const int* __restrict__ obs_cam,
-                                     const int* __restrict__ obs_line, long long* __restrict__ cam_pt,
-                                     long long* __restrict__ pt_idx) {
+__global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, const int* __restrict__ obs_cam,
+                                     const unsigned char* __restrict__ obs_ll, const TileMeta* __restrict__ meta,
+                                     long long* __restrict__ cam_pt, long long* __restrict__ pt_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const size_t o = orig_of ? (size_t)orig_of[i] : (size_t)i;
-  const long long c = obs_cam[i], l = obs_line[i];
+  if (i >= Mp) return;
+  const int src = slot_src[i];
+  if (src < 0) return;
+  const size_t o = (size_t)src;
+  const long long c = obs_cam[i], l = meta[i / kTile].l0 + obs_ll[i];
   cam_pt[2 * o] = c; cam_pt[2 * o + 1] = c;
   pt_idx[2 * o] = 2 * l; pt_idx[2 * o + 1] = 2 * l + 1;
 }
@@ -135,120 +196,191 @@ __global__ void k_point_wise_indices(int m, const int* __restrict__ orig_of, con
 // K1/K2/K3 (line side): residuals, Jacobian rows, per-line blocks V_l, g_l
 // ---------------------------------------------------------------------------------
 struct EvalArgs {
-  int m;
-  const int* group_line;   // [ngroups+1] first line of each group
-  const int* line_ptr;     // [nl+1]
+  int Mp, ntiles, lmax;    // lmax: max lines per tile rounded up to 8 (sizes the smem stage)
+  const TileMeta* meta;
   const int* obs_cam;
-  const int* obs_line;
+  const unsigned char* obs_ll;
   const int* cam_pos;
-  const double* cst;       // [9][m]
+  const double* cst;       // [9][Mp]
   const CamRec* recs;
   const double* pts;       // [nl][6]
-  double* r;               // [m]
-  double* jl;              // [6][m] line order
+  double* r;               // [Mp]
+  double* jl;              // [6][Mp] slot order
   double* jc;              // [6][m] camera order
+  size_t m;                // stride of jc
   double* V;               // [nl][21]
   double* gl;              // [nl][6]
-  double* cost_partial;    // [ngroups]
-  double* proj;            // optional (2m,3) p_hat output in caller order (lba_project)
-  const int* orig_of;
+  double* cost_partial;    // [gridDim]
 };
 
 __constant__ int c_sym_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ int c_sym_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
-constexpr int kStagePad = kTile + 2;  // row stride of the smem staging rows (bank spread)
+// shared-memory stage of k_eval: cst[9][256] | cam[256] | cam_pos[256] | ll[256] | meta | pts[lmax][6]
+constexpr int kEvOffCam = 9 * kTile * 8;
+constexpr int kEvOffPos = kEvOffCam + kTile * 4;
+constexpr int kEvOffLl = kEvOffPos + kTile * 4;
+constexpr int kEvOffMeta = kEvOffLl + kTile;
+constexpr int kEvOffPts = kEvOffMeta + (int)sizeof(TileMeta);
+__host__ __device__ inline int eval_stage_bytes(int lmax) { return (kEvOffPts + lmax * 48 + 127) & ~127; }
+constexpr int kEvRow = 9;  // staging row stride in doubles: (jl[6], r, pad) -> 72 B, conflict-free per half-warp
+__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac) {
+  return kStages * eval_stage_bytes(lmax) + (with_jac ? kTile * kEvRow * 8 : 0) + 128;
+}
 
 template <bool WITH_JAC>
-__global__ void __launch_bounds__(kTile, WITH_JAC ? 2 : 3) k_eval(const EvalArgs a) {
+__global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kTile / 32];
-  __shared__ double stage[WITH_JAC ? 7 * kStagePad : 1];
-  const int g = blockIdx.x;
-  const int l0 = a.group_line[g], l1 = a.group_line[g + 1];
-  const int o0 = a.line_ptr[l0], o1 = a.line_ptr[l1];
-  const int i = o0 + threadIdx.x;
-  const bool active = i < o1;
-  const size_t M = (size_t)a.m;
-  double r = 0.0;
-  double jl[6] = {0, 0, 0, 0, 0, 0};
-  if (active) {
-    const int cam = a.obs_cam[i];
-    const int line = a.obs_line[i];
-    double n[3], m0[3], m1[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      n[k] = __ldg(a.cst + (size_t)k * M + i);
-      m0[k] = __ldg(a.cst + (size_t)(3 + k) * M + i);
-      m1[k] = __ldg(a.cst + (size_t)(6 + k) * M + i);
-    }
-    double w[3], c[3], A, B, C;
-    load_camrec(a.recs, cam, w, c, A, B, C);
-    double X[6];
-    load6(a.pts + (size_t)line * 6, X);
-    double R[9];
-    build_R(w, A, B, R);
-    double tq[3] = {0, 0, 0};
-    const double e0 = endpoint_term<WITH_JAC>(R, c, X, n, m0, jl, tq);
-    const double e1 = endpoint_term<WITH_JAC>(R, c, X + 3, n, m1, jl + 3, tq);
-    r = e0 + e1;
-    a.r[i] = r;
-    if (WITH_JAC) {
-      double G[9];
-      build_G(w, B, C, G);
-      const int pos = a.cam_pos[i];
-      // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1)
-      a.jc[0 * M + pos] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
-      a.jc[1 * M + pos] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
-      a.jc[2 * M + pos] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
-      a.jc[3 * M + pos] = -(jl[0] + jl[3]);
-      a.jc[4 * M + pos] = -(jl[1] + jl[4]);
-      a.jc[5 * M + pos] = -(jl[2] + jl[5]);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a.jl[(size_t)k * M + i] = jl[k];
-    }
+  __shared__ uint64_t full[kStages];
+  const int stage_bytes = eval_stage_bytes(a.lmax);
+  double* s_stg = reinterpret_cast<double*>(smem + (size_t)kStages * stage_bytes);  // [256][kEvRow], WITH_JAC only
+  const size_t M = (size_t)a.Mp;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  const int t = threadIdx.x;
+
+  if (t == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
   }
-  if (WITH_JAC) {
+  __syncthreads();
+
+  auto issue = [&](int it, int nl, int l0) {
+    const int tile = first + it * stride;
+    unsigned char* st = smem + (size_t)(it % kStages) * stage_bytes;
+    uint64_t* bar = &full[it % kStages];
+    const uint32_t bytes = 9 * kTile * 8 + kTile * 4 + (WITH_JAC ? kTile * 4 : 0) + kTile + (uint32_t)sizeof(TileMeta) + nl * 48;
+    mbar_expect_tx(bar, bytes);
+    const size_t o = (size_t)tile * kTile;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) stage[k * kStagePad + threadIdx.x] = jl[k];
-    stage[6 * kStagePad + threadIdx.x] = r;
+    for (int k = 0; k < 9; ++k) bulk_g2s(st + k * kTile * 8, a.cst + (size_t)k * M + o, kTile * 8, bar);
+    bulk_g2s(st + kEvOffCam, a.obs_cam + o, kTile * 4, bar);
+    if (WITH_JAC) bulk_g2s(st + kEvOffPos, a.cam_pos + o, kTile * 4, bar);
+    bulk_g2s(st + kEvOffLl, a.obs_ll + o, kTile, bar);
+    bulk_g2s(st + kEvOffMeta, a.meta + tile, sizeof(TileMeta), bar);
+    if (nl > 0) bulk_g2s(st + kEvOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
+  };
+  // thread 0 keeps (l0, nl) of the tile it will issue next in registers, one iteration ahead
+  int nx_l0 = 0, nx_nl = 0;
+  if (t == 0) {
+    for (int it = 0; it < kStages && it < my_n; ++it) {
+      const TileMeta* mt = a.meta + first + it * stride;
+      issue(it, mt->nl, mt->l0);
+    }
+    if (kStages < my_n) { const TileMeta* mt = a.meta + first + kStages * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
   }
-  const double cs = block_sum<kTile>(r * r, red);  // contains the barrier that publishes `stage`
-  if (threadIdx.x == 0) a.cost_partial[g] = cs;
-  if (WITH_JAC) {
-    // segmented sums: one work item per (line of the group, block entry); fixed order.
-    const int nwork = (l1 - l0) * 27;
-    for (int wi = threadIdx.x; wi < nwork; wi += kTile) {
-      const int ll = wi / 27, e = wi - ll * 27;
-      const int line = l0 + ll;
-      const int s0 = a.line_ptr[line] - o0, s1 = a.line_ptr[line + 1] - o0;
-      double acc = 0.0;
-      if (e < 21) {
-        const double* ra = stage + c_sym_a[e] * kStagePad;
-        const double* rb = stage + c_sym_b[e] * kStagePad;
-        for (int s = s0; s < s1; ++s) acc += ra[s] * rb[s];
-        a.V[(size_t)line * 21 + e] = acc;
-      } else {
-        const double* ra = stage + (e - 21) * kStagePad;
-        const double* rr = stage + 6 * kStagePad;
-        for (int s = s0; s < s1; ++s) acc += ra[s] * rr[s];
-        a.gl[(size_t)line * 6 + (e - 21)] = acc;
+
+  double cost_acc = 0.0;
+  for (int it = 0; it < my_n; ++it) {
+    const int tile = first + it * stride;
+    unsigned char* st = smem + (size_t)(it % kStages) * stage_bytes;
+    double* s_cst = reinterpret_cast<double*>(st);
+    const int* s_cam = reinterpret_cast<const int*>(st + kEvOffCam);
+    const int* s_pos = reinterpret_cast<const int*>(st + kEvOffPos);
+    const unsigned char* s_ll = st + kEvOffLl;
+    const TileMeta* s_meta = reinterpret_cast<const TileMeta*>(st + kEvOffMeta);
+    const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
+    int cur_l0 = 0, cur_nl = 0;
+    if (t == 0 && it + kStages + 1 < my_n) {  // prefetch the scalars for the issue after next
+      const TileMeta* mt = a.meta + first + (it + kStages + 1) * stride;
+      cur_l0 = mt->l0; cur_nl = mt->nl;
+    }
+    mbar_wait(&full[it % kStages], (it / kStages) & 1);
+
+    const int cam = s_cam[t];
+    const bool active = cam >= 0;
+    const size_t i = (size_t)tile * kTile + t;
+    double r = 0.0;
+    double jl[6] = {0, 0, 0, 0, 0, 0};
+    if (active) {
+      double n[3], m0[3], m1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        n[k] = s_cst[k * kTile + t];
+        m0[k] = s_cst[(3 + k) * kTile + t];
+        m1[k] = s_cst[(6 + k) * kTile + t];
+      }
+      double w[3], c[3], A, B, C;
+      load_camrec(a.recs, cam, w, c, A, B, C);
+      const double* X = s_pts + (int)s_ll[t] * 6;
+      double X0[3] = {X[0], X[1], X[2]}, X1[3] = {X[3], X[4], X[5]};
+      double R[9];
+      build_R(w, A, B, R);
+      double tq[3] = {0, 0, 0};
+      const double e0 = endpoint_term<WITH_JAC>(R, c, X0, n, m0, jl, tq);
+      const double e1 = endpoint_term<WITH_JAC>(R, c, X1, n, m1, jl + 3, tq);
+      r = e0 + e1;
+      if (WITH_JAC) {
+        double G[9];
+        build_G(w, B, C, G);
+        const size_t pos = (size_t)s_pos[t];
+        // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1)
+        a.jc[0 * a.m + pos] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
+        a.jc[1 * a.m + pos] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
+        a.jc[2 * a.m + pos] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
+        a.jc[3 * a.m + pos] = -(jl[0] + jl[3]);
+        a.jc[4 * a.m + pos] = -(jl[1] + jl[4]);
+        a.jc[5 * a.m + pos] = -(jl[2] + jl[5]);
       }
     }
+    a.r[i] = r;
+    cost_acc += r * r;
+    if (WITH_JAC) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.jl[(size_t)k * M + i] = jl[k];
+      // stage (jl, r) row-major with an odd-word stride for the per-line segmented sums
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_stg[t * kEvRow + k] = jl[k];
+      s_stg[t * kEvRow + 6] = r;
+      __syncthreads();
+      const int l0 = s_meta->l0, nlg = s_meta->nl;
+      const int nwork = nlg * 27;
+      for (int wi = t; wi < nwork; wi += kTile) {
+        const int ll = wi / 27, e = wi - ll * 27;
+        const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
+        const int ca = e < 21 ? c_sym_a[e] : e - 21, cb = e < 21 ? c_sym_b[e] : 6;
+        double acc = 0.0;
+        for (int s = s0; s < s1; ++s) acc += s_stg[s * kEvRow + ca] * s_stg[s * kEvRow + cb];
+        if (e < 21) a.V[(size_t)(l0 + ll) * 21 + e] = acc;
+        else a.gl[(size_t)(l0 + ll) * 6 + (e - 21)] = acc;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();  // the stage is free: refill it with tile it + kStages
+    if (t == 0) {
+      if (it + kStages < my_n) issue(it + kStages, nx_nl, nx_l0);
+      nx_l0 = cur_l0; nx_nl = cur_nl;
+    }
   }
+  const double cs = block_sum<kTile>(cost_acc, red);
+  if (t == 0) a.cost_partial[blockIdx.x] = cs;
 }
 
 // project(): p_hat rows 2i+e in the caller's observation order (API parity only; cold path)
-__global__ void k_project(const EvalArgs a) {
+struct ProjectArgs {
+  int Mp;
+  const int* slot_src;
+  const int* obs_cam;
+  const unsigned char* obs_ll;
+  const TileMeta* meta;
+  const CamRec* recs;
+  const double* pts;
+  double* proj;
+};
+__global__ void k_project(const ProjectArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.m) return;
-  const int cam = a.obs_cam[i], line = a.obs_line[i];
+  if (i >= a.Mp) return;
+  const int src = a.slot_src[i];
+  if (src < 0) return;
+  const int cam = a.obs_cam[i], line = a.meta[i / kTile].l0 + a.obs_ll[i];
   double w[3], c[3], A, B, C;
   load_camrec(a.recs, cam, w, c, A, B, C);
   double X[6];
   load6(a.pts + (size_t)line * 6, X);
   double R[9];
   build_R(w, A, B, R);
-  const size_t o = a.orig_of ? (size_t)a.orig_of[i] : (size_t)i;
+  const size_t o = (size_t)src;
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const double d0 = X[3 * e] - c[0], d1 = X[3 * e + 1] - c[1], d2 = X[3 * e + 2] - c[2];
@@ -267,7 +399,7 @@ __global__ void k_project(const EvalArgs a) {
 // over the camera-ordered Jacobian copy.  wa == nullptr means weight 1.
 // One CTA per camera; 27 register accumulators per thread, warp-shuffle + smem reduce.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCamThreads) k_cam_accum(int m, const int* __restrict__ cam_ptr,
+__global__ void __launch_bounds__(kCamThreads) k_cam_accum(size_t m, const int* __restrict__ cam_ptr,
                                                             const int* __restrict__ cam_perm,
                                                             const double* __restrict__ jc,
                                                             const double* __restrict__ wa,
@@ -276,7 +408,6 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(int m, const int* __r
   __shared__ double sm[kCamThreads / 32][27];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
-  const size_t M = (size_t)m;
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
@@ -284,7 +415,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(int m, const int* __r
     const int i = cam_perm[j];
     double x[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = __ldg(jc + (size_t)k * M + j);
+    for (int k = 0; k < 6; ++k) x[k] = __ldg(jc + (size_t)k * m + j);
     const double a = wa ? __ldg(wa + i) : 1.0;
     const double b = __ldg(wb + i);
     int e = 0;
@@ -347,38 +478,10 @@ __global__ void __launch_bounds__(128) k_line_factor(int nl, double lam, const d
   for (int k = 0; k < 6; ++k) g[k] = gl[(size_t)l * 6 + k];
   sym6_matvec(S, g, yy);
 #pragma unroll
-  for (int e = 0; e < 21; ++e) Vinv[(size_t)l * 21 + e] = S[e];
+  for (int e = 0; e < 21; ++e) Vinv[(size_t)l * kVinvStride + e] = S[e];
+  Vinv[(size_t)l * kVinvStride + 21] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) y[(size_t)l * 6 + k] = yy[k];
-}
-
-// per observation: wk[i] = 1 - jl_i^T Vinv jl_i (block-Jacobi weight), wr[i] = jl_i . y_l (Schur rhs weight)
-__global__ void __launch_bounds__(256) k_line_scalars(int m, const int* __restrict__ obs_line,
-                                                       const double* __restrict__ jl, const double* __restrict__ Vinv,
-                                                       const double* __restrict__ y, double* __restrict__ wk,
-                                                       double* __restrict__ wr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const size_t M = (size_t)m;
-  const int l = obs_line[i];
-  double x[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) x[k] = __ldg(jl + (size_t)k * M + i);
-  const double* S = Vinv + (size_t)l * 21;
-  double q = 0.0;
-  int e = 0;
-#pragma unroll
-  for (int p = 0; p < 6; ++p) {
-    q += __ldg(S + e) * x[p] * x[p];
-    ++e;
-#pragma unroll
-    for (int s = p + 1; s < 6; ++s) { q += 2.0 * __ldg(S + e) * x[p] * x[s]; ++e; }
-  }
-  double d = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) d += x[k] * __ldg(y + (size_t)l * 6 + k);
-  wk[i] = 1.0 - q;
-  wr[i] = d;
 }
 
 // per camera: Minv = (lam Dc + Mpart)^-1 (block-Jacobi), b = -gc + bpart (Schur rhs)
@@ -433,134 +536,239 @@ __global__ void k_make_table(int nc, const double* __restrict__ Gm, const double
 }
 
 struct LinePassArgs {
-  int m;
-  const int* group_line;
-  const int* line_ptr;
+  int Mp, ntiles, lmax;
+  const TileMeta* meta;
   const int* obs_cam;
-  const int* obs_line;
-  const double* jl;      // [6][m]
+  const unsigned char* obs_ll;
+  const double* jl;      // [6][Mp]
   const double* pts;     // [nl][6]
   const double* tab;     // [nc][6]
-  const double* Vinv;    // [nl][21]
-  double* w;             // MATVEC out [m]
+  const double* Vinv;    // [nl][22]
+  double* w;             // MATVEC out [Mp];  SCALARS out: wk
+  double* w2;            // SCALARS out: wr
+  const double* y;       // SCALARS: [nl][6]
   // BACKSUB only
   const double* gl;      // [nl][6]
-  const double* r;       // [m]
+  const double* r;       // [Mp]
   double* pts_new;       // [nl][6]
-  double* partial;       // [ngroups][4]: r.jd, jd.jd, |dl|^2, |pts|^2
+  double* partial;       // [gridDim][4]: r.jd, jd.jd, |dl|^2, |pts|^2
   const CgState* st;     // MATVEC: early exit when done
 };
 
-enum { kModeMatvec = 0, kModeBacksub = 1 };
+enum { kModeMatvec = 0, kModeBacksub = 1, kModeScalars = 2 };
 
-// Line-ordered half of S*p (MATVEC) and the back-substitution (BACKSUB).
+// stage: jl[6][256] | cam[256] | ll[256] | meta | pts[lmax][6] | Vinv[lmax][22] | aux[lmax][6] | r[256]
+//   aux = gl (BACKSUB) or y (SCALARS)
+constexpr int kLpOffCam = 6 * kTile * 8;
+constexpr int kLpOffLl = kLpOffCam + kTile * 4;
+constexpr int kLpOffMeta = kLpOffLl + kTile;
+constexpr int kLpOffPts = kLpOffMeta + (int)sizeof(TileMeta);
+__host__ __device__ inline int lp_off_vinv(int lmax) { return kLpOffPts + lmax * 48; }
+__host__ __device__ inline int lp_off_aux(int lmax) { return lp_off_vinv(lmax) + lmax * kVinvStride * 8; }
+__host__ __device__ inline int lp_off_r(int lmax) { return lp_off_aux(lmax) + lmax * 48; }
+__host__ __device__ inline int lp_stage_bytes(int lmax, int mode) {
+  const int end = mode == kModeMatvec ? lp_off_aux(lmax) : (mode == kModeScalars ? lp_off_r(lmax) : lp_off_r(lmax) + kTile * 8);
+  return (end + 127) & ~127;
+}
+constexpr int kLpRow = 7;  // staging row stride in doubles (6 + pad): 56 B, conflict-free per half-warp
+__host__ __device__ inline int lp_smem_bytes(int lmax, int mode) {
+  return kLpStages * lp_stage_bytes(lmax, mode) + lmax * 48 /* ul */ + (mode == kModeScalars ? 0 : kTile * kLpRow * 8) + 128;
+}
+
+// Line-ordered half of S*p (MATVEC), the back-substitution (BACKSUB) and the per-observation
+// Schur weights (SCALARS).
 //   s_i = jc_i . v_{c_i} (via the table),  t_l = sum_{i in l} jl_i s_i,
 //   MATVEC:  u_l = Vinv_l t_l,           w_i = s_i - jl_i . u_l
 //   BACKSUB: dl  = -Vinv_l (gl_l + t_l), (J delta)_i = s_i + jl_i . dl
+//   SCALARS: wk_i = 1 - jl_i^T Vinv_l jl_i,  wr_i = jl_i . y_l
 template <int MODE>
 __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
-  __shared__ double stage[6 * kStagePad];
-  __shared__ double ul[kTile * 6];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kTile / 32];
+  __shared__ uint64_t full[kLpStages];
   if (MODE == kModeMatvec && a.st->done) return;
-  const int g = blockIdx.x;
-  const int l0 = a.group_line[g], l1 = a.group_line[g + 1];
-  const int o0 = a.line_ptr[l0], o1 = a.line_ptr[l1];
-  const int i = o0 + threadIdx.x;
-  const bool active = i < o1;
-  const size_t M = (size_t)a.m;
-  double jl[6] = {0, 0, 0, 0, 0, 0};
-  double s = 0.0;
-  int ll = 0;
-  if (active) {
-    const int cam = a.obs_cam[i];
-    const int line = a.obs_line[i];
-    ll = line - l0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) jl[k] = __ldg(a.jl + (size_t)k * M + i);
-    double t[6], X[6];
-    load6(a.tab + (size_t)cam * 6, t);
-    load6(a.pts + (size_t)line * 6, X);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double* Xe = X + 3 * e;
-      const double v0 = t[1] * Xe[2] - t[2] * Xe[1] - t[3];
-      const double v1 = t[2] * Xe[0] - t[0] * Xe[2] - t[4];
-      const double v2 = t[0] * Xe[1] - t[1] * Xe[0] - t[5];
-      s += jl[3 * e] * v0 + jl[3 * e + 1] * v1 + jl[3 * e + 2] * v2;
-    }
+  const int stage_bytes = lp_stage_bytes(a.lmax, MODE);
+  double* ul = reinterpret_cast<double*>(smem + (size_t)kLpStages * stage_bytes);
+  double* s_stg = ul + a.lmax * 6;  // [256][kLpRow]
+  const size_t M = (size_t)a.Mp;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  const int t = threadIdx.x;
+  const int off_vinv = lp_off_vinv(a.lmax), off_aux = lp_off_aux(a.lmax), off_r = lp_off_r(a.lmax);
+
+  if (t == 0) {
+    for (int s = 0; s < kLpStages; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
   }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) stage[k * kStagePad + threadIdx.x] = jl[k] * s;
   __syncthreads();
-  // 8 lanes per line: lane b < 6 sums component b, then the 6x6 product by shuffles.
-  {
-    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    const int nlg = l1 - l0;
-    const int rounds = (nlg + (kTile / 8) - 1) / (kTile / 8);
-    for (int rd = 0; rd < rounds; ++rd) {
-      const int lx = rd * (kTile / 8) + grp;
-      const bool have = lx < nlg;
-      const int line = l0 + (have ? lx : 0);
-      double tb = 0.0;
-      if (have && sub < 6) {
-        const int s0 = a.line_ptr[line] - o0, s1 = a.line_ptr[line + 1] - o0;
-        const double* row = stage + sub * kStagePad;
-        for (int q = s0; q < s1; ++q) tb += row[q];
-        if (MODE == kModeBacksub) tb += a.gl[(size_t)line * 6 + sub];
-      }
-      double u = 0.0;
-      const double* S = a.Vinv + (size_t)line * 21;
+
+  auto issue = [&](int it, int nl, int l0) {
+    const int tile = first + it * stride;
+    unsigned char* st = smem + (size_t)(it % kLpStages) * stage_bytes;
+    uint64_t* bar = &full[it % kLpStages];
+    uint32_t bytes = 6 * kTile * 8 + kTile + (uint32_t)sizeof(TileMeta) + nl * kVinvStride * 8;
+    if (MODE != kModeScalars) bytes += kTile * 4 + nl * 48;
+    if (MODE != kModeMatvec) bytes += nl * 48;
+    if (MODE == kModeBacksub) bytes += kTile * 8;
+    mbar_expect_tx(bar, bytes);
+    const size_t o = (size_t)tile * kTile;
 #pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        const double tv = __shfl_sync(0xffffffffu, tb, (threadIdx.x & 24) + b);
-        if (have && sub < 6) u += __ldg(S + sym_idx(sub < b ? sub : b, sub < b ? b : sub)) * tv;
-      }
-      if (have && sub < 6) {
-        if (MODE == kModeBacksub) {
-          u = -u;
-          const double x = a.pts[(size_t)line * 6 + sub];
-          a.pts_new[(size_t)line * 6 + sub] = x + u;
+    for (int k = 0; k < 6; ++k) bulk_g2s(st + k * kTile * 8, a.jl + (size_t)k * M + o, kTile * 8, bar);
+    if (MODE != kModeScalars) bulk_g2s(st + kLpOffCam, a.obs_cam + o, kTile * 4, bar);
+    bulk_g2s(st + kLpOffLl, a.obs_ll + o, kTile, bar);
+    bulk_g2s(st + kLpOffMeta, a.meta + tile, sizeof(TileMeta), bar);
+    if (nl > 0) {
+      if (MODE != kModeScalars) bulk_g2s(st + kLpOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
+      bulk_g2s(st + off_vinv, a.Vinv + (size_t)l0 * kVinvStride, nl * kVinvStride * 8, bar);
+      if (MODE == kModeBacksub) bulk_g2s(st + off_aux, a.gl + (size_t)l0 * 6, nl * 48, bar);
+      if (MODE == kModeScalars) bulk_g2s(st + off_aux, a.y + (size_t)l0 * 6, nl * 48, bar);
+    }
+    if (MODE == kModeBacksub) bulk_g2s(st + off_r, a.r + o, kTile * 8, bar);
+  };
+  int nx_l0 = 0, nx_nl = 0;
+  if (t == 0) {
+    for (int it = 0; it < kLpStages && it < my_n; ++it) {
+      const TileMeta* mt = a.meta + first + it * stride;
+      issue(it, mt->nl, mt->l0);
+    }
+    if (kLpStages < my_n) { const TileMeta* mt = a.meta + first + kLpStages * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
+  }
+
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;  // BACKSUB partial sums
+  for (int it = 0; it < my_n; ++it) {
+    const int tile = first + it * stride;
+    unsigned char* st = smem + (size_t)(it % kLpStages) * stage_bytes;
+    double* s_jl = reinterpret_cast<double*>(st);
+    const int* s_cam = reinterpret_cast<const int*>(st + kLpOffCam);
+    const unsigned char* s_ll = st + kLpOffLl;
+    const TileMeta* s_meta = reinterpret_cast<const TileMeta*>(st + kLpOffMeta);
+    const double* s_pts = reinterpret_cast<const double*>(st + kLpOffPts);
+    const double* s_vinv = reinterpret_cast<const double*>(st + off_vinv);
+    const double* s_aux = reinterpret_cast<const double*>(st + off_aux);
+    const double* s_r = reinterpret_cast<const double*>(st + off_r);
+    int cur_l0 = 0, cur_nl = 0;
+    if (t == 0 && it + kLpStages + 1 < my_n) {
+      const TileMeta* mt = a.meta + first + (it + kLpStages + 1) * stride;
+      cur_l0 = mt->l0; cur_nl = mt->nl;
+    }
+    mbar_wait(&full[it % kLpStages], (it / kLpStages) & 1);
+
+    const size_t i = (size_t)tile * kTile + t;
+    const int nobs = s_meta->nobs;
+    const bool active = t < nobs;
+    const int ll = active ? (int)s_ll[t] : 0;
+    double jl[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) jl[k] = s_jl[k * kTile + t];
+
+    if (MODE == kModeScalars) {
+      double q = 0.0, d = 0.0;
+      if (active) {
+        const double* S = s_vinv + ll * kVinvStride;
+        int e = 0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          q += S[e] * jl[p] * jl[p];
+          ++e;
+#pragma unroll
+          for (int s = p + 1; s < 6; ++s) { q += 2.0 * S[e] * jl[p] * jl[s]; ++e; }
         }
-        ul[lx * 6 + sub] = u;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d += jl[k] * s_aux[ll * 6 + k];
+      }
+      a.w[i] = active ? 1.0 - q : 0.0;
+      a.w2[i] = d;
+    } else {
+      double s = 0.0;
+      if (active) {
+        const int cam = s_cam[t];
+        double tb[6];
+        load6(a.tab + (size_t)cam * 6, tb);
+        const double* X = s_pts + ll * 6;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double* Xe = X + 3 * e;
+          const double v0 = tb[1] * Xe[2] - tb[2] * Xe[1] - tb[3];
+          const double v1 = tb[2] * Xe[0] - tb[0] * Xe[2] - tb[4];
+          const double v2 = tb[0] * Xe[1] - tb[1] * Xe[0] - tb[5];
+          s += jl[3 * e] * v0 + jl[3 * e + 1] * v1 + jl[3 * e + 2] * v2;
+        }
+      }
+      // contributions jl_i s_i staged row-major with an odd-word stride (bank-conflict free)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_stg[t * kLpRow + k] = jl[k] * s;
+      __syncthreads();
+      // 8 lanes per line: lane b < 6 sums component b, then the 6x6 product by shuffles
+      {
+        const int sub = t & 7, grp = t >> 3;
+        const int nlg = s_meta->nl, l0 = s_meta->l0;
+        const int rounds = (nlg + (kTile / 8) - 1) / (kTile / 8);
+        for (int rd = 0; rd < rounds; ++rd) {
+          const int lx = rd * (kTile / 8) + grp;
+          const bool have = lx < nlg && sub < 6;
+          double tv = 0.0;
+          if (have) {
+            const int s0 = lx ? s_meta->lend[lx - 1] : 0, s1 = s_meta->lend[lx];
+            for (int q = s0; q < s1; ++q) tv += s_stg[q * kLpRow + sub];
+            if (MODE == kModeBacksub) tv += s_aux[lx * 6 + sub];
+          }
+          double u = 0.0;
+          const double* S = s_vinv + (have ? lx : 0) * kVinvStride;
+#pragma unroll
+          for (int b = 0; b < 6; ++b) {
+            const double tvb = __shfl_sync(0xffffffffu, tv, (t & 24) + b);
+            if (have) u += S[sym_idx(sub < b ? sub : b, sub < b ? b : sub)] * tvb;
+          }
+          if (have) {
+            if (MODE == kModeBacksub) {
+              u = -u;
+              const double x = s_pts[lx * 6 + sub];
+              a.pts_new[(size_t)(l0 + lx) * 6 + sub] = x + u;
+              p2 += u * u;
+              p3 += x * x;
+            }
+            ul[lx * 6 + sub] = u;
+          }
+        }
+      }
+      __syncthreads();
+      double d = 0.0;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d += jl[k] * ul[ll * 6 + k];
+      }
+      if (MODE == kModeMatvec) {
+        a.w[i] = active ? s - d : 0.0;
+      } else {
+        const double jd = active ? s + d : 0.0;
+        const double rr = active ? s_r[t] : 0.0;
+        p0 += rr * jd;
+        p1 += jd * jd;
       }
     }
-  }
-  __syncthreads();
-  double d = 0.0;
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d += jl[k] * ul[ll * 6 + k];
-  }
-  if (MODE == kModeMatvec) {
-    if (active) a.w[i] = s - d;
-  } else {
-    const double jd = active ? s + d : 0.0;
-    const double rr = active ? __ldg(a.r + i) : 0.0;
-    // per-group partial sums for the model reduction and the step / parameter norms
-    double dl2 = 0.0, x2 = 0.0;
-    const int nlg = l1 - l0;
-    for (int q = threadIdx.x; q < nlg * 6; q += kTile) {
-      const double u = ul[q];
-      const double x = a.pts[(size_t)l0 * 6 + q];
-      dl2 += u * u;
-      x2 += x * x;
+    fence_proxy_async();
+    __syncthreads();  // the stage (and ul) are free
+    if (t == 0) {
+      if (it + kLpStages < my_n) issue(it + kLpStages, nx_nl, nx_l0);
+      nx_l0 = cur_l0; nx_nl = cur_nl;
     }
-    const double s0 = block_sum<kTile>(rr * jd, red);
-    const double s1 = block_sum<kTile>(jd * jd, red);
-    const double s2 = block_sum<kTile>(dl2, red);
-    const double s3 = block_sum<kTile>(x2, red);
-    if (threadIdx.x == 0) {
-      a.partial[(size_t)g * 4 + 0] = s0;
-      a.partial[(size_t)g * 4 + 1] = s1;
-      a.partial[(size_t)g * 4 + 2] = s2;
-      a.partial[(size_t)g * 4 + 3] = s3;
+  }
+  if (MODE == kModeBacksub) {
+    const double s0 = block_sum<kTile>(p0, red);
+    const double s1 = block_sum<kTile>(p1, red);
+    const double s2 = block_sum<kTile>(p2, red);
+    const double s3 = block_sum<kTile>(p3, red);
+    if (t == 0) {
+      a.partial[(size_t)blockIdx.x * 4 + 0] = s0;
+      a.partial[(size_t)blockIdx.x * 4 + 1] = s1;
+      a.partial[(size_t)blockIdx.x * 4 + 2] = s2;
+      a.partial[(size_t)blockIdx.x * 4 + 3] = s3;
     }
   }
 }
 
 // Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}
-__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int m, const int* __restrict__ cam_ptr,
+__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(size_t m, const int* __restrict__ cam_ptr,
                                                           const int* __restrict__ cam_perm,
                                                           const double* __restrict__ jc, const double* __restrict__ w,
                                                           double* __restrict__ qpart, const CgState* __restrict__ st) {
@@ -568,12 +776,11 @@ __global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int m, const int* __res
   if (st->done) return;
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
-  const size_t M = (size_t)m;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     const double wi = __ldg(w + cam_perm[j]);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc[k] += wi * __ldg(jc + (size_t)k * M + j);
+    for (int k = 0; k < 6; ++k) acc[k] += wi * __ldg(jc + (size_t)k * m + j);
   }
   const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
@@ -760,25 +967,28 @@ __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __re
   if (t < n) out[t] = a[t] - b[t];
 }
 
-__global__ void k_scatter_to_caller_order(int m, const int* __restrict__ orig_of, const double* __restrict__ src,
-                                          double* __restrict__ dst) {
+// slot order -> caller's observation order
+__global__ void k_slots_to_caller(int Mp, const int* __restrict__ slot_src, const double* __restrict__ src,
+                                  double* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  dst[orig_of[i]] = src[i];
+  if (i >= Mp) return;
+  const int o = slot_src[i];
+  if (o >= 0) dst[o] = src[i];
 }
 
 // Jacobian rows in API layout: jcam (m,6) interleaved [w0,c0,w1,c1,w2,c2], jline (m,6); caller order.
-__global__ void k_export_jacobian(int m, const int* __restrict__ orig_of, const int* __restrict__ cam_pos,
+__global__ void k_export_jacobian(int Mp, size_t m, const int* __restrict__ slot_src, const int* __restrict__ cam_pos,
                                   const double* __restrict__ jl, const double* __restrict__ jc,
                                   double* __restrict__ jcam, double* __restrict__ jline) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const size_t M = (size_t)m;
-  const size_t o = orig_of ? (size_t)orig_of[i] : (size_t)i;
-  const int pos = cam_pos[i];
+  if (i >= Mp) return;
+  const int src = slot_src[i];
+  if (src < 0) return;
+  const size_t M = (size_t)Mp, o = (size_t)src;
+  const size_t pos = (size_t)cam_pos[i];
   for (int k = 0; k < 3; ++k) {
-    jcam[o * 6 + 2 * k] = jc[(size_t)k * M + pos];
-    jcam[o * 6 + 2 * k + 1] = jc[(size_t)(3 + k) * M + pos];
+    jcam[o * 6 + 2 * k] = jc[(size_t)k * m + pos];
+    jcam[o * 6 + 2 * k + 1] = jc[(size_t)(3 + k) * m + pos];
   }
   for (int k = 0; k < 6; ++k) jline[o * 6 + k] = jl[(size_t)k * M + i];
 }
