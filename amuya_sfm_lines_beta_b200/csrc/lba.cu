@@ -113,9 +113,14 @@ struct lba_ctx {
   // persistent-grid sizes and dynamic shared memory of the pipelined line-order kernels
   int grid_eval_j = 1, grid_eval_r = 1, grid_lp[3] = {1, 1, 1};
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
+  bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
+  int eval_stages_j = 3, eval_stages_r = 3;
 
   // state
-  DBuf<double> cams, cams_new, pts, pts_new, Gm, api_tmp;
+  DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
+  DBuf<unsigned int> tickets;
+  bool pending_first = true;
+  int line_scaling_mode = 2;   // consumed by the next k_line_factor: 0 keep, 1 running max, 2 first
   DBuf<CamRec> recs, recs_new;
   DBuf<double> r, r_new, jl, jc, w, wk, wr;
   DBuf<double> V, gl, Vinv, y, Dl;
@@ -222,6 +227,8 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CKR(c->cgst.alloc(1));
   CKR(c->gbits.alloc(1));
   CKR(c->clamped.alloc(1));
+  CKR(c->tickets.alloc(4));
+  CK(cudaMemsetAsync(c->tickets.p, 0, 16, c->stream));
   CK(cudaMemsetAsync(c->scal.p, 0, sizeof(Scalars), c->stream));
   CK(cudaMemsetAsync(c->clamped.p, 0, sizeof(int), c->stream));
   *out = c;
@@ -468,24 +475,39 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
 
   // persistent grids: SMs x resident CTAs for each pipelined kernel at this problem's stage size
   {
-    auto plan = [&](auto kern, int smem, int* grid) -> int {
+    auto plan = [&](auto kern, int threads, int smem, int nsub, int* grid) -> int {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTile, (size_t)smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, (size_t)smem));
       if (nb < 1) return fail(LBA_ERR_UNSUPPORTED, "line-order kernel does not fit on an SM (%d B shared memory)", smem);
-      *grid = std::max(1, std::min(ntiles, nb * ctx->n_sm));
+      *grid = std::max(1, std::min((ntiles + nsub - 1) / nsub, nb * ctx->n_sm));
       return LBA_OK;
     };
-    ctx->smem_eval_j = eval_smem_bytes(lmax, true);
-    ctx->smem_eval_r = eval_smem_bytes(lmax, false);
-    CKR(plan(k_eval<true>, ctx->smem_eval_j, &ctx->grid_eval_j));
-    CKR(plan(k_eval<false>, ctx->smem_eval_r, &ctx->grid_eval_r));
+    int max_smem = 0;
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    // preferred: 2 sub-groups per CTA sharing a shared-memory camera table (1 CTA / SM)
+    ctx->eval_tab_smem = false;
+    if (nc > 0 && eval_smem_bytes(lmax, true, 2, 2, nc) + 4096 <= max_smem) {
+      ctx->eval_tab_smem = true;
+      ctx->eval_stages_j = 2;
+      ctx->eval_stages_r = eval_smem_bytes(lmax, false, 3, 2, nc) + 4096 <= max_smem ? 3 : 2;
+      ctx->smem_eval_j = eval_smem_bytes(lmax, true, ctx->eval_stages_j, 2, nc);
+      ctx->smem_eval_r = eval_smem_bytes(lmax, false, ctx->eval_stages_r, 2, nc);
+      CKR(plan(k_eval<true, 2, true>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
+      CKR(plan(k_eval<false, 2, true>, 2 * kTile, ctx->smem_eval_r, 2, &ctx->grid_eval_r));
+    } else {
+      ctx->eval_stages_j = ctx->eval_stages_r = 3;
+      ctx->smem_eval_j = eval_smem_bytes(lmax, true, 3, 1, 0);
+      ctx->smem_eval_r = eval_smem_bytes(lmax, false, 3, 1, 0);
+      CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
+      CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
+    }
     ctx->smem_lp[0] = lp_smem_bytes(lmax, kModeMatvec);
     ctx->smem_lp[1] = lp_smem_bytes(lmax, kModeBacksub);
     ctx->smem_lp[2] = lp_smem_bytes(lmax, kModeScalars);
-    CKR(plan(k_line_pass<kModeMatvec>, ctx->smem_lp[0], &ctx->grid_lp[0]));
-    CKR(plan(k_line_pass<kModeBacksub>, ctx->smem_lp[1], &ctx->grid_lp[1]));
-    CKR(plan(k_line_pass<kModeScalars>, ctx->smem_lp[2], &ctx->grid_lp[2]));
+    CKR(plan(k_line_pass<kModeMatvec>, kTile, ctx->smem_lp[0], 1, &ctx->grid_lp[0]));
+    CKR(plan(k_line_pass<kModeBacksub>, kTile, ctx->smem_lp[1], 1, &ctx->grid_lp[1]));
+    CKR(plan(k_line_pass<kModeScalars>, kTile, ctx->smem_lp[2], 1, &ctx->grid_lp[2]));
   }
 
   // state buffers
@@ -493,7 +515,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   const size_t NG = (size_t)std::max({ctx->grid_eval_j, ctx->grid_eval_r, ctx->grid_lp[1], 1});
   CKR(ctx->cams.alloc(NC * 6)); CKR(ctx->cams_new.alloc(NC * 6)); CKR(ctx->api_tmp.alloc(std::max(NC * 6, (size_t)1)));
   CKR(ctx->pts.alloc(NL * 6 + 2)); CKR(ctx->pts_new.alloc(NL * 6 + 2));
-  CKR(ctx->Gm.alloc(NC * 9)); CKR(ctx->recs.alloc(NC)); CKR(ctx->recs_new.alloc(NC));
+  CKR(ctx->Gm.alloc(NC * 9)); CKR(ctx->Gm_new.alloc(NC * 9)); CKR(ctx->recs.alloc(NC)); CKR(ctx->recs_new.alloc(NC));
   CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * (size_t)m));
   CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M)); CKR(ctx->dense_tmp.alloc((size_t)m));
   CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
@@ -515,10 +537,12 @@ static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc *
 
 static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
   EvalArgs a;
-  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.meta = c->meta.p; a.obs_cam = c->obs_cam.p;
+  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3;
+  a.meta = c->meta.p; a.obs_cam = c->obs_cam.p;
   a.obs_ll = c->obs_ll.p; a.cam_pos = c->cam_pos.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
-  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.m = (size_t)c->m; a.V = c->V.p; a.gl = c->gl.p;
+  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p;
   a.cost_partial = c->cost_partial.p;
+  a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost; a.gbits = c->gbits.p;
   return a;
 }
 
@@ -552,49 +576,52 @@ static int store_state(lba_ctx* c, double* cams_api, double* pts_api) {
   return LBA_OK;
 }
 
-// residual-only pass at (recs, pts) -> r_out, scal.cost (all-reduced)
+// residual-only pass at (recs, pts) -> r_out, scal.cost (local sum; callers all-reduce)
 static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, double* r_out) {
-  int ng = 0;
   if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, recs, pts, r_out);
-    ng = c->grid_eval_r;
-    LAUNCH_DYN(c, LBA_K_RESIDUAL, k_eval<false>, ng, kTile, c->smem_eval_r, a);
+    a.nstages = c->eval_stages_r;
+    if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 2, true>), c->grid_eval_r, 2 * kTile, c->smem_eval_r, a);
+    else LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 1, false>), c->grid_eval_r, kTile, c->smem_eval_r, a);
+  } else {
+    CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
   }
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ng, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
   return LBA_OK;
 }
 
-// fused residual + Jacobian + line blocks at the current state -> r, jl, jc, V, gl, scal.cost
+// fused residual + Jacobian + line blocks (+ line scaling, line part of the gradient norm) at the
+// current state -> r, jl, jc, V, gl, Dl, scal.cost
 static int run_jacobian(lba_ctx* c) {
-  int ng = 0;
+  c->pending_first = !c->have_scaling;
+  c->line_scaling_mode = c->pending_first ? 2 : 1;
+  CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
   if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, c->recs.p, c->pts.p, c->r.p);
-    ng = c->grid_eval_j;
-    LAUNCH_DYN(c, LBA_K_JACOBIAN, k_eval<true>, ng, kTile, c->smem_eval_j, a);
+    a.nstages = c->eval_stages_j;
+    if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
+    else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
+  } else {
+    CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
   }
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ng, 1, c->cost_partial.p, &c->scal.p->cost, 0.5);
   c->have_eval = true;
   c->have_blocks = false;
   return LBA_OK;
 }
 
-// camera blocks U_c, g_c (+ all-reduce), Marquardt scaling, gradient inf-norm
-static int run_blocks(lba_ctx* c, bool update_scaling) {
+// camera side of the normal equations: diag(U_c) (or the full blocks) and g_c, all-reduced; camera
+// scaling; camera part of the gradient inf-norm
+static int run_blocks(lba_ctx* c, bool full) {
   if (c->nc > 0) {
-    LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, (size_t)c->m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-           (const double*)nullptr, c->r.p, c->U.p, gc_of(c));
+    if (full)
+      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+             (const double*)nullptr, c->r.p, c->U.p, gc_of(c));
+    else
+      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, c->U.p, gc_of(c));
     CKR(allreduce_sum(c, c->U.p, (size_t)c->nc * 27));
-    CK(cudaMemcpyAsync(c->gc.p, gc_of(c), (size_t)c->nc * 48, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(c, LBA_K_MISC, k_cam_post, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, gc_of(c), c->Dc.p,
+           c->pending_first ? 1 : 0, c->gbits.p);
   }
-  if (update_scaling) {
-    const int first = c->have_scaling ? 0 : 1;
-    if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_update_scaling, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, c->Dc.p, first);
-    if (c->nl > 0) LAUNCH(c, LBA_K_MISC, k_update_scaling, cdiv((long long)c->nl * 6, 256), 256, c->nl, c->V.p, c->Dl.p, first);
-    c->have_scaling = true;
-  }
-  CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
-  if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_absmax, std::min(cdiv((long long)c->nc * 6, 256), 4 * c->n_sm), 256, (size_t)c->nc * 6, c->gc.p, c->gbits.p);
-  if (c->nl > 0) LAUNCH(c, LBA_K_MISC, k_absmax, std::min(cdiv((long long)c->nl * 6, 256), 4 * c->n_sm), 256, (size_t)c->nl * 6, c->gl.p, c->gbits.p);
+  c->have_scaling = true;
   CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
   c->have_blocks = true;
   return LBA_OK;
@@ -606,35 +633,36 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
                      int* breakdown_out) {
   const int nc = c->nc, nl = c->nl, m = c->m;
   if (nl > 0)
-    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, 128), 128, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p);
+    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, 128), 128, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode);
+  c->line_scaling_mode = 0;
   LinePassArgs la;
   la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.meta = c->meta.p; la.obs_cam = c->obs_cam.p;
   la.obs_ll = c->obs_ll.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
   la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p;
-  la.partial = c->bs_partial.p; la.st = c->cgst.p;
+  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &c->scal.p->rjd; la.st = c->cgst.p;
   if (c->ntiles > 0)
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
   if (nc > 0) {
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, (size_t)m, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
            (const double*)c->wk.p, c->wr.p, c->Mpart.p, bpart_of(c));
     CKR(allreduce_sum(c, c->Mpart.p, (size_t)nc * 27));
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, gc_of(c), bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
   }
   CgArgs ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
   ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
-  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_init, 1, kCgThreads, ca);
+  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, kCgCtas, kCgBlock, ca);
 
   int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
   int issued = 0;
   while (true) {
     for (int q = 0; q < chunk && issued < pcg_max_iter; ++q, ++issued) {
       if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], la);
-      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, (size_t)m, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
+      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
       CKR(allreduce_sum(c, c->qpart.p, (size_t)nc * 6));
-      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_update, 1, kCgThreads, ca);
+      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, kCgCtas, kCgBlock, ca);
     }
     CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -645,17 +673,15 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   *breakdown_out = c->h_cgst->breakdown;
   *chunk_hint = c->h_cgst->k + 1;
 
-  // back-substitution and candidate point
-  if (nc > 0) LAUNCH(c, LBA_K_MISC, k_make_table, cdiv(nc, 128), 128, nc, c->Gm.p, c->cams.p, c->cgx.p, c->tab.p);
-  int ngb = 0;
+  // back-substitution and candidate point (k_cg_step left the gather table of the solution in tab)
   if (c->ntiles > 0) {
-    ngb = c->grid_lp[1];
-    LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, ngb, kTile, c->smem_lp[1], la);
-  } else if (nl > 0) {
-    CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)nl * 48, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->grid_lp[1], kTile, c->smem_lp[1], la);
+  } else {
+    if (nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)nl * 48, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
   }
-  LAUNCH(c, LBA_K_MISC, k_reduce_partials, 1, 1024, ngb, 4, c->bs_partial.p, &c->scal.p->rjd, 1.0);
-  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, nc, c->cams.p, c->cgx.p, c->cams_new.p, &c->scal.p->dc2, &c->scal.p->x2_cams);
+  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, nc, c->cams.p, c->cgx.p, c->cams_new.p, c->recs_new.p, c->Gm_new.p,
+         &c->scal.p->dc2, &c->scal.p->x2_cams);
   return LBA_OK;
 }
 
@@ -731,6 +757,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
                                       double* jcam, double* jline) {
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CKR(load_state(ctx, cams, pts));
+  ctx->have_scaling = false;
   CKR(run_jacobian(ctx));
   CKR(export_residuals(ctx, ctx->r.p, residuals));
   const int m = ctx->m;
@@ -738,7 +765,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
     if (!jcam || !jline) return fail(LBA_ERR_ARG, "jcam and jline must both be given or both be NULL");
     DBuf<double> tmp;
     CKR(tmp.alloc((size_t)12 * m));
-    LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(ctx->Mp, 256), 256, ctx->Mp, (size_t)m, ctx->slot_src.p,
+    LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(ctx->Mp, 256), 256, ctx->Mp, ctx->slot_src.p,
            ctx->cam_pos.p, ctx->jl.p, ctx->jc.p, tmp.p, tmp.p + (size_t)6 * m);
     CK(cudaMemcpyAsync(jcam, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaMemcpyAsync(jline, tmp.p + (size_t)6 * m, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
@@ -753,7 +780,7 @@ extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double*
   CK(cudaSetDevice(ctx->device));
   CKR(run_blocks(ctx, true));
   if (U && ctx->nc) CK(cudaMemcpyAsync(U, ctx->U.p, (size_t)ctx->nc * 21 * 8, cudaMemcpyDefault, ctx->stream));
-  if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, ctx->gc.p, (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
+  if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, gc_of(ctx), (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
   if (V && ctx->nl) CK(cudaMemcpyAsync(V, ctx->V.p, (size_t)ctx->nl * 21 * 8, cudaMemcpyDefault, ctx->stream));
   if (gl && ctx->nl) CK(cudaMemcpyAsync(gl, ctx->gl.p, (size_t)ctx->nl * 6 * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -765,7 +792,7 @@ extern "C" int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int3
   if (!ctx || !ctx->have_eval) return fail(LBA_ERR_STATE, "no resident evaluation: call lba_residuals_jacobian first");
   if (!(lambda > 0.0)) return fail(LBA_ERR_ARG, "lambda must be positive");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->have_blocks) CKR(run_blocks(ctx, true));
+  if (!ctx->have_blocks) CKR(run_blocks(ctx, false));
   int hint = 8, iters = 0, brk = 0;
   CKR(run_solve(ctx, lambda, pcg_tol, pcg_max_iter, &hint, &iters, &brk));
   if (pcg_iters) *pcg_iters = iters;
@@ -797,7 +824,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   CKR(run_jacobian(c));
   rep->n_jac = 1;
   CKR(allreduce_sum(c, &c->scal.p->cost, 1));
-  CKR(run_blocks(c, true));
+  CKR(run_blocks(c, false));
   CKR(fetch_scalars(c));
   double cost = c->h_scal->cost;
   rep->cost_init = cost;
@@ -812,9 +839,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     int q = 0, brk = 0;
     CKR(run_solve(c, lam, o.pcg_tol, o.pcg_max_iter, &chunk_hint, &q, &brk));
     rep->pcg_iters_total += q;
-    // trial evaluation at x + delta
-    if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_cam_prepare, cdiv(c->nc, 128), 128, c->nc, c->cams_new.p, c->recs_new.p, (double*)nullptr);
-    // keep the pre-step cost: run_residual overwrites scal.cost with the trial cost
+    // trial evaluation at x + delta (k_cam_step prepared the camera records of the candidate)
     CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
     rep->n_res += 1;
     CKR(allreduce_sum(c, &c->scal.p->cost, 5));  // cost, rjd, jd2, dl2, x2_lines are contiguous
@@ -844,11 +869,12 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     if (accepted) {
       std::swap(c->cams.p, c->cams_new.p); std::swap(c->cams.n, c->cams_new.n);
       std::swap(c->pts.p, c->pts_new.p); std::swap(c->pts.n, c->pts_new.n);
+      std::swap(c->recs.p, c->recs_new.p); std::swap(c->recs.n, c->recs_new.n);
+      std::swap(c->Gm.p, c->Gm_new.p); std::swap(c->Gm.n, c->Gm_new.n);
       cost = cost_new;
-      if (c->nc > 0) LAUNCH(c, LBA_K_MISC, k_cam_prepare, cdiv(c->nc, 128), 128, c->nc, c->cams.p, c->recs.p, c->Gm.p);
       CKR(run_jacobian(c));
       rep->n_jac += 1;
-      CKR(run_blocks(c, true));
+      CKR(run_blocks(c, false));
       CKR(fetch_scalars(c));
       g_norm = gnorm_host(c);
       lam = lam * std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * ratio - 1.0, 3.0));

@@ -10,7 +10,8 @@
 //     cst[9][Mp] = n, m0 = n x p0, m1 = n x p1;  obs_cam[Mp]; obs_ll[Mp] (local line id, u8);
 //     cam_pos[Mp]; r[Mp]; jl[6][Mp]; w[Mp]; wk[Mp]; wr[Mp];  TileMeta[ntiles]
 // CAMERA ORDER (stable counting sort of the same observations by camera), dense m entries:
-//     jc[6][m]; cam_perm[m] (camera-order position -> slot); cam_ptr[Nc+1]
+//     jc[m][6] (one 48 B record per observation, so the scatter from the line-ordered Jacobian
+//     kernel is 3 x 16 B stores); cam_perm[m] (camera-order position -> slot); cam_ptr[Nc+1]
 // per line:   pts[Nl][6] = [X0,X1]; V[Nl][21]; gl[Nl][6]; Vinv[Nl][22] (21 + pad: 16 B aligned
 //             rows); y[Nl][6]; Dl[Nl][6]
 // per camera: cams[Nc][6] = [w,c]; CamRec[Nc]; G[Nc][9]; U[Nc][21]; gc[Nc][6]; Dc[Nc][6];
@@ -31,6 +32,7 @@
 // every sum has a fixed order, so results are bit-reproducible run to run.
 #pragma once
 #include "lba_geometry.cuh"
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace lba {
@@ -103,6 +105,32 @@ __device__ __forceinline__ double block_sum(double v, double* red /* >= THREADS/
   }
   __syncthreads();
   return red[0];
+}
+
+// Grid-wide sum without a second launch: every CTA publishes its partial(s), the CTA that takes the
+// last ticket adds them up in index order (fixed order => bit-reproducible) and resets the ticket.
+template <int THREADS, int NCOLS>
+__device__ __forceinline__ void last_cta_reduce(const double (&mine)[NCOLS], double* partial, unsigned int* ticket,
+                                                double* out, double scale, double* red) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < NCOLS; ++c) partial[(size_t)blockIdx.x * NCOLS + c] = mine[c];
+    __threadfence();
+    const unsigned int tk = atomicAdd(ticket, 1u);
+    s_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int c = 0; c < NCOLS; ++c) {
+    double acc = 0.0;
+    for (int g = threadIdx.x; g < (int)gridDim.x; g += THREADS) acc += __ldcg(partial + (size_t)g * NCOLS + c);
+    const double sum = block_sum<THREADS>(acc, red);
+    if (threadIdx.x == 0) out[c] = sum * scale;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
@@ -197,6 +225,7 @@ __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, c
 // ---------------------------------------------------------------------------------
 struct EvalArgs {
   int Mp, ntiles, lmax;    // lmax: max lines per tile rounded up to 8 (sizes the smem stage)
+  int nc, nstages;         // cameras (size of the shared-memory table), pipeline depth (<= kMaxStages)
   const TileMeta* meta;
   const int* obs_cam;
   const unsigned char* obs_ll;
@@ -206,15 +235,25 @@ struct EvalArgs {
   const double* pts;       // [nl][6]
   double* r;               // [Mp]
   double* jl;              // [6][Mp] slot order
-  double* jc;              // [6][m] camera order
-  size_t m;                // stride of jc
+  double* jc;              // [m][6] camera order, one 48 B record per observation
   double* V;               // [nl][21]
   double* gl;              // [nl][6]
   double* cost_partial;    // [gridDim]
+  unsigned int* ticket;    // last-CTA reduction ticket
+  double* cost_out;        // 0.5 * sum r^2
+  unsigned long long* gbits;  // inf-norm of the gradient, as ordered bits
 };
 
 __constant__ int c_sym_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ int c_sym_b[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+constexpr int kMaxStages = 4;
+// 256-thread sub-group barrier (the sub-groups of one CTA run independent tile pipelines)
+template <int NSUB>
+__device__ __forceinline__ void sub_sync(int sub) {
+  if (NSUB == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(kTile) : "memory");
+}
 
 // shared-memory stage of k_eval: cst[9][256] | cam[256] | cam_pos[256] | ll[256] | meta | pts[lmax][6]
 constexpr int kEvOffCam = 9 * kTile * 8;
@@ -224,32 +263,48 @@ constexpr int kEvOffMeta = kEvOffLl + kTile;
 constexpr int kEvOffPts = kEvOffMeta + (int)sizeof(TileMeta);
 __host__ __device__ inline int eval_stage_bytes(int lmax) { return (kEvOffPts + lmax * 48 + 127) & ~127; }
 constexpr int kEvRow = 9;  // staging row stride in doubles: (jl[6], r, pad) -> 72 B, conflict-free per half-warp
-__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac) {
-  return kStages * eval_stage_bytes(lmax) + (with_jac ? kTile * kEvRow * 8 : 0) + 128;
+__host__ __device__ inline int eval_sub_bytes(int lmax, bool with_jac, int nstages) {
+  return nstages * eval_stage_bytes(lmax) + (with_jac ? kTile * kEvRow * 8 : 0);
+}
+__host__ __device__ inline int eval_tab_bytes(int nc) { return (nc * (int)sizeof(CamRec) + 127) & ~127; }
+__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac, int nstages, int nsub, int nc_tab) {
+  return eval_tab_bytes(nc_tab) + nsub * eval_sub_bytes(lmax, with_jac, nstages) + 128;
 }
 
-template <bool WITH_JAC>
-__global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
+// Fused residual (+ Jacobian + per-line blocks) over the tiles.  A CTA is NSUB independent
+// 256-thread sub-groups; with TAB_SMEM they share one shared-memory copy of the camera table
+// (the per-observation camera gather is the L1-wavefront hot spot when it goes to global memory).
+template <bool WITH_JAC, int NSUB, bool TAB_SMEM>
+__global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ double red[kTile / 32];
-  __shared__ uint64_t full[kStages];
+  __shared__ double red[kTile * NSUB / 32];
+  __shared__ uint64_t full[NSUB][kMaxStages];
+  const int S = a.nstages;
   const int stage_bytes = eval_stage_bytes(a.lmax);
-  double* s_stg = reinterpret_cast<double*>(smem + (size_t)kStages * stage_bytes);  // [256][kEvRow], WITH_JAC only
+  const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile;
+  const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
+  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, WITH_JAC, S);
+  double* s_stg = reinterpret_cast<double*>(sbase + (size_t)S * stage_bytes);  // [256][kEvRow], WITH_JAC only
+  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : a.recs;
   const size_t M = (size_t)a.Mp;
-  const int first = blockIdx.x, stride = gridDim.x;
+  const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  const int t = threadIdx.x;
 
   if (t == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&full[sub][s], 1);
     fence_barrier_init();
+  }
+  if (TAB_SMEM) {
+    const double2* src = reinterpret_cast<const double2*>(a.recs);
+    double2* dst = reinterpret_cast<double2*>(smem);
+    for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kTile * NSUB) dst[q] = __ldg(src + q);
   }
   __syncthreads();
 
   auto issue = [&](int it, int nl, int l0) {
     const int tile = first + it * stride;
-    unsigned char* st = smem + (size_t)(it % kStages) * stage_bytes;
-    uint64_t* bar = &full[it % kStages];
+    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    uint64_t* bar = &full[sub][it % S];
     const uint32_t bytes = 9 * kTile * 8 + kTile * 4 + (WITH_JAC ? kTile * 4 : 0) + kTile + (uint32_t)sizeof(TileMeta) + nl * 48;
     mbar_expect_tx(bar, bytes);
     const size_t o = (size_t)tile * kTile;
@@ -261,32 +316,32 @@ __global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
     bulk_g2s(st + kEvOffMeta, a.meta + tile, sizeof(TileMeta), bar);
     if (nl > 0) bulk_g2s(st + kEvOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
   };
-  // thread 0 keeps (l0, nl) of the tile it will issue next in registers, one iteration ahead
+  // the issuing thread keeps (l0, nl) of the tile it will issue next in registers, one iteration ahead
   int nx_l0 = 0, nx_nl = 0;
   if (t == 0) {
-    for (int it = 0; it < kStages && it < my_n; ++it) {
+    for (int it = 0; it < S && it < my_n; ++it) {
       const TileMeta* mt = a.meta + first + it * stride;
       issue(it, mt->nl, mt->l0);
     }
-    if (kStages < my_n) { const TileMeta* mt = a.meta + first + kStages * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
+    if (S < my_n) { const TileMeta* mt = a.meta + first + S * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
   }
 
-  double cost_acc = 0.0;
+  double cost_acc = 0.0, gmax = 0.0;
   for (int it = 0; it < my_n; ++it) {
     const int tile = first + it * stride;
-    unsigned char* st = smem + (size_t)(it % kStages) * stage_bytes;
-    double* s_cst = reinterpret_cast<double*>(st);
+    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    const double* s_cst = reinterpret_cast<const double*>(st);
     const int* s_cam = reinterpret_cast<const int*>(st + kEvOffCam);
     const int* s_pos = reinterpret_cast<const int*>(st + kEvOffPos);
     const unsigned char* s_ll = st + kEvOffLl;
     const TileMeta* s_meta = reinterpret_cast<const TileMeta*>(st + kEvOffMeta);
     const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
     int cur_l0 = 0, cur_nl = 0;
-    if (t == 0 && it + kStages + 1 < my_n) {  // prefetch the scalars for the issue after next
-      const TileMeta* mt = a.meta + first + (it + kStages + 1) * stride;
+    if (t == 0 && it + S + 1 < my_n) {  // prefetch the scalars for the issue after next
+      const TileMeta* mt = a.meta + first + (it + S + 1) * stride;
       cur_l0 = mt->l0; cur_nl = mt->nl;
     }
-    mbar_wait(&full[it % kStages], (it / kStages) & 1);
+    mbar_wait(&full[sub][it % S], (it / S) & 1);
 
     const int cam = s_cam[t];
     const bool active = cam >= 0;
@@ -302,7 +357,14 @@ __global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
         m1[k] = s_cst[(6 + k) * kTile + t];
       }
       double w[3], c[3], A, B, C;
-      load_camrec(a.recs, cam, w, c, A, B, C);
+      if (TAB_SMEM) {
+        const double2* p = reinterpret_cast<const double2*>(recs + cam);
+        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
+        A = v3.x; B = v3.y; C = v4.x;
+      } else {
+        load_camrec(recs, cam, w, c, A, B, C);
+      }
       const double* X = s_pts + (int)s_ll[t] * 6;
       double X0[3] = {X[0], X[1], X[2]}, X1[3] = {X[3], X[4], X[5]};
       double R[9];
@@ -314,14 +376,11 @@ __global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
       if (WITH_JAC) {
         double G[9];
         build_G(w, B, C, G);
-        const size_t pos = (size_t)s_pos[t];
-        // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1)
-        a.jc[0 * a.m + pos] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
-        a.jc[1 * a.m + pos] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
-        a.jc[2 * a.m + pos] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
-        a.jc[3 * a.m + pos] = -(jl[0] + jl[3]);
-        a.jc[4 * a.m + pos] = -(jl[1] + jl[4]);
-        a.jc[5 * a.m + pos] = -(jl[2] + jl[5]);
+        // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
+        double2* dst = reinterpret_cast<double2*>(a.jc + (size_t)s_pos[t] * 6);
+        dst[0] = make_double2(G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2], G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2]);
+        dst[1] = make_double2(G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2], -(jl[0] + jl[3]));
+        dst[2] = make_double2(-(jl[1] + jl[4]), -(jl[2] + jl[5]));
       }
     }
     a.r[i] = r;
@@ -333,7 +392,7 @@ __global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) s_stg[t * kEvRow + k] = jl[k];
       s_stg[t * kEvRow + 6] = r;
-      __syncthreads();
+      sub_sync<NSUB>(sub);
       const int l0 = s_meta->l0, nlg = s_meta->nl;
       const int nwork = nlg * 27;
       for (int wi = t; wi < nwork; wi += kTile) {
@@ -342,19 +401,32 @@ __global__ void __launch_bounds__(kTile, 2) k_eval(const EvalArgs a) {
         const int ca = e < 21 ? c_sym_a[e] : e - 21, cb = e < 21 ? c_sym_b[e] : 6;
         double acc = 0.0;
         for (int s = s0; s < s1; ++s) acc += s_stg[s * kEvRow + ca] * s_stg[s * kEvRow + cb];
-        if (e < 21) a.V[(size_t)(l0 + ll) * 21 + e] = acc;
-        else a.gl[(size_t)(l0 + ll) * 6 + (e - 21)] = acc;
+        if (e < 21) {
+          a.V[(size_t)(l0 + ll) * 21 + e] = acc;
+        } else {
+          a.gl[(size_t)(l0 + ll) * 6 + (e - 21)] = acc;
+          const double ab = fabs(acc);
+          gmax = (ab > gmax || ab != ab) ? ab : gmax;
+        }
       }
     }
     fence_proxy_async();
-    __syncthreads();  // the stage is free: refill it with tile it + kStages
+    sub_sync<NSUB>(sub);  // the stage is free: refill it with tile it + S
     if (t == 0) {
-      if (it + kStages < my_n) issue(it + kStages, nx_nl, nx_l0);
+      if (it + S < my_n) issue(it + S, nx_nl, nx_l0);
       nx_l0 = cur_l0; nx_nl = cur_nl;
     }
   }
-  const double cs = block_sum<kTile>(cost_acc, red);
-  if (t == 0) a.cost_partial[blockIdx.x] = cs;
+  if (WITH_JAC) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, gmax, o);
+      gmax = (other > gmax || other != other) ? other : gmax;
+    }
+    if ((threadIdx.x & 31) == 0 && gmax != 0.0) atomicMax(a.gbits, (unsigned long long)__double_as_longlong(gmax));
+  }
+  const double cs[1] = {block_sum<kTile * NSUB>(cost_acc, red)};
+  last_cta_reduce<kTile * NSUB, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
 }
 
 // project(): p_hat rows 2i+e in the caller's observation order (API parity only; cold path)
@@ -399,7 +471,41 @@ __global__ void k_project(const ProjectArgs a) {
 // over the camera-ordered Jacobian copy.  wa == nullptr means weight 1.
 // One CTA per camera; 27 register accumulators per thread, warp-shuffle + smem reduce.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCamThreads) k_cam_accum(size_t m, const int* __restrict__ cam_ptr,
+// diag(U_c) and g_c only (all the LM loop needs from U): 12 accumulators instead of 27
+__global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict__ cam_ptr,
+                                                           const int* __restrict__ cam_perm,
+                                                           const double* __restrict__ jc, const double* __restrict__ r,
+                                                           double* __restrict__ S, double* __restrict__ v) {
+  __shared__ double sm[kCamThreads / 32][12];
+  const int c = blockIdx.x;
+  const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+    double x[6];
+    load6(jc + (size_t)j * 6, x);
+    const double b = __ldg(r + cam_perm[j]);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) { acc[p] += x[p] * x[p]; acc[6 + p] += b * x[p]; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (l == 0) sm[w][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+    if (threadIdx.x < 6) S[(size_t)c * 21 + sym_idx(threadIdx.x, threadIdx.x)] = s;
+    else v[(size_t)c * 6 + threadIdx.x - 6] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict__ cam_ptr,
                                                             const int* __restrict__ cam_perm,
                                                             const double* __restrict__ jc,
                                                             const double* __restrict__ wa,
@@ -414,8 +520,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(size_t m, const int* 
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     const int i = cam_perm[j];
     double x[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = __ldg(jc + (size_t)k * m + j);
+    load6(jc + (size_t)j * 6, x);
     const double a = wa ? __ldg(wa + i) : 1.0;
     const double b = __ldg(wb + i);
     int e = 0;
@@ -456,21 +561,54 @@ __global__ void k_update_scaling(int nblocks, const double* __restrict__ S /*[n]
   D[t] = first ? d : fmax(D[t], d);
 }
 
+// after the all-reduce of U|gc: camera scaling + gradient inf-norm in one launch
+__global__ void k_cam_post(int nc, const double* __restrict__ S, const double* __restrict__ gc, double* __restrict__ D,
+                           int first, unsigned long long* __restrict__ gbits) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double mx = 0.0;
+  if (t < nc * 6) {
+    const int b = t / 6, k = t % 6;
+    double d = S[(size_t)b * 21 + sym_idx(k, k)];
+    if (d == 0.0) d = 1.0;
+    D[t] = first ? d : fmax(D[t], d);
+    mx = fabs(gc[t]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (other > mx || other != other) ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mx != 0.0) atomicMax(gbits, (unsigned long long)__double_as_longlong(mx));
+}
+
 // ---------------------------------------------------------------------------------
 // K4: Schur elimination pieces
 // ---------------------------------------------------------------------------------
-// per line: Vinv = (V + lam Dl)^-1, y = Vinv gl
+// per line: Vinv = (V + lam Dl)^-1, y = Vinv gl.  scaling_mode: 0 keep Dl, 1 Dl = max(Dl, diag V),
+// 2 Dl = diag V (first Jacobian); zeros -> 1  (Marquardt scaling, the analogue of scipy's
+// compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at bundle_adjustment.py:319).
 __global__ void __launch_bounds__(128) k_line_factor(int nl, double lam, const double* __restrict__ V,
-                                                      const double* __restrict__ Dl, const double* __restrict__ gl,
+                                                      double* __restrict__ Dl, const double* __restrict__ gl,
                                                       double* __restrict__ Vinv, double* __restrict__ y,
-                                                      int* __restrict__ clamped) {
+                                                      int* __restrict__ clamped, int scaling_mode) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nl) return;
   double S[21];
 #pragma unroll
   for (int e = 0; e < 21; ++e) S[e] = V[(size_t)l * 21 + e];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * Dl[(size_t)l * 6 + k];
+  for (int k = 0; k < 6; ++k) {
+    double D;
+    if (scaling_mode == 0) {
+      D = Dl[(size_t)l * 6 + k];
+    } else {
+      double d = S[sym_idx(k, k)];
+      if (d == 0.0) d = 1.0;
+      D = scaling_mode == 2 ? d : fmax(Dl[(size_t)l * 6 + k], d);
+      Dl[(size_t)l * 6 + k] = D;
+    }
+    S[sym_idx(k, k)] += lam * D;
+  }
   const int cl = spd6_inverse(S);
   if (cl) atomicAdd(clamped, cl);
   double g[6], yy[6];
@@ -552,6 +690,8 @@ struct LinePassArgs {
   const double* r;       // [Mp]
   double* pts_new;       // [nl][6]
   double* partial;       // [gridDim][4]: r.jd, jd.jd, |dl|^2, |pts|^2
+  unsigned int* ticket;  // BACKSUB: last-CTA reduction
+  double* out4;          // BACKSUB: the four sums
   const CgState* st;     // MATVEC: early exit when done
 };
 
@@ -754,21 +894,14 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     }
   }
   if (MODE == kModeBacksub) {
-    const double s0 = block_sum<kTile>(p0, red);
-    const double s1 = block_sum<kTile>(p1, red);
-    const double s2 = block_sum<kTile>(p2, red);
-    const double s3 = block_sum<kTile>(p3, red);
-    if (t == 0) {
-      a.partial[(size_t)blockIdx.x * 4 + 0] = s0;
-      a.partial[(size_t)blockIdx.x * 4 + 1] = s1;
-      a.partial[(size_t)blockIdx.x * 4 + 2] = s2;
-      a.partial[(size_t)blockIdx.x * 4 + 3] = s3;
-    }
+    const double sums[4] = {block_sum<kTile>(p0, red), block_sum<kTile>(p1, red), block_sum<kTile>(p2, red),
+                            block_sum<kTile>(p3, red)};
+    last_cta_reduce<kTile, 4>(sums, a.partial, a.ticket, a.out4, 1.0, red);
   }
 }
 
 // Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}
-__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(size_t m, const int* __restrict__ cam_ptr,
+__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(const int* __restrict__ cam_ptr,
                                                           const int* __restrict__ cam_perm,
                                                           const double* __restrict__ jc, const double* __restrict__ w,
                                                           double* __restrict__ qpart, const CgState* __restrict__ st) {
@@ -779,8 +912,10 @@ __global__ void __launch_bounds__(kCamThreads) k_pcg_cam(size_t m, const int* __
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     const double wi = __ldg(w + cam_perm[j]);
+    double x[6];
+    load6(jc + (size_t)j * 6, x);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc[k] += wi * __ldg(jc + (size_t)k * m + j);
+    for (int k = 0; k < 6; ++k) acc[k] += wi * x[k];
   }
   const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
@@ -811,91 +946,150 @@ struct CgArgs {
   CgState* st;
 };
 
-// x = 0, r = b, z = Minv r, p = z, rz0 = r.z ; table(p).   One CTA.
-__global__ void __launch_bounds__(kCgThreads) k_cg_init(const CgArgs a) {
-  __shared__ double red[kCgThreads / 32];
-  double acc = 0.0;
-  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
-    double rr[6], zz[6], S[21];
+// The CG vector work is one thread-block CLUSTER (8 CTAs x 512 threads on 8 SMs of one GPC): every
+// camera owns 8 consecutive lanes (6 active), dot products are reduced inside each CTA and then
+// combined through distributed shared memory in rank order, so every CTA holds the same bits.
+constexpr int kCgCtas = 8;
+constexpr int kCgBlock = 512;
+
+__device__ __forceinline__ double cluster_sum(double v, double* red, double* slot /* this CTA's slot in smem */) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const double mine = block_sum<kCgBlock>(v, red);
+  if (threadIdx.x == 0) *slot = mine;
+  cl.sync();
+  double tot = 0.0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) rr[k] = a.b[(size_t)c * 6 + k];
+  for (int rk = 0; rk < kCgCtas; ++rk) tot += *cl.map_shared_rank(slot, rk);
+  return tot;
+}
+
+// z_k = sum_j Minv[k][j] r_j inside an 8-lane camera group (lane k holds r_k)
+__device__ __forceinline__ double group_minv(const double* __restrict__ Minv_c, double rk, int k, bool act) {
+  double z = 0.0;
+  const int base = (threadIdx.x & 31) & 24;
 #pragma unroll
-    for (int e = 0; e < 21; ++e) S[e] = a.Minv[(size_t)c * 21 + e];
-    sym6_matvec(S, rr, zz);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      a.x[(size_t)c * 6 + k] = 0.0;
-      a.r[(size_t)c * 6 + k] = rr[k];
-      a.z[(size_t)c * 6 + k] = zz[k];
-      a.p[(size_t)c * 6 + k] = zz[k];
-      acc += rr[k] * zz[k];
-    }
-    make_tab_entry(a.Gm + (size_t)c * 9, a.cams + (size_t)c * 6, zz, a.tab + (size_t)c * 6);
+  for (int j = 0; j < 6; ++j) {
+    const double rj = __shfl_sync(0xffffffffu, rk, base + j);
+    if (act) z += Minv_c[sym_idx(k < j ? k : j, k < j ? j : k)] * rj;
   }
-  const double rz = block_sum<kCgThreads>(acc, red);
-  if (threadIdx.x == 0) {
+  return z;
+}
+
+// lane k of a camera group writes tab[k] for the vector whose component k it holds
+__device__ __forceinline__ void group_table(const double* __restrict__ G, const double* __restrict__ cam, double vk, int k,
+                                            bool act, double* __restrict__ tab_c) {
+  const int base = (threadIdx.x & 31) & 24;
+  double v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = __shfl_sync(0xffffffffu, vk, base + j);
+  if (!act) return;
+  const double a0 = G[0] * v[0] + G[1] * v[1] + G[2] * v[2];
+  const double a1 = G[3] * v[0] + G[4] * v[1] + G[5] * v[2];
+  const double a2 = G[6] * v[0] + G[7] * v[1] + G[8] * v[2];
+  const double c0 = cam[3], c1 = cam[4], c2 = cam[5];
+  double out;
+  switch (k) {
+    case 0: out = a0; break;
+    case 1: out = a1; break;
+    case 2: out = a2; break;
+    case 3: out = a1 * c2 - a2 * c1 + v[3]; break;
+    case 4: out = a2 * c0 - a0 * c2 + v[4]; break;
+    default: out = a0 * c1 - a1 * c0 + v[5]; break;
+  }
+  tab_c[k] = out;
+}
+
+// x = 0, r = b, z = Minv r, p = z, rz0 = r.z ; table(p)
+__global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
+  namespace cg = cooperative_groups;
+  __shared__ double red[kCgBlock / 32];
+  __shared__ double slot[2];
+  const int gt = blockIdx.x * kCgBlock + threadIdx.x;
+  const int k = gt & 7;
+  const int groups = kCgCtas * kCgBlock / 8;
+  double acc = 0.0;
+  for (int c0 = 0; c0 < a.nc; c0 += groups) {
+    const int c = c0 + (gt >> 3);
+    const bool act = c < a.nc && k < 6;
+    const size_t e = (size_t)c * 6 + k;
+    const double rk = act ? a.b[e] : 0.0;
+    const double zk = group_minv(a.Minv + (size_t)(act ? c : 0) * 21, rk, k, act);
+    if (act) {
+      a.x[e] = 0.0; a.r[e] = rk; a.z[e] = zk; a.p[e] = zk;
+      acc += rk * zk;
+    }
+    group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, zk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
+  }
+  const double rz = cluster_sum(acc, red, &slot[0]);
+  if (gt == 0) {
     a.st->rz = rz; a.st->rz0 = rz; a.st->pq = 0.0; a.st->k = 0;
     a.st->breakdown = 0;
     a.st->done = !(rz > 0.0);
   }
+  cg::this_cluster().sync();  // keep shared memory alive until every CTA has read the slots
 }
 
-// One CG step after q = S p is available (q = qpart + lam Dc p).   One CTA.
-__global__ void __launch_bounds__(kCgThreads) k_cg_update(const CgArgs a) {
-  __shared__ double red[kCgThreads / 32];
-  if (a.st->done) return;
-  const double rz = a.st->rz;
+// One CG step after q = S p is available (q = qpart + lam Dc p).  When the iteration stops, the
+// gather table of the SOLUTION x is written instead of that of the next direction, ready for the
+// back-substitution pass.
+__global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
+  namespace cg = cooperative_groups;
+  __shared__ double red[kCgBlock / 32];
+  __shared__ double slot[2];
+  if (a.st->done) return;   // uniform over the whole cluster
+  const double rz = a.st->rz, rz0 = a.st->rz0;
+  const int k_new = a.st->k + 1;
+  const int gt = blockIdx.x * kCgBlock + threadIdx.x;
+  const int k = gt & 7;
+  const int groups = kCgCtas * kCgBlock / 8;
   double acc = 0.0;
-  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const size_t t = (size_t)c * 6 + k;
-      const double pp = a.p[t];
-      const double q = a.qpart[t] + a.lam * a.Dc[t] * pp;
-      a.z[t] = q;  // z is free until the preconditioner is applied below; reuse it to keep q
+  for (int c0 = 0; c0 < a.nc; c0 += groups) {
+    const int c = c0 + (gt >> 3);
+    if (c < a.nc && k < 6) {
+      const size_t e = (size_t)c * 6 + k;
+      const double pp = a.p[e];
+      const double q = a.qpart[e] + a.lam * a.Dc[e] * pp;
+      a.z[e] = q;  // z is free until the preconditioner is applied below; reuse it to keep q
       acc += pp * q;
     }
   }
-  const double pq = block_sum<kCgThreads>(acc, red);
+  const double pq = cluster_sum(acc, red, &slot[0]);
   const bool ok = pq > 0.0;
   const double alpha = ok ? rz / pq : 0.0;
   acc = 0.0;
-  for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
-    double rr[6], zz[6], S[21];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const size_t t = (size_t)c * 6 + k;
-      a.x[t] += alpha * a.p[t];
-      rr[k] = a.r[t] - alpha * a.z[t];
-      a.r[t] = rr[k];
+  for (int c0 = 0; c0 < a.nc; c0 += groups) {
+    const int c = c0 + (gt >> 3);
+    const bool act = c < a.nc && k < 6;
+    const size_t e = (size_t)c * 6 + k;
+    double rk = 0.0;
+    if (act) {
+      a.x[e] += alpha * a.p[e];
+      rk = a.r[e] - alpha * a.z[e];
+      a.r[e] = rk;
     }
-#pragma unroll
-    for (int e = 0; e < 21; ++e) S[e] = a.Minv[(size_t)c * 21 + e];
-    sym6_matvec(S, rr, zz);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      a.z[(size_t)c * 6 + k] = zz[k];
-      acc += rr[k] * zz[k];
+    const double zk = group_minv(a.Minv + (size_t)(act ? c : 0) * 21, rk, k, act);
+    if (act) {
+      a.z[e] = zk;
+      acc += rk * zk;
     }
   }
-  const double rz_new = block_sum<kCgThreads>(acc, red);
-  const int k_new = a.st->k + 1;
-  const bool stop = !ok || rz_new <= a.tol2 * a.st->rz0 || k_new >= a.max_iter;
-  __syncthreads();
-  if (!stop) {
-    const double beta = rz_new / rz;
-    for (int c = threadIdx.x; c < a.nc; c += kCgThreads) {
-      double pn[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const size_t t = (size_t)c * 6 + k;
-        pn[k] = a.z[t] + beta * a.p[t];
-        a.p[t] = pn[k];
-      }
-      make_tab_entry(a.Gm + (size_t)c * 9, a.cams + (size_t)c * 6, pn, a.tab + (size_t)c * 6);
+  const double rz_new = cluster_sum(acc, red, &slot[1]);
+  const bool stop = !ok || rz_new <= a.tol2 * rz0 || k_new >= a.max_iter;
+  const double beta = stop ? 0.0 : rz_new / rz;
+  for (int c0 = 0; c0 < a.nc; c0 += groups) {
+    const int c = c0 + (gt >> 3);
+    const bool act = c < a.nc && k < 6;
+    const size_t e = (size_t)c * 6 + k;
+    double vk = 0.0;
+    if (act) {
+      if (stop) vk = a.x[e];
+      else { vk = a.z[e] + beta * a.p[e]; a.p[e] = vk; }
     }
+    group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, vk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
   }
-  if (threadIdx.x == 0) {
+  cg::this_cluster().sync();  // every CTA has read st and the slots
+  if (gt == 0) {
     a.st->pq = pq;
     a.st->k = k_new;
     a.st->rz = rz_new;
@@ -930,17 +1124,31 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(int n, int ncols, cons
   }
 }
 
-// cams_new = cams + dc ; norms.  One CTA.
+// cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms.  One CTA.
 __global__ void __launch_bounds__(1024) k_cam_step(int nc, const double* __restrict__ cams,
                                                     const double* __restrict__ dc, double* __restrict__ cams_new,
+                                                    CamRec* __restrict__ recs_new, double* __restrict__ Gm_new,
                                                     double* __restrict__ out_dc2, double* __restrict__ out_x2) {
   __shared__ double red[32];
   double d2 = 0.0, x2 = 0.0;
-  for (int t = threadIdx.x; t < nc * 6; t += 1024) {
-    const double x = cams[t], d = dc[t];
-    cams_new[t] = x + d;
-    d2 += d * d;
-    x2 += x * x;
+  for (int c = threadIdx.x; c < nc; c += 1024) {
+    CamRec rec;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double x = cams[c * 6 + k], d = dc[c * 6 + k];
+      const double xn = x + d;
+      cams_new[c * 6 + k] = xn;
+      if (k < 3) rec.w[k] = xn; else rec.c[k - 3] = xn;
+      d2 += d * d;
+      x2 += x * x;
+    }
+    rodrigues_coeffs(rec.w, rec.A, rec.B, rec.C);
+    rec.pad = 0.0;
+    recs_new[c] = rec;
+    double G[9];
+    build_G(rec.w, rec.B, rec.C, G);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Gm_new[c * 9 + k] = G[k];
   }
   const double s0 = block_sum<1024>(d2, red);
   const double s1 = block_sum<1024>(x2, red);
@@ -977,7 +1185,7 @@ __global__ void k_slots_to_caller(int Mp, const int* __restrict__ slot_src, cons
 }
 
 // Jacobian rows in API layout: jcam (m,6) interleaved [w0,c0,w1,c1,w2,c2], jline (m,6); caller order.
-__global__ void k_export_jacobian(int Mp, size_t m, const int* __restrict__ slot_src, const int* __restrict__ cam_pos,
+__global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, const int* __restrict__ cam_pos,
                                   const double* __restrict__ jl, const double* __restrict__ jc,
                                   double* __restrict__ jcam, double* __restrict__ jline) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -987,8 +1195,8 @@ __global__ void k_export_jacobian(int Mp, size_t m, const int* __restrict__ slot
   const size_t M = (size_t)Mp, o = (size_t)src;
   const size_t pos = (size_t)cam_pos[i];
   for (int k = 0; k < 3; ++k) {
-    jcam[o * 6 + 2 * k] = jc[(size_t)k * m + pos];
-    jcam[o * 6 + 2 * k + 1] = jc[(size_t)(3 + k) * m + pos];
+    jcam[o * 6 + 2 * k] = jc[pos * 6 + k];
+    jcam[o * 6 + 2 * k + 1] = jc[pos * 6 + 3 + k];
   }
   for (int k = 0; k < 6; ++k) jline[o * 6 + k] = jl[(size_t)k * M + i];
 }
