@@ -122,14 +122,14 @@ struct lba_ctx {
   bool pending_first = true;
   int line_scaling_mode = 2;   // consumed by the next k_line_factor: 0 keep, 1 running max, 2 first
   DBuf<CamRec> recs, recs_new;
-  DBuf<double> r, r_new, jl, jc, w, wk, wr;
-  DBuf<double> V, gl, Vinv, y, Dl;
+  DBuf<double> r, r_new, jl, jl_new, jc, jc_new, w, wk, wr;
+  DBuf<double> V, V_new, gl, gl_new, Vinv, y, Dl;
   DBuf<double> U, gc, Dc, Mpart, bpart, Minv, b;
   DBuf<double> cgx, cgr, cgz, cgp, tab, qpart;
   DBuf<double> cost_partial, bs_partial;
   DBuf<Scalars> scal;
   DBuf<CgState> cgst;
-  DBuf<unsigned long long> gbits;
+  DBuf<unsigned long long> gbits, gbits_new;
   DBuf<int> clamped;
   Scalars* h_scal = nullptr;   // pinned
   CgState* h_cgst = nullptr;   // pinned
@@ -226,6 +226,7 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CKR(c->scal.alloc(1));
   CKR(c->cgst.alloc(1));
   CKR(c->gbits.alloc(1));
+  CKR(c->gbits_new.alloc(1));
   CKR(c->clamped.alloc(1));
   CKR(c->tickets.alloc(4));
   CK(cudaMemsetAsync(c->tickets.p, 0, 16, c->stream));
@@ -517,8 +518,9 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->pts.alloc(NL * 6 + 2)); CKR(ctx->pts_new.alloc(NL * 6 + 2));
   CKR(ctx->Gm.alloc(NC * 9)); CKR(ctx->Gm_new.alloc(NC * 9)); CKR(ctx->recs.alloc(NC)); CKR(ctx->recs_new.alloc(NC));
   CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * (size_t)m));
+  CKR(ctx->jl_new.alloc(6 * M)); CKR(ctx->jc_new.alloc(6 * (size_t)m));
   CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M)); CKR(ctx->dense_tmp.alloc((size_t)m));
-  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
+  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->V_new.alloc(NL * 21)); CKR(ctx->gl_new.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
   CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6));
   CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
   CKR(ctx->Mpart.alloc(NC * 27)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
@@ -589,23 +591,46 @@ static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, doubl
   return LBA_OK;
 }
 
-// fused residual + Jacobian + line blocks (+ line scaling, line part of the gradient norm) at the
-// current state -> r, jl, jc, V, gl, Dl, scal.cost
-static int run_jacobian(lba_ctx* c) {
-  c->pending_first = !c->have_scaling;
-  c->line_scaling_mode = c->pending_first ? 2 : 1;
-  CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
+// fused residual + Jacobian + line blocks (+ line part of the gradient norm) -> scal.cost and either
+// the resident evaluation set (r, jl, jc, V, gl, gbits) or, speculatively at the trial point, the
+// "_new" set that is swapped in when the step is accepted
+static int run_jacobian(lba_ctx* c, bool into_new) {
+  unsigned long long* gb = into_new ? c->gbits_new.p : c->gbits.p;
+  CK(cudaMemsetAsync(gb, 0, 8, c->stream));
   if (c->ntiles > 0) {
-    EvalArgs a = eval_args(c, c->recs.p, c->pts.p, c->r.p);
+    EvalArgs a = into_new ? eval_args(c, c->recs_new.p, c->pts_new.p, c->r_new.p) : eval_args(c, c->recs.p, c->pts.p, c->r.p);
+    if (into_new) { a.jl = c->jl_new.p; a.jc = c->jc_new.p; a.V = c->V_new.p; a.gl = c->gl_new.p; }
+    a.gbits = gb;
     a.nstages = c->eval_stages_j;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
   } else {
     CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
   }
-  c->have_eval = true;
-  c->have_blocks = false;
+  if (!into_new) {
+    c->pending_first = !c->have_scaling;
+    c->line_scaling_mode = c->pending_first ? 2 : 1;
+    c->have_eval = true;
+    c->have_blocks = false;
+  }
   return LBA_OK;
+}
+
+template <typename T>
+static inline void swap_buf(DBuf<T>& a, DBuf<T>& b) { std::swap(a.p, b.p); std::swap(a.n, b.n); }
+
+// the trial point becomes the current point: parameters, camera records and the evaluation set
+static void accept_candidate(lba_ctx* c, bool have_new_eval) {
+  swap_buf(c->cams, c->cams_new); swap_buf(c->pts, c->pts_new);
+  swap_buf(c->recs, c->recs_new); swap_buf(c->Gm, c->Gm_new);
+  if (have_new_eval) {
+    swap_buf(c->r, c->r_new); swap_buf(c->jl, c->jl_new); swap_buf(c->jc, c->jc_new);
+    swap_buf(c->V, c->V_new); swap_buf(c->gl, c->gl_new); swap_buf(c->gbits, c->gbits_new);
+    c->pending_first = false;
+    c->line_scaling_mode = 1;
+    c->have_eval = true;
+    c->have_blocks = false;
+  }
 }
 
 // camera side of the normal equations: diag(U_c) (or the full blocks) and g_c, all-reduced; camera
@@ -627,15 +652,21 @@ static int run_blocks(lba_ctx* c, bool full) {
   return LBA_OK;
 }
 
-// Solve the damped system for the resident evaluation: leaves dc in cgx, the candidate
-// parameters in cams_new / pts_new and the model-reduction sums in scal.
-static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
-                     int* breakdown_out) {
-  const int nc = c->nc, nl = c->nl, m = c->m;
-  if (nl > 0)
-    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, 128), 128, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode);
-  c->line_scaling_mode = 0;
+// ---- the damped solve, in three stream-ordered pieces -------------------------------------------
+struct SolvePlan {
+  CgArgs ca;
   LinePassArgs la;
+  int issued = 0;
+};
+
+// (1) Schur elimination set-up for damping lam and the first CG state
+static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, SolvePlan* sp) {
+  const int nc = c->nc, nl = c->nl;
+  if (nl > 0) {
+    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, kLfLines), kLfLines, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode);
+    c->line_scaling_mode = 0;
+  }
+  LinePassArgs& la = sp->la;
   la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.meta = c->meta.p; la.obs_cam = c->obs_cam.p;
   la.obs_ll = c->obs_ll.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
   la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p;
@@ -649,40 +680,56 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
     CKR(allreduce_sum(c, c->Mpart.p, (size_t)nc * 27));
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, gc_of(c), bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
   }
-  CgArgs ca;
+  CgArgs& ca = sp->ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
   ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
   LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, kCgCtas, kCgBlock, ca);
+  sp->issued = 0;
+  return LBA_OK;
+}
 
+// (2) n more PCG iterations (kernels return at once when the device-side `done` flag is set)
+static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
+  for (int q = 0; q < n && sp->issued < sp->ca.max_iter; ++q, ++sp->issued) {
+    if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
+    if (c->nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
+    CKR(allreduce_sum(c, c->qpart.p, (size_t)c->nc * 6));
+    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, kCgCtas, kCgBlock, sp->ca);
+  }
+  CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+  return LBA_OK;
+}
+
+// (3) back-substitution and the candidate point (k_cg_step left the gather table of the solution)
+static int solve_finish(lba_ctx* c, SolvePlan* sp) {
+  if (c->ntiles > 0) {
+    LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->grid_lp[1], kTile, c->smem_lp[1], sp->la);
+  } else {
+    if (c->nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
+  }
+  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, c->nc, c->cams.p, c->cgx.p, c->cams_new.p, c->recs_new.p, c->Gm_new.p,
+         &c->scal.p->dc2, &c->scal.p->x2_cams);
+  return LBA_OK;
+}
+
+// the three pieces with a host check of the CG flag in between (stand-alone lba_schur_solve)
+static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
+                     int* breakdown_out) {
+  SolvePlan sp;
+  CKR(solve_setup(c, lam, pcg_tol, pcg_max_iter, &sp));
   int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
-  int issued = 0;
   while (true) {
-    for (int q = 0; q < chunk && issued < pcg_max_iter; ++q, ++issued) {
-      if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], la);
-      if (nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
-      CKR(allreduce_sum(c, c->qpart.p, (size_t)nc * 6));
-      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, kCgCtas, kCgBlock, ca);
-    }
-    CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    CKR(solve_iterate(c, &sp, chunk));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->h_cgst->done || issued >= pcg_max_iter) break;
+    if (c->h_cgst->done || sp.issued >= pcg_max_iter) break;
     chunk = 4;
   }
   *iters_out = c->h_cgst->k;
   *breakdown_out = c->h_cgst->breakdown;
   *chunk_hint = c->h_cgst->k + 1;
-
-  // back-substitution and candidate point (k_cg_step left the gather table of the solution in tab)
-  if (c->ntiles > 0) {
-    LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->grid_lp[1], kTile, c->smem_lp[1], la);
-  } else {
-    if (nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)nl * 48, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
-  }
-  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, nc, c->cams.p, c->cgx.p, c->cams_new.p, c->recs_new.p, c->Gm_new.p,
-         &c->scal.p->dc2, &c->scal.p->x2_cams);
-  return LBA_OK;
+  return solve_finish(c, &sp);
 }
 
 static int fetch_scalars(lba_ctx* c) {
@@ -758,7 +805,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CKR(load_state(ctx, cams, pts));
   ctx->have_scaling = false;
-  CKR(run_jacobian(ctx));
+  CKR(run_jacobian(ctx, false));
   CKR(export_residuals(ctx, ctx->r.p, residuals));
   const int m = ctx->m;
   if (m > 0 && (jcam || jline)) {
@@ -821,7 +868,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   CKR(load_state(c, cams_api, pts_api));
   c->have_scaling = false;
   CK(cudaMemsetAsync(c->clamped.p, 0, 4, c->stream));
-  CKR(run_jacobian(c));
+  CKR(run_jacobian(c, false));
   rep->n_jac = 1;
   CKR(allreduce_sum(c, &c->scal.p->cost, 1));
   CKR(run_blocks(c, false));
@@ -832,18 +879,40 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   double g_norm = gnorm_host(c);
   double lam = o.lambda0, nu = 2.0;
   int status = 0, it = 0, chunk_hint = 8;
+  const bool speculative = !(o.reserved & 1);
   if (o.verbose >= 2)
     printf("   Iteration     Total nfev        Cost      Cost reduction    Step norm     Optimality   \n");
+  // One host synchronisation per LM iteration: the whole iteration (elimination, a predicted number
+  // of PCG steps, back-substitution, the trial evaluation -- speculatively with its Jacobian -- and,
+  // after an accepted step, the camera blocks of the next one) is enqueued before the host looks at
+  // any scalar.  The gradient norm of the state the solve started from arrives with the same copy;
+  // if it is already below gtol the enqueued work is discarded (same decisions as checking first).
+  bool g_pending = false;   // g_norm of the current state is still in flight
   while (it < o.max_iter) {
-    if (g_norm < o.gtol) { status = 1; break; }
-    int q = 0, brk = 0;
-    CKR(run_solve(c, lam, o.pcg_tol, o.pcg_max_iter, &chunk_hint, &q, &brk));
+    if (!g_pending && g_norm < o.gtol) { status = 1; break; }
+    SolvePlan sp;
+    CKR(solve_setup(c, lam, o.pcg_tol, o.pcg_max_iter, &sp));
+    int launch = std::max(1, std::min(chunk_hint, o.pcg_max_iter));
+    bool trial_done = false;
+    while (true) {
+      CKR(solve_iterate(c, &sp, launch));
+      CKR(solve_finish(c, &sp));
+      if (speculative) CKR(run_jacobian(c, true)); else CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
+      CKR(allreduce_sum(c, &c->scal.p->cost, 5));  // cost, rjd, jd2, dl2, x2_lines are contiguous
+      CKR(fetch_scalars(c));
+      trial_done = c->h_cgst->done || sp.issued >= o.pcg_max_iter;
+      if (trial_done) break;
+      launch = 4;   // the prediction was short: more PCG steps, then redo the (cheap to discard) tail
+    }
+    if (g_pending) {
+      g_norm = gnorm_host(c);
+      g_pending = false;
+      if (g_norm < o.gtol) { status = 1; break; }
+    }
+    const int q = c->h_cgst->k;
+    chunk_hint = q + 1;
     rep->pcg_iters_total += q;
-    // trial evaluation at x + delta (k_cam_step prepared the camera records of the candidate)
-    CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
-    rep->n_res += 1;
-    CKR(allreduce_sum(c, &c->scal.p->cost, 5));  // cost, rjd, jd2, dl2, x2_lines are contiguous
-    CKR(fetch_scalars(c));
+    if (speculative) rep->n_jac += 1; else rep->n_res += 1;
     const Scalars s = *c->h_scal;
     const double cost_new = s.cost;
     const double pred = -s.rjd - 0.5 * s.jd2;
@@ -867,16 +936,11 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
              accepted ? "ok" : "rej");
     ++it;
     if (accepted) {
-      std::swap(c->cams.p, c->cams_new.p); std::swap(c->cams.n, c->cams_new.n);
-      std::swap(c->pts.p, c->pts_new.p); std::swap(c->pts.n, c->pts_new.n);
-      std::swap(c->recs.p, c->recs_new.p); std::swap(c->recs.n, c->recs_new.n);
-      std::swap(c->Gm.p, c->Gm_new.p); std::swap(c->Gm.n, c->Gm_new.n);
+      accept_candidate(c, speculative);
       cost = cost_new;
-      CKR(run_jacobian(c));
-      rep->n_jac += 1;
-      CKR(run_blocks(c, false));
-      CKR(fetch_scalars(c));
-      g_norm = gnorm_host(c);
+      if (!speculative) { CKR(run_jacobian(c, false)); rep->n_jac += 1; }
+      CKR(run_blocks(c, false));   // camera gradient / scaling of the new state; its norm is read at the next sync
+      g_pending = true;
       lam = lam * std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * ratio - 1.0, 3.0));
       lam = std::min(std::max(lam, o.lambda_min), o.lambda_max);
       nu = 2.0;
@@ -889,6 +953,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     else if (xtol_ok) status = 3;
     if (status) break;
   }
+  if (g_pending) { CKR(fetch_scalars(c)); g_norm = gnorm_host(c); }
   rep->iterations = it;
   rep->status = status;
   rep->cost = cost;

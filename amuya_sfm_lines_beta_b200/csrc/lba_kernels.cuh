@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict_
   double acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+#pragma unroll 4
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     double x[6];
     load6(jc + (size_t)j * 6, x);
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+#pragma unroll 2
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     const int i = cam_perm[j];
     double x[6];
@@ -587,39 +589,64 @@ __global__ void k_cam_post(int nc, const double* __restrict__ S, const double* _
 // per line: Vinv = (V + lam Dl)^-1, y = Vinv gl.  scaling_mode: 0 keep Dl, 1 Dl = max(Dl, diag V),
 // 2 Dl = diag V (first Jacobian); zeros -> 1  (Marquardt scaling, the analogue of scipy's
 // compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at bundle_adjustment.py:319).
-__global__ void __launch_bounds__(128) k_line_factor(int nl, double lam, const double* __restrict__ V,
-                                                      double* __restrict__ Dl, const double* __restrict__ gl,
-                                                      double* __restrict__ Vinv, double* __restrict__ y,
-                                                      int* __restrict__ clamped, int scaling_mode) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= nl) return;
-  double S[21];
-#pragma unroll
-  for (int e = 0; e < 21; ++e) S[e] = V[(size_t)l * 21 + e];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    double D;
-    if (scaling_mode == 0) {
-      D = Dl[(size_t)l * 6 + k];
-    } else {
-      double d = S[sym_idx(k, k)];
-      if (d == 0.0) d = 1.0;
-      D = scaling_mode == 2 ? d : fmax(Dl[(size_t)l * 6 + k], d);
-      Dl[(size_t)l * 6 + k] = D;
-    }
-    S[sym_idx(k, k)] += lam * D;
+constexpr int kLfLines = 128;  // lines per CTA of k_line_factor
+__global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, const double* __restrict__ V,
+                                                           double* __restrict__ Dl, const double* __restrict__ gl,
+                                                           double* __restrict__ Vinv, double* __restrict__ y,
+                                                           int* __restrict__ clamped, int scaling_mode) {
+  // the per-line records are AoS (21 / 6 / 22 doubles): move them through shared memory so that
+  // global traffic is fully coalesced and each thread reads its own row conflict-free (odd strides)
+  __shared__ double sV[kLfLines * kVinvStride];
+  __shared__ double sD[kLfLines * 6];
+  __shared__ double sg[kLfLines * 6];
+  const int l0 = blockIdx.x * kLfLines;
+  const int n = min(kLfLines, nl - l0);
+  const int t = threadIdx.x;
+  for (int q = t; q < n * 21; q += kLfLines) sV[q] = __ldg(V + (size_t)l0 * 21 + q);
+  for (int q = t; q < n * 6; q += kLfLines) {
+    sg[q] = __ldg(gl + (size_t)l0 * 6 + q);
+    if (scaling_mode != 2) sD[q] = Dl[(size_t)l0 * 6 + q];
   }
-  const int cl = spd6_inverse(S);
+  __syncthreads();
+  double S[21], yy[6];
+  int cl = 0;
+  if (t < n) {
+#pragma unroll
+    for (int e = 0; e < 21; ++e) S[e] = sV[t * 21 + e];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double D;
+      if (scaling_mode == 0) {
+        D = sD[t * 6 + k];
+      } else {
+        double d = S[sym_idx(k, k)];
+        if (d == 0.0) d = 1.0;
+        D = scaling_mode == 2 ? d : fmax(sD[t * 6 + k], d);
+        sD[t * 6 + k] = D;
+      }
+      S[sym_idx(k, k)] += lam * D;
+    }
+    cl = spd6_inverse(S);
+    double g[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = sg[t * 6 + k];
+    sym6_matvec(S, g, yy);
+  }
   if (cl) atomicAdd(clamped, cl);
-  double g[6], yy[6];
+  __syncthreads();
+  if (t < n) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) g[k] = gl[(size_t)l * 6 + k];
-  sym6_matvec(S, g, yy);
+    for (int e = 0; e < 21; ++e) sV[t * kVinvStride + e] = S[e];
+    sV[t * kVinvStride + 21] = 0.0;
 #pragma unroll
-  for (int e = 0; e < 21; ++e) Vinv[(size_t)l * kVinvStride + e] = S[e];
-  Vinv[(size_t)l * kVinvStride + 21] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) y[(size_t)l * 6 + k] = yy[k];
+    for (int k = 0; k < 6; ++k) sg[t * 6 + k] = yy[k];
+  }
+  __syncthreads();
+  for (int q = t; q < n * kVinvStride; q += kLfLines) Vinv[(size_t)l0 * kVinvStride + q] = sV[q];
+  for (int q = t; q < n * 6; q += kLfLines) {
+    y[(size_t)l0 * 6 + q] = sg[q];
+    if (scaling_mode != 0) Dl[(size_t)l0 * 6 + q] = sD[q];
+  }
 }
 
 // per camera: Minv = (lam Dc + Mpart)^-1 (block-Jacobi), b = -gc + bpart (Schur rhs)
@@ -910,6 +937,7 @@ __global__ void __launch_bounds__(kCamThreads) k_pcg_cam(const int* __restrict__
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
   double acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
   for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
     const double wi = __ldg(w + cam_perm[j]);
     double x[6];
