@@ -9,6 +9,7 @@
 #include "../../include/lba.h"
 #include "lba_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -109,7 +110,9 @@ struct lba_ctx {
   DBuf<int> obs_cam, cam_pos, cam_perm, cam_ptr, slot_src;
   DBuf<unsigned char> obs_ll;
   DBuf<TileMeta> meta;
-  DBuf<double> cst, dense_tmp;
+  DBuf<int> sort_tmp;            // keys/values in and out of the device radix sort (4 x Mp)
+  DBuf<unsigned char> cub_tmp;
+  DBuf<double> cst, dense_tmp, h2d_stage;   // h2d_stage: grow-only staging for host-side n/p0/p1
   // persistent-grid sizes and dynamic shared memory of the pipelined line-order kernels
   int grid_eval_j = 1, grid_eval_r = 1, grid_lp[3] = {1, 1, 1};
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
@@ -357,6 +360,14 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CK(cudaSetDevice(ctx->device));
   const int m = (int)m64, nc = (int)nc64, nl = (int)nl64;
   ctx->have_problem = ctx->have_eval = ctx->have_blocks = ctx->have_scaling = false;
+  const bool dbg = getenv("LBA_DEBUG_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lba_set_problem] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
 
   // indices to the host (they drive the one-time layout construction)
   std::vector<int64_t> hc, hl;
@@ -383,6 +394,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   if (kmax > LBA_MAX_OBS_PER_LINE)
     return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
 
+  lap("validate + line histogram");
   // line order: stable counting sort by line (identity when the input is already sorted)
   std::vector<int> order(m);   // line-sorted position -> caller's observation index
   if (sorted) {
@@ -406,13 +418,14 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     }
     if (open) meta.push_back(cur);
   }
+  lap("order + tiles");
   const int ntiles = (int)meta.size();
   const long long Mp64 = (long long)ntiles * kTile;
   if (Mp64 > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "padded observation count out of range");
   const int Mp = (int)Mp64;
   int lmax = 8;
   for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 7) & ~7);
-  std::vector<int> obs_cam((size_t)Mp, -1), slot_src((size_t)Mp, -1), slot_of_sorted(m);
+  std::vector<int> obs_cam((size_t)Mp, -1), slot_src((size_t)Mp, -1);
   std::vector<unsigned char> obs_ll((size_t)Mp, 0);
   for (int g = 0; g < ntiles; ++g) {
     const TileMeta& t = meta[g];
@@ -425,55 +438,57 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
         obs_cam[slot] = (int)pc[src];
         obs_ll[slot] = (unsigned char)ll;
         slot_src[slot] = src;
-        slot_of_sorted[sorted_pos] = (int)slot;
       }
     }
   }
-  // camera order: stable counting sort of the line-ordered observations by camera
-  std::vector<int> cam_ptr((size_t)nc + 1, 0), cam_perm(m), cam_pos((size_t)Mp, 0);
-  for (int i = 0; i < m; ++i) ++cam_ptr[(size_t)pc[i] + 1];
-  for (int c = 0; c < nc; ++c) cam_ptr[(size_t)c + 1] += cam_ptr[c];
-  {
-    std::vector<int> cur(cam_ptr.begin(), cam_ptr.end() - 1);
-    for (int i = 0; i < m; ++i) {
-      const int slot = slot_of_sorted[i];
-      const int j = cur[obs_cam[slot]]++;
-      cam_perm[j] = slot;
-      cam_pos[slot] = j;
-    }
-  }
-
+  lap("slot arrays");
   ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ntiles = ntiles; ctx->Mp = Mp; ctx->lmax = lmax;
   CKR(upload(ctx, ctx->obs_cam, obs_cam));
   CKR(upload(ctx, ctx->obs_ll, obs_ll));
-  CKR(upload(ctx, ctx->cam_pos, cam_pos));
-  CKR(upload(ctx, ctx->cam_perm, cam_perm));
-  CKR(upload(ctx, ctx->cam_ptr, cam_ptr));
+  // camera order on the device: stable LSD radix sort of (camera, slot) keeps the slot (line) order
+  // inside every camera, like the stable counting sort it replaces
+  CKR(ctx->cam_pos.alloc((size_t)Mp)); CKR(ctx->cam_perm.alloc((size_t)Mp)); CKR(ctx->cam_ptr.alloc((size_t)nc + 1));
+  if (Mp > 0) {
+    CKR(ctx->sort_tmp.alloc((size_t)3 * Mp));
+    int* keys_in = ctx->sort_tmp.p; int* vals_in = keys_in + Mp; int* keys_out = vals_in + Mp;
+    LAUNCH(ctx, LBA_K_MISC, k_cam_keys, cdiv(Mp, 256), 256, Mp, nc, ctx->obs_cam.p, keys_in, vals_in);
+    int end_bit = 1;
+    while ((1LL << end_bit) <= nc) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, ctx->cam_perm.p, Mp, 0, end_bit, ctx->stream));
+    CKR(ctx->cub_tmp.alloc(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, ctx->cam_perm.p, Mp, 0, end_bit, ctx->stream));
+    CK(cudaMemsetAsync(ctx->cam_pos.p, 0, (size_t)Mp * 4, ctx->stream));
+    LAUNCH(ctx, LBA_K_MISC, k_cam_index, cdiv(Mp, 256), 256, Mp, m, nc, keys_out, ctx->cam_perm.p, ctx->cam_pos.p, ctx->cam_ptr.p);
+  } else {
+    CK(cudaMemsetAsync(ctx->cam_ptr.p, 0, ((size_t)nc + 1) * 4, ctx->stream));
+  }
   CKR(upload(ctx, ctx->slot_src, slot_src));
   CKR(upload(ctx, ctx->meta, meta));
 
+  lap("index uploads (async)");
   // observation constants: AoS (m,3) -> SoA over slots, m_e = n x p_e
   CKR(ctx->cst.alloc((size_t)9 * Mp));
   if (m > 0) {
-    DBuf<double> tmp;
     const double* src[3] = {n, p0, p1};
     const double* dev[3];
     size_t need = 0;
     for (int k = 0; k < 3; ++k) if (!is_device_ptr(src[k])) need += (size_t)3 * m;
-    CKR(tmp.alloc(need));
+    CKR(ctx->h2d_stage.alloc(need));
+    lap("staging alloc");
     size_t off = 0;
     for (int k = 0; k < 3; ++k) {
       if (is_device_ptr(src[k])) { dev[k] = src[k]; continue; }
-      CK(cudaMemcpyAsync(tmp.p + off, src[k], (size_t)3 * m * 8, cudaMemcpyHostToDevice, ctx->stream));
-      dev[k] = tmp.p + off;
+      CK(cudaMemcpyAsync(ctx->h2d_stage.p + off, src[k], (size_t)3 * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+      dev[k] = ctx->h2d_stage.p + off;
       off += (size_t)3 * m;
     }
     LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(Mp, 256), 256, Mp, ctx->slot_src.p, dev[0], dev[1], dev[2], ctx->cst.p);
-    CK(cudaStreamSynchronize(ctx->stream));  // tmp and the host vectors go out of scope
+    CK(cudaStreamSynchronize(ctx->stream));  // the host index vectors go out of scope
   } else {
     CK(cudaStreamSynchronize(ctx->stream));
   }
-
+  lap("constants H2D + transpose + sync");
   // persistent grids: SMs x resident CTAs for each pipelined kernel at this problem's stage size
   {
     auto plan = [&](auto kern, int threads, int smem, int nsub, int* grid) -> int {
@@ -511,6 +526,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     CKR(plan(k_line_pass<kModeScalars>, kTile, ctx->smem_lp[2], 1, &ctx->grid_lp[2]));
   }
 
+  lap("kernel planning");
   // state buffers
   const size_t M = (size_t)Mp, NC = (size_t)nc, NL = (size_t)nl;
   const size_t NG = (size_t)std::max({ctx->grid_eval_j, ctx->grid_eval_r, ctx->grid_lp[1], 1});
@@ -527,6 +543,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
   CKR(ctx->tab.alloc(NC * 6)); CKR(ctx->qpart.alloc(NC * 6));
   CKR(ctx->cost_partial.alloc(NG)); CKR(ctx->bs_partial.alloc(NG * 4));
+  lap("state buffers");
   ctx->have_problem = true;
   if (ctx->launch_err) return LBA_ERR_CUDA;
   return LBA_OK;

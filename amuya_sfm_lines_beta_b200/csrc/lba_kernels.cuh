@@ -206,6 +206,27 @@ __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* _
   }
 }
 
+// ---- camera order on the device: stable radix sort of (camera, slot), then these two kernels ----
+__global__ void k_cam_keys(int Mp, int nc, const int* __restrict__ obs_cam, int* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp) return;
+  const int c = obs_cam[i];
+  keys[i] = c < 0 ? nc : c;   // padding slots sort behind every camera
+  vals[i] = i;
+}
+// sorted (key, slot) -> cam_pos[slot] = j, cam_ptr[c] = first j with key >= c
+__global__ void k_cam_index(int Mp, int m, int nc, const int* __restrict__ keys, const int* __restrict__ slots,
+                            int* __restrict__ cam_pos, int* __restrict__ cam_ptr) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Mp) return;
+  const int k = keys[j];
+  if (j < m) cam_pos[slots[j]] = j;
+  const int kprev = j > 0 ? keys[j - 1] : -1;
+  for (int c = kprev + 1; c <= k && c <= nc; ++c) cam_ptr[c] = j;
+  if (j == Mp - 1)
+    for (int c = k + 1; c <= nc; ++c) cam_ptr[c] = m;
+}
+
 // point_wise_input (:235-243) integer expansion, in the caller's observation order.
 __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, const int* __restrict__ obs_cam,
                                      const unsigned char* __restrict__ obs_ll, const TileMeta* __restrict__ meta,
