@@ -107,9 +107,8 @@ struct lba_ctx {
   // problem
   int m = 0, nc = 0, nl = 0, ntiles = 0, Mp = 0, lmax = 8;
   bool have_problem = false, have_eval = false, have_blocks = false, have_scaling = false;
-  DBuf<int> obs_cam, cam_pos, cam_perm, cam_ptr, slot_src;
-  DBuf<unsigned char> obs_ll;
-  DBuf<TileMeta> meta;
+  DBuf<int> cam_perm, cam_ptr, slot_src;
+  DBuf<TileIdx> tidx;
   DBuf<int> sort_tmp;            // keys/values in and out of the device radix sort (4 x Mp)
   DBuf<unsigned char> cub_tmp;
   DBuf<double> cst, dense_tmp, h2d_stage;   // h2d_stage: grow-only staging for host-side n/p0/p1
@@ -129,7 +128,7 @@ struct lba_ctx {
   DBuf<double> V, V_new, gl, gl_new, Vinv, y, Dl;
   DBuf<double> U, gc, Dc, Mpart, bpart, Minv, b;
   DBuf<double> cgx, cgr, cgz, cgp, tab, qpart;
-  DBuf<double> cost_partial, bs_partial;
+  DBuf<double> cost_partial, bs_partial, cam_partial;
   DBuf<Scalars> scal;
   DBuf<CgState> cgst;
   DBuf<unsigned long long> gbits, gbits_new;
@@ -425,46 +424,48 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   const int Mp = (int)Mp64;
   int lmax = 8;
   for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 7) & ~7);
-  std::vector<int> obs_cam((size_t)Mp, -1), slot_src((size_t)Mp, -1);
-  std::vector<unsigned char> obs_ll((size_t)Mp, 0);
+  std::vector<int> slot_src((size_t)Mp, -1);
+  std::vector<TileIdx> tidx((size_t)ntiles);
   for (int g = 0; g < ntiles; ++g) {
     const TileMeta& t = meta[g];
+    TileIdx& ti = tidx[g];
+    ti.meta = t;
+    memset(ti.ll, 0, sizeof ti.ll);
+    memset(ti.pos, 0, sizeof ti.pos);
+    for (int sl = 0; sl < kTile; ++sl) ti.cam[sl] = -1;
     int sorted_pos = line_ptr[t.l0];
     for (int ll = 0; ll < t.nl; ++ll) {
       const int s0 = ll ? t.lend[ll - 1] : 0, s1 = t.lend[ll];
       for (int sl = s0; sl < s1; ++sl, ++sorted_pos) {
         const size_t slot = (size_t)g * kTile + sl;
         const int src = order[sorted_pos];
-        obs_cam[slot] = (int)pc[src];
-        obs_ll[slot] = (unsigned char)ll;
+        ti.cam[sl] = (int)pc[src];
+        ti.ll[sl] = (unsigned char)ll;
         slot_src[slot] = src;
       }
     }
   }
   lap("slot arrays");
   ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ntiles = ntiles; ctx->Mp = Mp; ctx->lmax = lmax;
-  CKR(upload(ctx, ctx->obs_cam, obs_cam));
-  CKR(upload(ctx, ctx->obs_ll, obs_ll));
+  CKR(upload(ctx, ctx->tidx, tidx));
   // camera order on the device: stable LSD radix sort of (camera, slot) keeps the slot (line) order
   // inside every camera, like the stable counting sort it replaces
-  CKR(ctx->cam_pos.alloc((size_t)Mp)); CKR(ctx->cam_perm.alloc((size_t)Mp)); CKR(ctx->cam_ptr.alloc((size_t)nc + 1));
+  CKR(ctx->cam_perm.alloc((size_t)Mp)); CKR(ctx->cam_ptr.alloc((size_t)nc + 1));
   if (Mp > 0) {
     CKR(ctx->sort_tmp.alloc((size_t)3 * Mp));
     int* keys_in = ctx->sort_tmp.p; int* vals_in = keys_in + Mp; int* keys_out = vals_in + Mp;
-    LAUNCH(ctx, LBA_K_MISC, k_cam_keys, cdiv(Mp, 256), 256, Mp, nc, ctx->obs_cam.p, keys_in, vals_in);
+    LAUNCH(ctx, LBA_K_MISC, k_cam_keys, cdiv(Mp, 256), 256, Mp, nc, ctx->tidx.p, keys_in, vals_in);
     int end_bit = 1;
     while ((1LL << end_bit) <= nc) ++end_bit;
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, ctx->cam_perm.p, Mp, 0, end_bit, ctx->stream));
     CKR(ctx->cub_tmp.alloc(tmp_bytes));
     CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, ctx->cam_perm.p, Mp, 0, end_bit, ctx->stream));
-    CK(cudaMemsetAsync(ctx->cam_pos.p, 0, (size_t)Mp * 4, ctx->stream));
-    LAUNCH(ctx, LBA_K_MISC, k_cam_index, cdiv(Mp, 256), 256, Mp, m, nc, keys_out, ctx->cam_perm.p, ctx->cam_pos.p, ctx->cam_ptr.p);
+    LAUNCH(ctx, LBA_K_MISC, k_cam_index, cdiv(Mp, 256), 256, Mp, m, nc, keys_out, ctx->cam_perm.p, ctx->tidx.p, ctx->cam_ptr.p);
   } else {
     CK(cudaMemsetAsync(ctx->cam_ptr.p, 0, ((size_t)nc + 1) * 4, ctx->stream));
   }
   CKR(upload(ctx, ctx->slot_src, slot_src));
-  CKR(upload(ctx, ctx->meta, meta));
 
   lap("index uploads (async)");
   // observation constants: AoS (m,3) -> SoA over slots, m_e = n x p_e
@@ -543,6 +544,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
   CKR(ctx->tab.alloc(NC * 6)); CKR(ctx->qpart.alloc(NC * 6));
   CKR(ctx->cost_partial.alloc(NG)); CKR(ctx->bs_partial.alloc(NG * 4));
+  CKR(ctx->cam_partial.alloc(2 * (size_t)cdiv(std::max(nc, 1), kCamStepThreads)));
   lap("state buffers");
   ctx->have_problem = true;
   if (ctx->launch_err) return LBA_ERR_CUDA;
@@ -557,8 +559,7 @@ static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc *
 static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
   EvalArgs a;
   a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3;
-  a.meta = c->meta.p; a.obs_cam = c->obs_cam.p;
-  a.obs_ll = c->obs_ll.p; a.cam_pos = c->cam_pos.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
+  a.tidx = c->tidx.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
   a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p;
   a.cost_partial = c->cost_partial.p;
   a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost; a.gbits = c->gbits.p;
@@ -684,8 +685,7 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     c->line_scaling_mode = 0;
   }
   LinePassArgs& la = sp->la;
-  la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.meta = c->meta.p; la.obs_cam = c->obs_cam.p;
-  la.obs_ll = c->obs_ll.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
+  la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.tidx = c->tidx.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
   la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p;
   la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &c->scal.p->rjd; la.st = c->cgst.p;
   if (c->ntiles > 0)
@@ -726,8 +726,11 @@ static int solve_finish(lba_ctx* c, SolvePlan* sp) {
     if (c->nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
   }
-  LAUNCH(c, LBA_K_MISC, k_cam_step, 1, 1024, c->nc, c->cams.p, c->cgx.p, c->cams_new.p, c->recs_new.p, c->Gm_new.p,
-         &c->scal.p->dc2, &c->scal.p->x2_cams);
+  if (c->nc > 0)
+    LAUNCH(c, LBA_K_MISC, k_cam_step, cdiv(c->nc, kCamStepThreads), kCamStepThreads, c->nc, c->cams.p, c->cgx.p, c->cams_new.p,
+           c->recs_new.p, c->Gm_new.p, c->cam_partial.p, c->tickets.p + 2, &c->scal.p->dc2);
+  else
+    CK(cudaMemsetAsync(&c->scal.p->dc2, 0, 16, c->stream));
   return LBA_OK;
 }
 
@@ -781,8 +784,8 @@ extern "C" int lba_point_wise_indices(lba_ctx* ctx, int64_t* cam_pt, int64_t* pt
   if (m == 0) return LBA_OK;
   DBuf<long long> tmp;
   CKR(tmp.alloc((size_t)4 * m));
-  LAUNCH(ctx, LBA_K_MISC, k_point_wise_indices, cdiv(ctx->Mp, 256), 256, ctx->Mp, ctx->slot_src.p, ctx->obs_cam.p,
-         ctx->obs_ll.p, ctx->meta.p, tmp.p, tmp.p + (size_t)2 * m);
+  LAUNCH(ctx, LBA_K_MISC, k_point_wise_indices, cdiv(ctx->Mp, 256), 256, ctx->Mp, ctx->slot_src.p, ctx->tidx.p,
+         tmp.p, tmp.p + (size_t)2 * m);
   CK(cudaMemcpyAsync(cam_pt, tmp.p, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(pt_idx, tmp.p + (size_t)2 * m, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -798,8 +801,8 @@ extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, 
   DBuf<double> tmp;
   CKR(tmp.alloc((size_t)6 * m));
   ProjectArgs a;
-  a.Mp = ctx->Mp; a.slot_src = ctx->slot_src.p; a.obs_cam = ctx->obs_cam.p; a.obs_ll = ctx->obs_ll.p;
-  a.meta = ctx->meta.p; a.recs = ctx->recs.p; a.pts = ctx->pts.p; a.proj = tmp.p;
+  a.Mp = ctx->Mp; a.slot_src = ctx->slot_src.p; a.tidx = ctx->tidx.p; a.recs = ctx->recs.p; a.pts = ctx->pts.p;
+  a.proj = tmp.p;
   LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(ctx->Mp, 256), 256, a);
   CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -830,7 +833,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
     DBuf<double> tmp;
     CKR(tmp.alloc((size_t)12 * m));
     LAUNCH(ctx, LBA_K_MISC, k_export_jacobian, cdiv(ctx->Mp, 256), 256, ctx->Mp, ctx->slot_src.p,
-           ctx->cam_pos.p, ctx->jl.p, ctx->jc.p, tmp.p, tmp.p + (size_t)6 * m);
+           ctx->tidx.p, ctx->jl.p, ctx->jc.p, tmp.p, tmp.p + (size_t)6 * m);
     CK(cudaMemcpyAsync(jcam, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaMemcpyAsync(jline, tmp.p + (size_t)6 * m, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

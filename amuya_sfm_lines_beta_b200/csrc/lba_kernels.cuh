@@ -4,11 +4,13 @@
 // -------------------------------------------------------------------------
 // LINE ORDER, tile-aligned "slots".  Observations are sorted by 3D line (the reference's own
 //   order, seq_utils.py:188-195) and packed into tiles of kTile = 256 slots; a tile holds whole
-//   lines only (<= kMaxLinesPerTile), the unused tail slots are padding (obs_cam = -1).  Every
-//   per-observation array has Mp = ntiles*256 entries, so tile g of any array is the aligned
-//   2 KB block [g*256, (g+1)*256) and can be moved by ONE bulk-async copy (TMA, cp.async.bulk):
-//     cst[9][Mp] = n, m0 = n x p0, m1 = n x p1;  obs_cam[Mp]; obs_ll[Mp] (local line id, u8);
-//     cam_pos[Mp]; r[Mp]; jl[6][Mp]; w[Mp]; wk[Mp]; wr[Mp];  TileMeta[ntiles]
+//   lines only (<= kMaxLinesPerTile), the unused tail slots are padding (camera = -1).  The
+//   per-observation data are packed TILE-MAJOR so that everything one kernel needs of a tile is
+//   a handful of contiguous, 16 B-aligned blocks, each moved by ONE bulk-async copy (TMA,
+//   cp.async.bulk):
+//     cst[ntiles][9][256] = n, m0 = n x p0, m1 = n x p1 (18 KB per tile);  jl[ntiles][6][256]
+//     (12 KB per tile);  TileIdx[ntiles] = {line table, local line id, camera, camera-order
+//     position} (2.5 KB per tile);  r, w, wk, wr: [Mp] (2 KB per tile)
 // CAMERA ORDER (stable counting sort of the same observations by camera), dense m entries:
 //     jc[m][6] (one 48 B record per observation, so the scatter from the line-ordered Jacobian
 //     kernel is 3 x 16 B stores); cam_perm[m] (camera-order position -> slot); cam_ptr[Nc+1]
@@ -33,6 +35,7 @@
 #pragma once
 #include "lba_geometry.cuh"
 #include <cooperative_groups.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace lba {
@@ -53,6 +56,21 @@ struct __align__(16) TileMeta {
   unsigned short lend[kMaxLinesPerTile];  // exclusive end slot of local line ll (start = lend[ll-1] or 0)
 };
 static_assert(sizeof(TileMeta) % 16 == 0, "TileMeta must be bulk-copyable");
+
+// Everything integer a tile needs, packed so that ONE bulk copy brings it in (a prefix of it for the
+// kernels that do not need the later members).
+struct __align__(16) TileIdx {
+  TileMeta meta;
+  unsigned char ll[kTile];   // local line id of the slot
+  int cam[kTile];            // camera of the slot, -1 for padding
+  int pos[kTile];            // camera-order position of the slot
+};
+static_assert(sizeof(TileIdx) % 16 == 0 && offsetof(TileIdx, cam) % 16 == 0 && offsetof(TileIdx, pos) % 16 == 0,
+              "TileIdx prefixes must be bulk-copyable");
+// tile-major packing of the per-slot double arrays: element (k, slot) of an NK-row array
+__host__ __device__ inline size_t tm_index(int nk, int k, size_t slot) {
+  return ((slot / kTile) * nk + k) * kTile + (slot % kTile);
+}
 
 // ---- bulk-async (TMA) + mbarrier primitives ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,19 +179,19 @@ __global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, cons
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
-  const size_t M = (size_t)Mp;
+  double* o = cst + tm_index(9, 0, (size_t)i);   // rows of this slot are kTile apart
   if (src < 0) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) cst[(size_t)k * M + i] = 0.0;
+    for (int k = 0; k < 9; ++k) o[k * kTile] = 0.0;
     return;
   }
   const size_t s = (size_t)src;
   const double nx = n[3 * s], ny = n[3 * s + 1], nz = n[3 * s + 2];
   const double ax = p0[3 * s], ay = p0[3 * s + 1], az = p0[3 * s + 2];
   const double bx = p1[3 * s], by = p1[3 * s + 1], bz = p1[3 * s + 2];
-  cst[0 * M + i] = nx; cst[1 * M + i] = ny; cst[2 * M + i] = nz;
-  cst[3 * M + i] = ny * az - nz * ay; cst[4 * M + i] = nz * ax - nx * az; cst[5 * M + i] = nx * ay - ny * ax;
-  cst[6 * M + i] = ny * bz - nz * by; cst[7 * M + i] = nz * bx - nx * bz; cst[8 * M + i] = nx * by - ny * bx;
+  o[0 * kTile] = nx; o[1 * kTile] = ny; o[2 * kTile] = nz;
+  o[3 * kTile] = ny * az - nz * ay; o[4 * kTile] = nz * ax - nx * az; o[5 * kTile] = nx * ay - ny * ax;
+  o[6 * kTile] = ny * bz - nz * by; o[7 * kTile] = nz * bx - nx * bz; o[8 * kTile] = nx * by - ny * bx;
 }
 
 // (Nc,6) interleaved [w0,c0,w1,c1,w2,c2] <-> internal [w,c]
@@ -207,20 +225,20 @@ __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* _
 }
 
 // ---- camera order on the device: stable radix sort of (camera, slot), then these two kernels ----
-__global__ void k_cam_keys(int Mp, int nc, const int* __restrict__ obs_cam, int* __restrict__ keys, int* __restrict__ vals) {
+__global__ void k_cam_keys(int Mp, int nc, const TileIdx* __restrict__ tidx, int* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
-  const int c = obs_cam[i];
+  const int c = tidx[i / kTile].cam[i % kTile];
   keys[i] = c < 0 ? nc : c;   // padding slots sort behind every camera
   vals[i] = i;
 }
 // sorted (key, slot) -> cam_pos[slot] = j, cam_ptr[c] = first j with key >= c
 __global__ void k_cam_index(int Mp, int m, int nc, const int* __restrict__ keys, const int* __restrict__ slots,
-                            int* __restrict__ cam_pos, int* __restrict__ cam_ptr) {
+                            TileIdx* __restrict__ tidx, int* __restrict__ cam_ptr) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mp) return;
   const int k = keys[j];
-  if (j < m) cam_pos[slots[j]] = j;
+  if (j < m) { const int sl = slots[j]; tidx[sl / kTile].pos[sl % kTile] = j; }
   const int kprev = j > 0 ? keys[j - 1] : -1;
   for (int c = kprev + 1; c <= k && c <= nc; ++c) cam_ptr[c] = j;
   if (j == Mp - 1)
@@ -228,15 +246,15 @@ __global__ void k_cam_index(int Mp, int m, int nc, const int* __restrict__ keys,
 }
 
 // point_wise_input (:235-243) integer expansion, in the caller's observation order.
-__global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, const int* __restrict__ obs_cam,
-                                     const unsigned char* __restrict__ obs_ll, const TileMeta* __restrict__ meta,
+__global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, const TileIdx* __restrict__ tidx,
                                      long long* __restrict__ cam_pt, long long* __restrict__ pt_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
   if (src < 0) return;
   const size_t o = (size_t)src;
-  const long long c = obs_cam[i], l = meta[i / kTile].l0 + obs_ll[i];
+  const TileIdx& ti = tidx[i / kTile];
+  const long long c = ti.cam[i % kTile], l = ti.meta.l0 + ti.ll[i % kTile];
   cam_pt[2 * o] = c; cam_pt[2 * o + 1] = c;
   pt_idx[2 * o] = 2 * l; pt_idx[2 * o + 1] = 2 * l + 1;
 }
@@ -247,15 +265,12 @@ __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, c
 struct EvalArgs {
   int Mp, ntiles, lmax;    // lmax: max lines per tile rounded up to 8 (sizes the smem stage)
   int nc, nstages;         // cameras (size of the shared-memory table), pipeline depth (<= kMaxStages)
-  const TileMeta* meta;
-  const int* obs_cam;
-  const unsigned char* obs_ll;
-  const int* cam_pos;
-  const double* cst;       // [9][Mp]
+  const TileIdx* tidx;     // [ntiles]
+  const double* cst;       // [ntiles][9][256]
   const CamRec* recs;
   const double* pts;       // [nl][6]
   double* r;               // [Mp]
-  double* jl;              // [6][Mp] slot order
+  double* jl;              // [ntiles][6][256]
   double* jc;              // [m][6] camera order, one 48 B record per observation
   double* V;               // [nl][21]
   double* gl;              // [nl][6]
@@ -276,12 +291,9 @@ __device__ __forceinline__ void sub_sync(int sub) {
   else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(kTile) : "memory");
 }
 
-// shared-memory stage of k_eval: cst[9][256] | cam[256] | cam_pos[256] | ll[256] | meta | pts[lmax][6]
-constexpr int kEvOffCam = 9 * kTile * 8;
-constexpr int kEvOffPos = kEvOffCam + kTile * 4;
-constexpr int kEvOffLl = kEvOffPos + kTile * 4;
-constexpr int kEvOffMeta = kEvOffLl + kTile;
-constexpr int kEvOffPts = kEvOffMeta + (int)sizeof(TileMeta);
+// shared-memory stage of k_eval: cst[9][256] | TileIdx | pts[lmax][6]   (three bulk copies per tile)
+constexpr int kEvOffIdx = 9 * kTile * 8;
+constexpr int kEvOffPts = kEvOffIdx + (int)sizeof(TileIdx);
 __host__ __device__ inline int eval_stage_bytes(int lmax) { return (kEvOffPts + lmax * 48 + 127) & ~127; }
 constexpr int kEvRow = 9;  // staging row stride in doubles: (jl[6], r, pad) -> 72 B, conflict-free per half-warp
 __host__ __device__ inline int eval_sub_bytes(int lmax, bool with_jac, int nstages) {
@@ -326,25 +338,20 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     const int tile = first + it * stride;
     unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
     uint64_t* bar = &full[sub][it % S];
-    const uint32_t bytes = 9 * kTile * 8 + kTile * 4 + (WITH_JAC ? kTile * 4 : 0) + kTile + (uint32_t)sizeof(TileMeta) + nl * 48;
-    mbar_expect_tx(bar, bytes);
-    const size_t o = (size_t)tile * kTile;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) bulk_g2s(st + k * kTile * 8, a.cst + (size_t)k * M + o, kTile * 8, bar);
-    bulk_g2s(st + kEvOffCam, a.obs_cam + o, kTile * 4, bar);
-    if (WITH_JAC) bulk_g2s(st + kEvOffPos, a.cam_pos + o, kTile * 4, bar);
-    bulk_g2s(st + kEvOffLl, a.obs_ll + o, kTile, bar);
-    bulk_g2s(st + kEvOffMeta, a.meta + tile, sizeof(TileMeta), bar);
+    const uint32_t idx_bytes = WITH_JAC ? (uint32_t)sizeof(TileIdx) : (uint32_t)offsetof(TileIdx, pos);
+    mbar_expect_tx(bar, 9 * kTile * 8 + idx_bytes + nl * 48);
+    bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
+    bulk_g2s(st + kEvOffIdx, a.tidx + tile, idx_bytes, bar);
     if (nl > 0) bulk_g2s(st + kEvOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
   };
   // the issuing thread keeps (l0, nl) of the tile it will issue next in registers, one iteration ahead
   int nx_l0 = 0, nx_nl = 0;
   if (t == 0) {
     for (int it = 0; it < S && it < my_n; ++it) {
-      const TileMeta* mt = a.meta + first + it * stride;
+      const TileMeta* mt = &a.tidx[first + it * stride].meta;
       issue(it, mt->nl, mt->l0);
     }
-    if (S < my_n) { const TileMeta* mt = a.meta + first + S * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
+    if (S < my_n) { const TileMeta* mt = &a.tidx[first + S * stride].meta; nx_l0 = mt->l0; nx_nl = mt->nl; }
   }
 
   double cost_acc = 0.0, gmax = 0.0;
@@ -352,14 +359,15 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     const int tile = first + it * stride;
     unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
     const double* s_cst = reinterpret_cast<const double*>(st);
-    const int* s_cam = reinterpret_cast<const int*>(st + kEvOffCam);
-    const int* s_pos = reinterpret_cast<const int*>(st + kEvOffPos);
-    const unsigned char* s_ll = st + kEvOffLl;
-    const TileMeta* s_meta = reinterpret_cast<const TileMeta*>(st + kEvOffMeta);
+    const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
+    const int* s_cam = s_idx->cam;
+    const int* s_pos = s_idx->pos;
+    const unsigned char* s_ll = s_idx->ll;
+    const TileMeta* s_meta = &s_idx->meta;
     const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
     int cur_l0 = 0, cur_nl = 0;
     if (t == 0 && it + S + 1 < my_n) {  // prefetch the scalars for the issue after next
-      const TileMeta* mt = a.meta + first + (it + S + 1) * stride;
+      const TileMeta* mt = &a.tidx[first + (it + S + 1) * stride].meta;
       cur_l0 = mt->l0; cur_nl = mt->nl;
     }
     mbar_wait(&full[sub][it % S], (it / S) & 1);
@@ -408,27 +416,67 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     cost_acc += r * r;
     if (WITH_JAC) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) a.jl[(size_t)k * M + i] = jl[k];
+      for (int k = 0; k < 6; ++k) a.jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
       // stage (jl, r) row-major with an odd-word stride for the per-line segmented sums
 #pragma unroll
       for (int k = 0; k < 6; ++k) s_stg[t * kEvRow + k] = jl[k];
       s_stg[t * kEvRow + 6] = r;
       sub_sync<NSUB>(sub);
+      // per-line blocks V_l = sum jl jl^T (21) and g_l = sum jl r (6): four register-blocked work
+      // items per line (rows {0}, {1}, {2,5}, {3,4} of the upper triangle: 7/6/7/7 FMAs per
+      // observation on 7/6/5/4 shared-memory loads), fixed summation order
       const int l0 = s_meta->l0, nlg = s_meta->nl;
-      const int nwork = nlg * 27;
-      for (int wi = t; wi < nwork; wi += kTile) {
-        const int ll = wi / 27, e = wi - ll * 27;
+      for (int wi = t; wi < nlg * 4; wi += kTile) {
+        const int ll = wi >> 2, part = wi & 3;
         const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        const int ca = e < 21 ? c_sym_a[e] : e - 21, cb = e < 21 ? c_sym_b[e] : 6;
-        double acc = 0.0;
-        for (int s = s0; s < s1; ++s) acc += s_stg[s * kEvRow + ca] * s_stg[s * kEvRow + cb];
-        if (e < 21) {
-          a.V[(size_t)(l0 + ll) * 21 + e] = acc;
+        double* Vo = a.V + (size_t)(l0 + ll) * 21;
+        double* go = a.gl + (size_t)(l0 + ll) * 6;
+        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        double g0 = 0.0, g1 = 0.0;
+        if (part == 0) {
+          for (int s = s0; s < s1; ++s) {
+            const double* row = s_stg + s * kEvRow;
+            const double x0 = row[0];
+#pragma unroll
+            for (int b = 0; b < 6; ++b) acc[b] += x0 * row[b];
+            acc[6] += x0 * row[6];
+          }
+#pragma unroll
+          for (int b = 0; b < 6; ++b) Vo[b] = acc[b];
+          go[0] = acc[6]; g0 = acc[6];
+        } else if (part == 1) {
+          for (int s = s0; s < s1; ++s) {
+            const double* row = s_stg + s * kEvRow;
+            const double x1 = row[1];
+#pragma unroll
+            for (int b = 1; b < 6; ++b) acc[b] += x1 * row[b];
+            acc[6] += x1 * row[6];
+          }
+#pragma unroll
+          for (int b = 1; b < 6; ++b) Vo[5 + b] = acc[b];   // sym_idx(1,b) = 6 + (b-1)
+          go[1] = acc[6]; g0 = acc[6];
+        } else if (part == 2) {
+          for (int s = s0; s < s1; ++s) {
+            const double* row = s_stg + s * kEvRow;
+            const double x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5], rr = row[6];
+            acc[0] += x2 * x2; acc[1] += x2 * x3; acc[2] += x2 * x4; acc[3] += x2 * x5; acc[4] += x2 * rr;
+            acc[5] += x5 * x5; acc[6] += x5 * rr;
+          }
+          Vo[11] = acc[0]; Vo[12] = acc[1]; Vo[13] = acc[2]; Vo[14] = acc[3]; go[2] = acc[4];
+          Vo[20] = acc[5]; go[5] = acc[6]; g0 = acc[4]; g1 = acc[6];
         } else {
-          a.gl[(size_t)(l0 + ll) * 6 + (e - 21)] = acc;
-          const double ab = fabs(acc);
-          gmax = (ab > gmax || ab != ab) ? ab : gmax;
+          for (int s = s0; s < s1; ++s) {
+            const double* row = s_stg + s * kEvRow;
+            const double x3 = row[3], x4 = row[4], x5 = row[5], rr = row[6];
+            acc[0] += x3 * x3; acc[1] += x3 * x4; acc[2] += x3 * x5; acc[3] += x3 * rr;
+            acc[4] += x4 * x4; acc[5] += x4 * x5; acc[6] += x4 * rr;
+          }
+          Vo[15] = acc[0]; Vo[16] = acc[1]; Vo[17] = acc[2]; go[3] = acc[3];
+          Vo[18] = acc[4]; Vo[19] = acc[5]; go[4] = acc[6]; g0 = acc[3]; g1 = acc[6];
         }
+        const double ab0 = fabs(g0), ab1 = fabs(g1);
+        gmax = (ab0 > gmax || ab0 != ab0) ? ab0 : gmax;   // NaN propagates
+        gmax = (ab1 > gmax || ab1 != ab1) ? ab1 : gmax;
       }
     }
     fence_proxy_async();
@@ -454,9 +502,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
 struct ProjectArgs {
   int Mp;
   const int* slot_src;
-  const int* obs_cam;
-  const unsigned char* obs_ll;
-  const TileMeta* meta;
+  const TileIdx* tidx;
   const CamRec* recs;
   const double* pts;
   double* proj;
@@ -466,7 +512,8 @@ __global__ void k_project(const ProjectArgs a) {
   if (i >= a.Mp) return;
   const int src = a.slot_src[i];
   if (src < 0) return;
-  const int cam = a.obs_cam[i], line = a.meta[i / kTile].l0 + a.obs_ll[i];
+  const TileIdx& ti = a.tidx[i / kTile];
+  const int cam = ti.cam[i % kTile], line = ti.meta.l0 + ti.ll[i % kTile];
   double w[3], c[3], A, B, C;
   load_camrec(a.recs, cam, w, c, A, B, C);
   double X[6];
@@ -723,10 +770,8 @@ __global__ void k_make_table(int nc, const double* __restrict__ Gm, const double
 
 struct LinePassArgs {
   int Mp, ntiles, lmax;
-  const TileMeta* meta;
-  const int* obs_cam;
-  const unsigned char* obs_ll;
-  const double* jl;      // [6][Mp]
+  const TileIdx* tidx;   // [ntiles]
+  const double* jl;      // [ntiles][6][256]
   const double* pts;     // [nl][6]
   const double* tab;     // [nc][6]
   const double* Vinv;    // [nl][22]
@@ -745,12 +790,10 @@ struct LinePassArgs {
 
 enum { kModeMatvec = 0, kModeBacksub = 1, kModeScalars = 2 };
 
-// stage: jl[6][256] | cam[256] | ll[256] | meta | pts[lmax][6] | Vinv[lmax][22] | aux[lmax][6] | r[256]
+// stage: jl[6][256] | TileIdx prefix (meta, ll, cam) | pts[lmax][6] | Vinv[lmax][22] | aux[lmax][6] | r[256]
 //   aux = gl (BACKSUB) or y (SCALARS)
-constexpr int kLpOffCam = 6 * kTile * 8;
-constexpr int kLpOffLl = kLpOffCam + kTile * 4;
-constexpr int kLpOffMeta = kLpOffLl + kTile;
-constexpr int kLpOffPts = kLpOffMeta + (int)sizeof(TileMeta);
+constexpr int kLpOffIdx = 6 * kTile * 8;
+constexpr int kLpOffPts = kLpOffIdx + (int)offsetof(TileIdx, pos);
 __host__ __device__ inline int lp_off_vinv(int lmax) { return kLpOffPts + lmax * 48; }
 __host__ __device__ inline int lp_off_aux(int lmax) { return lp_off_vinv(lmax) + lmax * kVinvStride * 8; }
 __host__ __device__ inline int lp_off_r(int lmax) { return lp_off_aux(lmax) + lmax * 48; }
@@ -794,17 +837,15 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     const int tile = first + it * stride;
     unsigned char* st = smem + (size_t)(it % kLpStages) * stage_bytes;
     uint64_t* bar = &full[it % kLpStages];
-    uint32_t bytes = 6 * kTile * 8 + kTile + (uint32_t)sizeof(TileMeta) + nl * kVinvStride * 8;
-    if (MODE != kModeScalars) bytes += kTile * 4 + nl * 48;
+    const uint32_t idx_bytes = MODE == kModeScalars ? (uint32_t)offsetof(TileIdx, cam) : (uint32_t)offsetof(TileIdx, pos);
+    uint32_t bytes = 6 * kTile * 8 + idx_bytes + nl * kVinvStride * 8;
+    if (MODE != kModeScalars) bytes += nl * 48;
     if (MODE != kModeMatvec) bytes += nl * 48;
     if (MODE == kModeBacksub) bytes += kTile * 8;
     mbar_expect_tx(bar, bytes);
     const size_t o = (size_t)tile * kTile;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) bulk_g2s(st + k * kTile * 8, a.jl + (size_t)k * M + o, kTile * 8, bar);
-    if (MODE != kModeScalars) bulk_g2s(st + kLpOffCam, a.obs_cam + o, kTile * 4, bar);
-    bulk_g2s(st + kLpOffLl, a.obs_ll + o, kTile, bar);
-    bulk_g2s(st + kLpOffMeta, a.meta + tile, sizeof(TileMeta), bar);
+    bulk_g2s(st, a.jl + (size_t)tile * 6 * kTile, 6 * kTile * 8, bar);
+    bulk_g2s(st + kLpOffIdx, a.tidx + tile, idx_bytes, bar);
     if (nl > 0) {
       if (MODE != kModeScalars) bulk_g2s(st + kLpOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
       bulk_g2s(st + off_vinv, a.Vinv + (size_t)l0 * kVinvStride, nl * kVinvStride * 8, bar);
@@ -816,10 +857,10 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   int nx_l0 = 0, nx_nl = 0;
   if (t == 0) {
     for (int it = 0; it < kLpStages && it < my_n; ++it) {
-      const TileMeta* mt = a.meta + first + it * stride;
+      const TileMeta* mt = &a.tidx[first + it * stride].meta;
       issue(it, mt->nl, mt->l0);
     }
-    if (kLpStages < my_n) { const TileMeta* mt = a.meta + first + kLpStages * stride; nx_l0 = mt->l0; nx_nl = mt->nl; }
+    if (kLpStages < my_n) { const TileMeta* mt = &a.tidx[first + kLpStages * stride].meta; nx_l0 = mt->l0; nx_nl = mt->nl; }
   }
 
   double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;  // BACKSUB partial sums
@@ -827,16 +868,17 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     const int tile = first + it * stride;
     unsigned char* st = smem + (size_t)(it % kLpStages) * stage_bytes;
     double* s_jl = reinterpret_cast<double*>(st);
-    const int* s_cam = reinterpret_cast<const int*>(st + kLpOffCam);
-    const unsigned char* s_ll = st + kLpOffLl;
-    const TileMeta* s_meta = reinterpret_cast<const TileMeta*>(st + kLpOffMeta);
+    const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kLpOffIdx);
+    const int* s_cam = s_idx->cam;
+    const unsigned char* s_ll = s_idx->ll;
+    const TileMeta* s_meta = &s_idx->meta;
     const double* s_pts = reinterpret_cast<const double*>(st + kLpOffPts);
     const double* s_vinv = reinterpret_cast<const double*>(st + off_vinv);
     const double* s_aux = reinterpret_cast<const double*>(st + off_aux);
     const double* s_r = reinterpret_cast<const double*>(st + off_r);
     int cur_l0 = 0, cur_nl = 0;
     if (t == 0 && it + kLpStages + 1 < my_n) {
-      const TileMeta* mt = a.meta + first + (it + kLpStages + 1) * stride;
+      const TileMeta* mt = &a.tidx[first + (it + kLpStages + 1) * stride].meta;
       cur_l0 = mt->l0; cur_nl = mt->nl;
     }
     mbar_wait(&full[it % kLpStages], (it / kLpStages) & 1);
@@ -1173,14 +1215,18 @@ __global__ void __launch_bounds__(1024) k_reduce_partials(int n, int ncols, cons
   }
 }
 
-// cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms.  One CTA.
-__global__ void __launch_bounds__(1024) k_cam_step(int nc, const double* __restrict__ cams,
-                                                    const double* __restrict__ dc, double* __restrict__ cams_new,
-                                                    CamRec* __restrict__ recs_new, double* __restrict__ Gm_new,
-                                                    double* __restrict__ out_dc2, double* __restrict__ out_x2) {
-  __shared__ double red[32];
+// cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms
+// (grid-wide sums by the last CTA, fixed order).
+constexpr int kCamStepThreads = 128;
+__global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const double* __restrict__ cams,
+                                                               const double* __restrict__ dc, double* __restrict__ cams_new,
+                                                               CamRec* __restrict__ recs_new, double* __restrict__ Gm_new,
+                                                               double* __restrict__ partial, unsigned int* ticket,
+                                                               double* __restrict__ out2 /* dc2, x2_cams */) {
+  __shared__ double red[kCamStepThreads / 32];
   double d2 = 0.0, x2 = 0.0;
-  for (int c = threadIdx.x; c < nc; c += 1024) {
+  const int c = blockIdx.x * kCamStepThreads + threadIdx.x;
+  if (c < nc) {
     CamRec rec;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -1199,9 +1245,8 @@ __global__ void __launch_bounds__(1024) k_cam_step(int nc, const double* __restr
 #pragma unroll
     for (int k = 0; k < 9; ++k) Gm_new[c * 9 + k] = G[k];
   }
-  const double s0 = block_sum<1024>(d2, red);
-  const double s1 = block_sum<1024>(x2, red);
-  if (threadIdx.x == 0) { *out_dc2 = s0; *out_x2 = s1; }
+  const double sums[2] = {block_sum<kCamStepThreads>(d2, red), block_sum<kCamStepThreads>(x2, red)};
+  last_cta_reduce<kCamStepThreads, 2>(sums, partial, ticket, out2, 1.0, red);
 }
 
 // inf-norm via order-preserving integer max on non-negative doubles (exact, order independent)
@@ -1234,20 +1279,20 @@ __global__ void k_slots_to_caller(int Mp, const int* __restrict__ slot_src, cons
 }
 
 // Jacobian rows in API layout: jcam (m,6) interleaved [w0,c0,w1,c1,w2,c2], jline (m,6); caller order.
-__global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, const int* __restrict__ cam_pos,
+__global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, const TileIdx* __restrict__ tidx,
                                   const double* __restrict__ jl, const double* __restrict__ jc,
                                   double* __restrict__ jcam, double* __restrict__ jline) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
   if (src < 0) return;
-  const size_t M = (size_t)Mp, o = (size_t)src;
-  const size_t pos = (size_t)cam_pos[i];
+  const size_t o = (size_t)src;
+  const size_t pos = (size_t)tidx[i / kTile].pos[i % kTile];
   for (int k = 0; k < 3; ++k) {
     jcam[o * 6 + 2 * k] = jc[pos * 6 + k];
     jcam[o * 6 + 2 * k + 1] = jc[pos * 6 + 3 + k];
   }
-  for (int k = 0; k < 6; ++k) jline[o * 6 + k] = jl[(size_t)k * M + i];
+  for (int k = 0; k < 6; ++k) jline[o * 6 + k] = jl[tm_index(6, k, (size_t)i)];
 }
 
 // ---------------------------------------------------------------------------------
