@@ -131,6 +131,9 @@ struct lba_ctx {
   DBuf<double> cost_partial, bs_partial, cam_partial;
   DBuf<Scalars> scal;
   DBuf<CgState> cgst;
+  DBuf<GridBar> gridbar;
+  DBuf<double> cg_partial;
+  int cg_ctas = 1;
   DBuf<unsigned long long> gbits, gbits_new;
   DBuf<int> clamped;
   Scalars* h_scal = nullptr;   // pinned
@@ -227,6 +230,9 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaMallocHost(&c->h_clamped, sizeof(int)));
   CKR(c->scal.alloc(1));
   CKR(c->cgst.alloc(1));
+  CKR(c->gridbar.alloc(1));
+  CKR(c->cg_partial.alloc(2 * kCgMaxCtas));
+  CK(cudaMemsetAsync(c->gridbar.p, 0, sizeof(GridBar), c->stream));
   CKR(c->gbits.alloc(1));
   CKR(c->gbits_new.alloc(1));
   CKR(c->clamped.alloc(1));
@@ -519,6 +525,12 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
+    {  // CG vector kernels spin on a grid barrier: the grid must be co-resident
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cg_step, kCgBlock, 0));
+      const int want = cdiv((long long)std::max(nc, 1) * 8, kCgBlock);
+      ctx->cg_ctas = std::max(1, std::min({want, kCgMaxCtas, std::max(1, nb) * ctx->n_sm}));
+    }
     ctx->smem_lp[0] = lp_smem_bytes(lmax, kModeMatvec);
     ctx->smem_lp[1] = lp_smem_bytes(lmax, kModeBacksub);
     ctx->smem_lp[2] = lp_smem_bytes(lmax, kModeScalars);
@@ -701,7 +713,8 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
   ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
-  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, kCgCtas, kCgBlock, ca);
+  ca.partial = c->cg_partial.p; ca.gb = c->gridbar.p;
+  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, c->cg_ctas, kCgBlock, ca);
   sp->issued = 0;
   return LBA_OK;
 }
@@ -712,7 +725,7 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
     if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
     if (c->nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
     CKR(allreduce_sum(c, c->qpart.p, (size_t)c->nc * 6));
-    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, kCgCtas, kCgBlock, sp->ca);
+    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
   }
   CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
   return LBA_OK;

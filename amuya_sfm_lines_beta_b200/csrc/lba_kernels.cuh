@@ -34,7 +34,6 @@
 // every sum has a fixed order, so results are bit-reproducible run to run.
 #pragma once
 #include "lba_geometry.cuh"
-#include <cooperative_groups.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -1023,6 +1022,7 @@ __global__ void __launch_bounds__(kCamThreads) k_pcg_cam(const int* __restrict__
   }
 }
 
+struct GridBar;
 struct CgArgs {
   int nc;
   double lam, tol2;
@@ -1035,24 +1035,44 @@ struct CgArgs {
   const double* qpart;  // [nc][6] (all-reduced partial S p without the damping term)
   double* x; double* r; double* z; double* p; double* tab;
   CgState* st;
+  double* partial;   // [2][kCgMaxCtas] block sums of the grid-wide reductions
+  GridBar* gb;
 };
 
-// The CG vector work is one thread-block CLUSTER (8 CTAs x 512 threads on 8 SMs of one GPC): every
-// camera owns 8 consecutive lanes (6 active), dot products are reduced inside each CTA and then
-// combined through distributed shared memory in rank order, so every CTA holds the same bits.
-constexpr int kCgCtas = 8;
+// The CG vector work runs on a small co-resident grid (<= one CTA per SM): every camera owns 8
+// consecutive lanes (6 active); the two dot products of a step are grid-wide sums done with a
+// software grid barrier -- each CTA publishes its block sum, arrives on a global counter, spins until
+// all CTAs have arrived and then adds the partials in CTA order, so every CTA holds the same bits.
 constexpr int kCgBlock = 512;
+constexpr int kCgMaxCtas = 128;
 
-__device__ __forceinline__ double cluster_sum(double v, double* red, double* slot /* this CTA's slot in smem */) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cl = cg::this_cluster();
+struct GridBar {
+  unsigned long long count;   // monotonically increasing arrival counter
+  unsigned long long base;    // value of `count` when the current launch started
+};
+
+__device__ __forceinline__ double grid_sum(double v, double* red, double* partial /*[gridDim]*/, GridBar* gb,
+                                           unsigned long long target) {
   const double mine = block_sum<kCgBlock>(v, red);
-  if (threadIdx.x == 0) *slot = mine;
-  cl.sync();
-  double tot = 0.0;
-#pragma unroll
-  for (int rk = 0; rk < kCgCtas; ++rk) tot += *cl.map_shared_rank(slot, rk);
-  return tot;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = mine;
+    __threadfence();
+    atomicAdd(&gb->count, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(&gb->count) < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+  // one warp adds the published block sums (lane-strided, then the butterfly: the same order in every CTA)
+  if (threadIdx.x < 32) {
+    double tot = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) tot += __ldcg(partial + b);
+    tot = warp_sum(tot);
+    if (threadIdx.x == 0) red[0] = tot;
+  }
+  __syncthreads();
+  const double out = red[0];
+  __syncthreads();
+  return out;
 }
 
 // z_k = sum_j Minv[k][j] r_j inside an 8-lane camera group (lane k holds r_k)
@@ -1092,13 +1112,12 @@ __device__ __forceinline__ void group_table(const double* __restrict__ G, const 
 }
 
 // x = 0, r = b, z = Minv r, p = z, rz0 = r.z ; table(p)
-__global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
-  namespace cg = cooperative_groups;
+__global__ void __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
   __shared__ double red[kCgBlock / 32];
-  __shared__ double slot[2];
+  const unsigned long long base = a.gb->base;
   const int gt = blockIdx.x * kCgBlock + threadIdx.x;
   const int k = gt & 7;
-  const int groups = kCgCtas * kCgBlock / 8;
+  const int groups = gridDim.x * kCgBlock / 8;
   double acc = 0.0;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
     const int c = c0 + (gt >> 3);
@@ -1112,28 +1131,27 @@ __global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg
     }
     group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, zk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
   }
-  const double rz = cluster_sum(acc, red, &slot[0]);
+  const double rz = grid_sum(acc, red, a.partial, a.gb, base + gridDim.x);
   if (gt == 0) {
     a.st->rz = rz; a.st->rz0 = rz; a.st->pq = 0.0; a.st->k = 0;
     a.st->breakdown = 0;
     a.st->done = !(rz > 0.0);
+    a.gb->base = base + gridDim.x;
   }
-  cg::this_cluster().sync();  // keep shared memory alive until every CTA has read the slots
 }
 
 // One CG step after q = S p is available (q = qpart + lam Dc p).  When the iteration stops, the
 // gather table of the SOLUTION x is written instead of that of the next direction, ready for the
 // back-substitution pass.
-__global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
-  namespace cg = cooperative_groups;
+__global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
   __shared__ double red[kCgBlock / 32];
-  __shared__ double slot[2];
-  if (a.st->done) return;   // uniform over the whole cluster
+  if (a.st->done) return;   // uniform over the whole grid (written by the previous launch)
   const double rz = a.st->rz, rz0 = a.st->rz0;
   const int k_new = a.st->k + 1;
+  const unsigned long long base = a.gb->base;
   const int gt = blockIdx.x * kCgBlock + threadIdx.x;
   const int k = gt & 7;
-  const int groups = kCgCtas * kCgBlock / 8;
+  const int groups = gridDim.x * kCgBlock / 8;
   double acc = 0.0;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
     const int c = c0 + (gt >> 3);
@@ -1145,7 +1163,7 @@ __global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg
       acc += pp * q;
     }
   }
-  const double pq = cluster_sum(acc, red, &slot[0]);
+  const double pq = grid_sum(acc, red, a.partial, a.gb, base + gridDim.x);
   const bool ok = pq > 0.0;
   const double alpha = ok ? rz / pq : 0.0;
   acc = 0.0;
@@ -1165,7 +1183,7 @@ __global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg
       acc += rk * zk;
     }
   }
-  const double rz_new = cluster_sum(acc, red, &slot[1]);
+  const double rz_new = grid_sum(acc, red, a.partial + kCgMaxCtas, a.gb, base + 2ULL * gridDim.x);
   const bool stop = !ok || rz_new <= a.tol2 * rz0 || k_new >= a.max_iter;
   const double beta = stop ? 0.0 : rz_new / rz;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
@@ -1179,13 +1197,14 @@ __global__ void __cluster_dims__(kCgCtas, 1, 1) __launch_bounds__(kCgBlock) k_cg
     }
     group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, vk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
   }
-  cg::this_cluster().sync();  // every CTA has read st and the slots
+  // every CTA has read st and gb->base before the second barrier, so thread 0 may publish the new state
   if (gt == 0) {
     a.st->pq = pq;
     a.st->k = k_new;
     a.st->rz = rz_new;
     if (!ok) a.st->breakdown = 1;
     if (stop) a.st->done = 1;
+    a.gb->base = base + 2ULL * gridDim.x;
   }
 }
 
