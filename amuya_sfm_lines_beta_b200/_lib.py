@@ -22,7 +22,7 @@ EXPORTS = [
     "lba_last_error", "lba_version", "lba_default_options", "lba_create", "lba_destroy", "lba_set_stream",
     "lba_synchronize", "lba_set_problem", "lba_point_wise_indices", "lba_project", "lba_residuals",
     "lba_residuals_jacobian", "lba_normal_equations", "lba_schur_solve", "lba_lm_solve",
-    "lba_comm_unique_id", "lba_comm_init", "lba_comm_destroy", "lba_launch_count", "lba_set_profiling",
+    "lba_comm_unique_id", "lba_comm_init", "lba_comm_destroy", "lba_comm_peer_local", "lba_comm_peer_attach", "lba_launch_count", "lba_set_profiling",
     "lba_get_profile", "lba_kernel_class_name", "lba_measure_fp64_peak", "lba_measure_copy_bandwidth",
 ]
 
@@ -90,6 +90,8 @@ def load():
     lib.lba_comm_unique_id.argtypes = [vp]
     lib.lba_comm_init.argtypes = [vp, vp, i32, i32]
     lib.lba_comm_destroy.argtypes = [vp]
+    lib.lba_comm_peer_local.argtypes = [vp, vp, i64]
+    lib.lba_comm_peer_attach.argtypes = [vp, vp, i32, i32]
     lib.lba_launch_count.restype = i64
     lib.lba_launch_count.argtypes = [vp]
     lib.lba_set_profiling.argtypes = [vp, i32]

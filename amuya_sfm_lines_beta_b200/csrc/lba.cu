@@ -144,6 +144,15 @@ struct lba_ctx {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // NVLink peer-memory all-reduce (optional; falls back to NCCL when not attached)
+  bool peer_ready = false;
+  void* peer_local = nullptr;          // own symmetric buffer (cudaMalloc)
+  size_t peer_bytes = 0;
+  void* peer_mapped[kMaxPeers] = {nullptr};
+  PeerArgs peer_args;
+  size_t peer_cams = 0;                     // camera capacity of the per-camera regions
+  size_t rgn_off[kRgnCount] = {0}, rgn_cap[kRgnCount] = {0};   // in doubles (cap per slot)
+  unsigned long long rgn_seq[kRgnCount] = {0};
 
   // instrumentation
   int64_t launches = 0;
@@ -236,8 +245,8 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CKR(c->gbits.alloc(1));
   CKR(c->gbits_new.alloc(1));
   CKR(c->clamped.alloc(1));
-  CKR(c->tickets.alloc(4));
-  CK(cudaMemsetAsync(c->tickets.p, 0, 16, c->stream));
+  CKR(c->tickets.alloc(8));
+  CK(cudaMemsetAsync(c->tickets.p, 0, 32, c->stream));
   CK(cudaMemsetAsync(c->scal.p, 0, sizeof(Scalars), c->stream));
   CK(cudaMemsetAsync(c->clamped.p, 0, sizeof(int), c->stream));
   *out = c;
@@ -245,6 +254,15 @@ extern "C" int lba_create(int device, lba_ctx** out) {
 }
 
 extern "C" int lba_comm_destroy(lba_ctx* ctx) {
+  if (ctx && ctx->peer_local) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (ctx->peer_mapped[r] && ctx->peer_mapped[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
+    cudaFree(ctx->peer_local);
+    ctx->peer_local = nullptr;
+    ctx->peer_ready = false;
+    for (int r = 0; r < kMaxPeers; ++r) ctx->peer_mapped[r] = nullptr;
+  }
   if (ctx && ctx->comm) {
     cudaStreamSynchronize(ctx->stream);
     g_nccl.CommDestroy(ctx->comm);
@@ -331,16 +349,96 @@ extern "C" int lba_comm_init(lba_ctx* ctx, const void* id128, int32_t rank, int3
   return LBA_OK;
 }
 
-static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
-  if (c->world <= 1) return LBA_OK;
+static int nccl_allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
   c->pre(LBA_K_COMM);
   ncclResult_t r = g_nccl.AllReduce(buf, buf, n, dt, op, c->comm, c->stream);
   c->post(LBA_K_COMM);
-  --c->launches;  // a collective is not one of our kernels
+  --c->launches;  // a library collective is not one of our kernels
   if (r != ncclSuccess) return fail(LBA_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return LBA_OK;
 }
+
+static inline bool peer_fits(const lba_ctx* c, int region, size_t n) {
+  return c->world > 1 && c->peer_ready && n <= c->rgn_cap[region];
+}
+static inline size_t peer_slot_off(const lba_ctx* c, int region, unsigned long long seq) {
+  return c->rgn_off[region] + (size_t)(seq & 1ULL) * c->rgn_cap[region];
+}
+
+// Where a producer kernel should write the partial sums that will be all-reduced into `local`:
+// straight into the symmetric slot of the NEXT call on that region when the peer path is active.
+static double* reduce_target(lba_ctx* c, int region, double* local, size_t n) {
+  if (!peer_fits(c, region, n)) return local;
+  return reinterpret_cast<double*>((unsigned char*)c->peer_local + kPeerDataOff) + peer_slot_off(c, region, c->rgn_seq[region] + 1);
+}
+
+// Finish the all-reduce started by reduce_target: result in `local` on every rank.
+static int reduce_finish(lba_ctx* c, int region, double* local, size_t n) {
+  if (c->world <= 1 || n == 0) return LBA_OK;
+  if (!peer_fits(c, region, n)) return nccl_allreduce(c, local, n, ncclDouble, ncclSum);
+  const unsigned long long seq = ++c->rgn_seq[region];
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(32, (n / 2 + 511) / 512));
+  c->pre(LBA_K_COMM);
+  k_peer_reduce<false><<<grid, 512, 0, c->stream>>>(c->peer_args, region, peer_slot_off(c, region, seq), n, seq,
+                                                    (const double*)nullptr, local);
+  c->post(LBA_K_COMM);
+  return LBA_OK;
+}
+
+// Small in-place all-reduce of a few scalars that live in ordinary device memory (copy variant).
+static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+  if (c->world <= 1 || n == 0) return LBA_OK;
+  if (!peer_fits(c, kRgnS, n)) return nccl_allreduce(c, buf, n, dt, op);
+  const unsigned long long seq = ++c->rgn_seq[kRgnS];
+  c->pre(LBA_K_COMM);
+  if (op == ncclMax)
+    k_peer_reduce<true><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, (double*)buf);
+  else
+    k_peer_reduce<false><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, (double*)buf);
+  c->post(LBA_K_COMM);
+  return LBA_OK;
+}
 static int allreduce_sum(lba_ctx* c, double* buf, size_t n) { return allreduce(c, buf, n, ncclDouble, ncclSum); }
+
+extern "C" int lba_comm_peer_local(lba_ctx* ctx, void* handle64, int64_t bytes) {
+  if (!ctx || !handle64 || bytes < 4096) return fail(LBA_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (ctx->peer_local) return fail(LBA_ERR_STATE, "peer buffer already allocated");
+  CK(cudaMalloc(&ctx->peer_local, (size_t)bytes));
+  CK(cudaMemset(ctx->peer_local, 0, (size_t)bytes));
+  ctx->peer_bytes = (size_t)bytes;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->peer_local));
+  memcpy(handle64, &h, 64);
+  return LBA_OK;
+}
+
+extern "C" int lba_comm_peer_attach(lba_ctx* ctx, const void* handles, int32_t rank, int32_t world) {
+  if (!ctx || !handles) return fail(LBA_ERR_ARG, "bad argument");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) return fail(LBA_ERR_UNSUPPORTED, "peer all-reduce supports 2..%d ranks", kMaxPeers);
+  if (!ctx->peer_local) return fail(LBA_ERR_STATE, "call lba_comm_peer_local first");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ctx->peer_mapped[r] = ctx->peer_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char*)handles + (size_t)r * 64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_mapped[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LBA_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)); }
+  }
+  memset(&ctx->peer_args, 0, sizeof ctx->peer_args);
+  for (int r = 0; r < world; ++r) ctx->peer_args.peer[r] = (unsigned char*)ctx->peer_mapped[r];
+  ctx->peer_args.rank = rank; ctx->peer_args.world = world;
+  // regions: scalars (16), S*p partial (6 Nc), U|gc (27 Nc), M|b (27 Nc); two slots each
+  const size_t total = (ctx->peer_bytes - kPeerDataOff) / 8;
+  const size_t ncap = (total - 2 * 16) / (2 * (6 + 27 + 27));
+  ctx->peer_cams = ncap;
+  size_t off = 0;
+  const size_t caps[kRgnCount] = {6 * ncap, 27 * ncap, 27 * ncap, 16};
+  for (int g = 0; g < kRgnCount; ++g) { ctx->rgn_off[g] = off; ctx->rgn_cap[g] = caps[g] & ~(size_t)1; off += 2 * ctx->rgn_cap[g]; ctx->rgn_seq[g] = 0; }
+  ctx->peer_ready = true;
+  return LBA_OK;
+}
 
 // ---- problem set-up -------------------------------------------------------------------------------
 static bool is_device_ptr(const void* p) {
@@ -667,12 +765,16 @@ static void accept_candidate(lba_ctx* c, bool have_new_eval) {
 // scaling; camera part of the gradient inf-norm
 static int run_blocks(lba_ctx* c, bool full) {
   if (c->nc > 0) {
+    const size_t n27 = (size_t)c->nc * 27;
+    double* out = reduce_target(c, kRgnU, c->U.p, n27);
     if (full)
       LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-             (const double*)nullptr, c->r.p, c->U.p, gc_of(c));
-    else
-      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, c->U.p, gc_of(c));
-    CKR(allreduce_sum(c, c->U.p, (size_t)c->nc * 27));
+             (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21);
+    else {
+      if (out != c->U.p) CK(cudaMemsetAsync(out, 0, n27 * 8, c->stream));   // k_cam_grad writes the diagonal only
+      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out, out + (size_t)c->nc * 21);
+    }
+    CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     LAUNCH(c, LBA_K_MISC, k_cam_post, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, gc_of(c), c->Dc.p,
            c->pending_first ? 1 : 0, c->gbits.p);
   }
@@ -704,9 +806,11 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
   if (nc > 0) {
+    const size_t n27 = (size_t)nc * 27;
+    double* out = reduce_target(c, kRgnM, c->Mpart.p, n27);
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-           (const double*)c->wk.p, c->wr.p, c->Mpart.p, bpart_of(c));
-    CKR(allreduce_sum(c, c->Mpart.p, (size_t)nc * 27));
+           (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21);
+    CKR(reduce_finish(c, kRgnM, c->Mpart.p, n27));
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, gc_of(c), bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
   }
   CgArgs& ca = sp->ca;
@@ -723,8 +827,11 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
 static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
   for (int q = 0; q < n && sp->issued < sp->ca.max_iter; ++q, ++sp->issued) {
     if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
-    if (c->nc > 0) LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, c->qpart.p, c->cgst.p);
-    CKR(allreduce_sum(c, c->qpart.p, (size_t)c->nc * 6));
+    if (c->nc > 0) {
+      double* out = reduce_target(c, kRgnQ, c->qpart.p, (size_t)c->nc * 6);
+      LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p);
+      CKR(reduce_finish(c, kRgnQ, c->qpart.p, (size_t)c->nc * 6));
+    }
     LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
   }
   CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));

@@ -1315,6 +1315,90 @@ __global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, cons
 }
 
 // ---------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory (replaces ncclAllReduce for the small, latency-bound
+// per-camera vectors).  Every rank owns a "symmetric" buffer mapped into all peers (CUDA IPC):
+//   flags[region][2][kMaxPeers] (sequence numbers) | per region: data[2][cap] doubles (ping-pong)
+// The PRODUCER kernel of a partial sum (k_pcg_cam, k_cam_grad, k_cam_accum) writes straight into the
+// own slot (zero copy).  The reduce kernel of call #seq, slot seq&1: (1) one CTA stores seq into
+// flag[region][slot][my_rank] of EVERY rank (release, system scope) -- the partial was written by the
+// previous kernel on the stream, so it is complete; (2) every CTA waits until the own flags of all
+// ranks reach seq (acquire); (3) the W slots are added in rank order -- the same order on every rank,
+// so all ranks end with identical bits.  A slot is rewritten two calls later, after every peer has
+// signalled the call in between, i.e. has finished reading it.
+// ---------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+enum { kRgnQ = 0, kRgnU, kRgnM, kRgnS, kRgnCount };
+constexpr int kPeerDataOff = 1024;   // flags: kRgnCount*2*kMaxPeers*8 = 512 B
+
+struct PeerArgs {
+  unsigned char* peer[kMaxPeers];   // peer[r] = base of rank r's symmetric buffer as mapped here
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_relaxed_sys2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// slot_off: offset in doubles of (region, slot) inside the data area; n must be even (padded by the host)
+// src != nullptr: single-CTA mode that first copies n doubles from local memory into the own slot.
+template <bool MAX_U64>
+__global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int region, size_t slot_off, size_t n,
+                                                      unsigned long long seq, const double* __restrict__ src,
+                                                      double* __restrict__ dst) {
+  const int slot = (int)(seq & 1ULL);
+  const int t = threadIdx.x;
+  if (src) {
+    double* mine = reinterpret_cast<double*>(pa.peer[pa.rank] + kPeerDataOff) + slot_off;
+    for (size_t i = t; i < n; i += blockDim.x) mine[i] = src[i];
+    __syncthreads();
+  }
+  const int fidx = (region * 2 + slot) * kMaxPeers;
+  if (blockIdx.x == 0 && t < pa.world)
+    st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + fidx + pa.rank, seq);
+  if (t < pa.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + fidx + t;
+    while (ld_acquire_sys(f) < seq) { }
+  }
+  __syncthreads();
+  const size_t gsz = (size_t)gridDim.x * blockDim.x;
+  for (size_t i2 = (size_t)blockIdx.x * blockDim.x + t; 2 * i2 < n; i2 += gsz) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pa.world) v[r] = ld_relaxed_sys2(reinterpret_cast<const double*>(pa.peer[r] + kPeerDataOff) + slot_off + 2 * i2);
+    double2 acc;
+    if (MAX_U64) {
+      unsigned long long m0 = 0ULL, m1 = 0ULL;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < pa.world) {
+          const unsigned long long a0 = (unsigned long long)__double_as_longlong(v[r].x);
+          const unsigned long long a1 = (unsigned long long)__double_as_longlong(v[r].y);
+          m0 = a0 > m0 ? a0 : m0; m1 = a1 > m1 ? a1 : m1;
+        }
+      acc.x = __longlong_as_double((long long)m0); acc.y = __longlong_as_double((long long)m1);
+    } else {
+      acc.x = 0.0; acc.y = 0.0;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < pa.world) { acc.x += v[r].x; acc.y += v[r].y; }
+    }
+    if (2 * i2 + 1 < n) *reinterpret_cast<double2*>(dst + 2 * i2) = acc;
+    else dst[2 * i2] = acc.x;
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // microbenchmarks for the roofline denominators
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {

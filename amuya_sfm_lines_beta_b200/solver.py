@@ -184,8 +184,9 @@ class LineBA:
                         rep.n_res, rep.pcg_iters_total, rep.chol_clamped, rep.cost_init, rep.cost, rep.seconds, trace)
 
     # -- multi-GPU --------------------------------------------------------------------------
-    def init_comm(self, rank=None, world=None, group=None):
-        """Attach an NCCL communicator; the unique id travels over torch.distributed."""
+    def init_comm(self, rank=None, world=None, group=None, peer_bytes=64 << 20):
+        """Attach an NCCL communicator (the unique id travels over torch.distributed) and, unless
+        ``peer_bytes`` is 0, the NVLink peer-memory all-reduce buffers (CUDA IPC handles travel the same way)."""
         import torch
         import torch.distributed as dist
         rank = dist.get_rank(group) if rank is None else rank
@@ -203,6 +204,20 @@ class LineBA:
         buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
         check(self._lib.lba_comm_init(self._h, buf2, int(rank), int(world)))
         self.rank, self.world = int(rank), int(world)
+        import os as _os
+        if peer_bytes and world <= 8 and not _os.environ.get("LBA_NO_PEER"):
+            # NVLink peer-memory all-reduce for the small per-camera vectors: exchange CUDA IPC handles
+            h = (C.c_ubyte * 64)()
+            check(self._lib.lba_comm_peer_local(self._h, h, int(peer_bytes)))
+            mine = torch.tensor(list(bytes(h)), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                mine = mine.cuda(self.device)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)
+            raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+            hb = (C.c_ubyte * (64 * world)).from_buffer_copy(raw)
+            check(self._lib.lba_comm_peer_attach(self._h, hb, int(rank), int(world)))
+            self.peer_allreduce = True
         return self
 
     # -- instrumentation ------------------------------------------------------------------

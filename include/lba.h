@@ -167,6 +167,12 @@ int lba_lm_solve(lba_ctx* ctx, double* camera_params, double* points_3d, const l
 int lba_comm_unique_id(void* id128);
 int lba_comm_init(lba_ctx* ctx, const void* id128, int32_t rank, int32_t world_size);
 int lba_comm_destroy(lba_ctx* ctx);
+/* Optional: one-shot all-reduce over NVLink peer memory instead of ncclAllReduce for the small per-camera
+ * vectors.  Every rank allocates a symmetric buffer and exports a 64-byte CUDA IPC handle
+ * (lba_comm_peer_local); the handles of all ranks, concatenated in rank order, are then attached
+ * (lba_comm_peer_attach).  Payloads larger than half the buffer still go through NCCL. */
+int lba_comm_peer_local(lba_ctx* ctx, void* handle64, int64_t bytes);
+int lba_comm_peer_attach(lba_ctx* ctx, const void* handles, int32_t rank, int32_t world_size);
 
 /* Instrumentation. */
 int64_t lba_launch_count(lba_ctx* ctx);             /* kernels launched by this context so far */
