@@ -41,6 +41,23 @@ BYTES_PER_OBS = {
 }
 
 
+NCU_KERNEL_OF_CLASS = {"jacobian": "k_eval<1, 2, 1>", "residual": "k_eval<0, 2, 1>", "pcg_line": "k_line_pass<0>",
+                       "pcg_cam": "k_pcg_cam"}
+
+
+def read_traffic(kernel_class):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel from the committed
+    `ncu --set full` summary (profiles/kernels_r*.json, written by profiles/summarize.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "kernels_r*.json")))
+    if not files:
+        return None
+    d = json.load(open(files[-1])).get(NCU_KERNEL_OF_CLASS.get(kernel_class, ""), None)
+    if not d or d.get("dram_read_MB") is None:
+        return None
+    return (d["dram_read_MB"] + d["dram_write_MB"]) * 1e6
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -250,7 +267,8 @@ def main():
                              "frac": round(bpo * m_local / (avg_ms * 1e-3) / 1e9 / peak, 4), "launches": prof[k]["launches"]}
     if dom:
         roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": per_kernel[dom]["frac"], "traffic": read_traffic(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_OBS[dom] * m_local,
                 "algorithmic_bytes_per_obs": BYTES_PER_OBS[dom], "per_kernel": per_kernel, "time_shares": shares}
 
     fp64_tf = ba.measure_fp64_peak()
