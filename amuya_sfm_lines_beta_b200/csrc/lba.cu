@@ -109,7 +109,9 @@ struct lba_ctx {
   bool have_problem = false, have_eval = false, have_blocks = false, have_scaling = false;
   DBuf<int> cam_perm, cam_ptr, slot_src;
   DBuf<TileIdx> tidx;
-  DBuf<int> sort_tmp;            // keys/values in and out of the device radix sort (4 x Mp)
+  DBuf<int> sort_tmp, cam_sort_tmp, line_tmp;   // device radix-sort keys/values; per-line scratch
+  DBuf<long long> idx_stage;     // the caller's int64 index arrays on the device
+  DBuf<TileMeta> meta_stage;
   DBuf<unsigned char> cub_tmp;
   DBuf<double> cst, dense_tmp, h2d_stage;   // h2d_stage: grow-only staging for host-side n/p0/p1
   // persistent-grid sizes and dynamic shared memory of the pipelined line-order kernels
@@ -472,92 +474,99 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     tp0 = t;
   };
 
-  // indices to the host (they drive the one-time layout construction)
-  std::vector<int64_t> hc, hl;
-  const int64_t* pc = cam_idx;
-  const int64_t* pl = line_idx;
-  if (m > 0 && is_device_ptr(cam_idx)) { hc.resize(m); CK(cudaMemcpy(hc.data(), cam_idx, (size_t)m * 8, cudaMemcpyDeviceToHost)); pc = hc.data(); }
-  if (m > 0 && is_device_ptr(line_idx)) { hl.resize(m); CK(cudaMemcpy(hl.data(), line_idx, (size_t)m * 8, cudaMemcpyDeviceToHost)); pl = hl.data(); }
-
-  bool sorted = true;
+  // (1) the caller's index arrays go to the device; range checks, sortedness and the per-line
+  //     observation histogram are computed there
+  CKR(ctx->idx_stage.alloc((size_t)2 * m + 2));
+  long long* d_cam = ctx->idx_stage.p;
+  long long* d_line = ctx->idx_stage.p + m;
+  const long long* cam_dev = d_cam;
+  const long long* line_dev = d_line;
+  if (m > 0) {
+    if (is_device_ptr(cam_idx)) cam_dev = (const long long*)cam_idx;
+    else CK(cudaMemcpyAsync(d_cam, cam_idx, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (is_device_ptr(line_idx)) line_dev = (const long long*)line_idx;
+    else CK(cudaMemcpyAsync(d_line, line_idx, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CKR(ctx->line_tmp.alloc((size_t)3 * nl + 8));   // line_cnt | line_ptr | line_slot
+  int* d_line_cnt = ctx->line_tmp.p; int* d_line_ptr = d_line_cnt + nl + 1; int* d_line_slot = d_line_ptr + nl + 1;
+  int* d_flags = d_line_slot + nl + 1;
+  CK(cudaMemsetAsync(ctx->line_tmp.p, 0, ((size_t)3 * nl + 8) * 4, ctx->stream));
+  CKR(ctx->sort_tmp.alloc((size_t)4 * std::max(m, 1)));
+  if (m > 0)
+    LAUNCH(ctx, LBA_K_MISC, k_index_scan, cdiv(m, 256), 256, m, nc, nl, cam_dev, line_dev, d_line_cnt, d_flags, ctx->sort_tmp.p);
   std::vector<int> line_cnt((size_t)nl + 1, 0);
-  for (int i = 0; i < m; ++i) {
-    const int64_t c = pc[i], l = pl[i];
-    if (c < 0 || c >= nc) return fail(LBA_ERR_ARG, "camera_indices[%d]=%lld out of range [0,%d)", i, (long long)c, nc);
-    if (l < 0 || l >= nl) return fail(LBA_ERR_ARG, "lines_indices[%d]=%lld out of range [0,%d)", i, (long long)l, nl);
-    if (i > 0 && l < pl[i - 1]) sorted = false;
-    ++line_cnt[(size_t)l + 1];
-  }
-  std::vector<int> line_ptr((size_t)nl + 1, 0);
-  int kmax = 0;
-  for (int l = 0; l < nl; ++l) {
-    kmax = std::max(kmax, line_cnt[(size_t)l + 1]);
-    line_ptr[(size_t)l + 1] = line_ptr[l] + line_cnt[(size_t)l + 1];
-  }
-  if (kmax > LBA_MAX_OBS_PER_LINE)
-    return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
+  int h_flags[3] = {0, 0, 0};
+  if (nl > 0) CK(cudaMemcpyAsync(line_cnt.data(), d_line_cnt, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_flags, d_flags, 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (h_flags[0]) return fail(LBA_ERR_ARG, "camera_indices[%d] out of range [0,%d)", h_flags[0] - 1, nc);
+  if (h_flags[1]) return fail(LBA_ERR_ARG, "lines_indices[%d] out of range [0,%d)", h_flags[1] - 1, nl);
+  const bool sorted = h_flags[2] == 0;
+  lap("index H2D + device scan");
 
-  lap("validate + line histogram");
-  // line order: stable counting sort by line (identity when the input is already sorted)
-  std::vector<int> order(m);   // line-sorted position -> caller's observation index
-  if (sorted) {
-    for (int i = 0; i < m; ++i) order[i] = i;
-  } else {
-    std::vector<int> cur(line_ptr.begin(), line_ptr.end() - 1);
-    for (int i = 0; i < m; ++i) order[cur[pl[i]]++] = i;
-  }
-  // tiles: whole lines, at most kTile observations and kMaxLinesPerTile lines each
+  // (2) per-LINE work on the host: prefix sums and the greedy packing of whole lines into tiles
+  std::vector<int> line_ptr((size_t)nl + 1, 0), line_slot((size_t)nl + 1, 0);
   std::vector<TileMeta> meta;
+  int kmax = 0;
   {
     TileMeta cur;
     memset(&cur, 0, sizeof cur);
     bool open = false;
     for (int l = 0; l < nl; ++l) {
-      const int k = line_cnt[(size_t)l + 1];
+      const int k = line_cnt[l];
+      kmax = std::max(kmax, k);
+      line_ptr[(size_t)l + 1] = line_ptr[l] + k;
       if (open && (cur.nobs + k > kTile || cur.nl >= kMaxLinesPerTile)) { meta.push_back(cur); open = false; }
       if (!open) { memset(&cur, 0, sizeof cur); cur.l0 = l; open = true; }
+      line_slot[l] = (int)meta.size() * kTile + cur.nobs;
       cur.nobs += k;
-      cur.lend[cur.nl++] = (unsigned short)cur.nobs;
+      cur.lend[cur.nl++] = (unsigned short)std::min(cur.nobs, 65535);
     }
     if (open) meta.push_back(cur);
   }
-  lap("order + tiles");
+  if (kmax > LBA_MAX_OBS_PER_LINE)
+    return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
   const int ntiles = (int)meta.size();
   const long long Mp64 = (long long)ntiles * kTile;
   if (Mp64 > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "padded observation count out of range");
   const int Mp = (int)Mp64;
   int lmax = 8;
   for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 7) & ~7);
-  std::vector<int> slot_src((size_t)Mp, -1);
-  std::vector<TileIdx> tidx((size_t)ntiles);
-  for (int g = 0; g < ntiles; ++g) {
-    const TileMeta& t = meta[g];
-    TileIdx& ti = tidx[g];
-    ti.meta = t;
-    memset(ti.ll, 0, sizeof ti.ll);
-    memset(ti.pos, 0, sizeof ti.pos);
-    for (int sl = 0; sl < kTile; ++sl) ti.cam[sl] = -1;
-    int sorted_pos = line_ptr[t.l0];
-    for (int ll = 0; ll < t.nl; ++ll) {
-      const int s0 = ll ? t.lend[ll - 1] : 0, s1 = t.lend[ll];
-      for (int sl = s0; sl < s1; ++sl, ++sorted_pos) {
-        const size_t slot = (size_t)g * kTile + sl;
-        const int src = order[sorted_pos];
-        ti.cam[sl] = (int)pc[src];
-        ti.ll[sl] = (unsigned char)ll;
-        slot_src[slot] = src;
-      }
-    }
-  }
-  lap("slot arrays");
+  lap("host tiling (per line)");
+
+  // (3) back on the device: slot assignment of every observation
   ctx->m = m; ctx->nc = nc; ctx->nl = nl; ctx->ntiles = ntiles; ctx->Mp = Mp; ctx->lmax = lmax;
-  CKR(upload(ctx, ctx->tidx, tidx));
+  CKR(ctx->tidx.alloc((size_t)ntiles)); CKR(ctx->slot_src.alloc((size_t)Mp)); CKR(ctx->meta_stage.alloc((size_t)ntiles));
+  if (ntiles > 0) {
+    CK(cudaMemcpyAsync(ctx->meta_stage.p, meta.data(), (size_t)ntiles * sizeof(TileMeta), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_line_ptr, line_ptr.data(), ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_line_slot, line_slot.data(), ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, LBA_K_MISC, k_init_tidx, ntiles, kTile, ntiles, ctx->meta_stage.p, ctx->tidx.p);
+    CK(cudaMemsetAsync(ctx->slot_src.p, 0xFF, (size_t)Mp * 4, ctx->stream));   // -1 = padding
+  }
+  if (m > 0) {
+    const int* d_order = nullptr;
+    if (!sorted) {
+      // stable sort of the observations by line (the reference emits them sorted: seq_utils.py:190)
+      int* keys_in = ctx->sort_tmp.p; int* vals_in = keys_in + m; int* keys_out = vals_in + m; int* vals_out = keys_out + m;
+      LAUNCH(ctx, LBA_K_MISC, k_iota, cdiv(m, 256), 256, m, vals_in);
+      int end_bit = 1;
+      while ((1LL << end_bit) <= nl) ++end_bit;
+      size_t tmp_bytes = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, m, 0, end_bit, ctx->stream));
+      CKR(ctx->cub_tmp.alloc(tmp_bytes));
+      CK(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_bytes, keys_in, keys_out, vals_in, vals_out, m, 0, end_bit, ctx->stream));
+      d_order = vals_out;
+    }
+    LAUNCH(ctx, LBA_K_MISC, k_fill_slots, cdiv(m, 256), 256, m, d_order, cam_dev, line_dev, d_line_ptr, d_line_slot,
+           ctx->slot_src.p, ctx->tidx.p);
+  }
   // camera order on the device: stable LSD radix sort of (camera, slot) keeps the slot (line) order
   // inside every camera, like the stable counting sort it replaces
   CKR(ctx->cam_perm.alloc((size_t)Mp)); CKR(ctx->cam_ptr.alloc((size_t)nc + 1));
   if (Mp > 0) {
-    CKR(ctx->sort_tmp.alloc((size_t)3 * Mp));
-    int* keys_in = ctx->sort_tmp.p; int* vals_in = keys_in + Mp; int* keys_out = vals_in + Mp;
+    CKR(ctx->cam_sort_tmp.alloc((size_t)3 * Mp));
+    int* keys_in = ctx->cam_sort_tmp.p; int* vals_in = keys_in + Mp; int* keys_out = vals_in + Mp;
     LAUNCH(ctx, LBA_K_MISC, k_cam_keys, cdiv(Mp, 256), 256, Mp, nc, ctx->tidx.p, keys_in, vals_in);
     int end_bit = 1;
     while ((1LL << end_bit) <= nc) ++end_bit;
@@ -569,9 +578,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   } else {
     CK(cudaMemsetAsync(ctx->cam_ptr.p, 0, ((size_t)nc + 1) * 4, ctx->stream));
   }
-  CKR(upload(ctx, ctx->slot_src, slot_src));
-
-  lap("index uploads (async)");
+  lap("device slot fill + camera sort (async)");
   // observation constants: AoS (m,3) -> SoA over slots, m_e = n x p_e
   CKR(ctx->cst.alloc((size_t)9 * Mp));
   if (m > 0) {
@@ -589,7 +596,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       off += (size_t)3 * m;
     }
     LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(Mp, 256), 256, Mp, ctx->slot_src.p, dev[0], dev[1], dev[2], ctx->cst.p);
-    CK(cudaStreamSynchronize(ctx->stream));  // the host index vectors go out of scope
+    CK(cudaStreamSynchronize(ctx->stream));  // the host vectors (tile table, line offsets) go out of scope
   } else {
     CK(cudaStreamSynchronize(ctx->stream));
   }

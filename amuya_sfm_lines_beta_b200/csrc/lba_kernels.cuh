@@ -223,6 +223,48 @@ __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* _
   }
 }
 
+// ---- problem set-up on the device: only per-LINE work (tiling) stays on the host -------------------
+// range checks, sortedness and the per-line observation count of the caller's index arrays
+__global__ void k_index_scan(int m, int nc, int nl, const long long* __restrict__ cam, const long long* __restrict__ line,
+                             int* __restrict__ line_cnt, int* __restrict__ flags /* [0] bad cam, [1] bad line, [2] unsorted */,
+                             int* __restrict__ keys /* optional: line as int, for the stable sort of unsorted input */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long c = cam[i], l = line[i];
+  if (c < 0 || c >= nc) { atomicMax(&flags[0], i + 1); return; }
+  if (l < 0 || l >= nl) { atomicMax(&flags[1], i + 1); return; }
+  if (i > 0 && l < line[i - 1]) flags[2] = 1;
+  atomicAdd(&line_cnt[l], 1);
+  if (keys) keys[i] = (int)l;
+}
+__global__ void k_iota(int n, int* __restrict__ v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+// place every observation into its slot: line-sorted position i (order[i] = caller index, or identity)
+__global__ void k_fill_slots(int m, const int* __restrict__ order, const long long* __restrict__ cam,
+                             const long long* __restrict__ line, const int* __restrict__ line_ptr,
+                             const int* __restrict__ line_slot /* first slot of each line */, int* __restrict__ slot_src,
+                             TileIdx* __restrict__ tidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int src = order ? order[i] : i;
+  const int l = (int)line[src];
+  const int slot = line_slot[l] + (i - line_ptr[l]);
+  slot_src[slot] = src;
+  TileIdx& ti = tidx[slot / kTile];
+  ti.cam[slot % kTile] = (int)cam[src];
+  ti.ll[slot % kTile] = (unsigned char)(l - ti.meta.l0);
+}
+// TileIdx records start as {meta from the host, ll = 0, cam = -1, pos = 0}
+__global__ void k_init_tidx(int ntiles, const TileMeta* __restrict__ meta, TileIdx* __restrict__ tidx) {
+  const int g = blockIdx.x, t = threadIdx.x;
+  if (g >= ntiles) return;
+  TileIdx& ti = tidx[g];
+  if (t == 0) ti.meta = meta[g];
+  ti.ll[t] = 0; ti.cam[t] = -1; ti.pos[t] = 0;
+}
+
 // ---- camera order on the device: stable radix sort of (camera, slot), then these two kernels ----
 __global__ void k_cam_keys(int Mp, int nc, const TileIdx* __restrict__ tidx, int* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
