@@ -398,6 +398,37 @@ def test_device_resident_inputs(LineBA):
     ba.close(); ba2.close()
 
 
+def test_many_cameras_take_the_global_gather_variant(LineBA, orc):
+    """More cameras than the shared-memory camera table holds (~1.3k): the evaluation kernel falls back to
+    the global-memory gather variant; results must not change."""
+    s = synth(3000, 6000, 6, seed=4)
+    ba = make_ctx(LineBA, s)
+    r, jcam, jline = ba.residuals_jacobian(s.camera_params, s.points_3d)
+    r_o, jc_o, jl_o = _oracle_jac(orc, s)
+    assert np.all(np.abs(r - r_o) <= residual_tol(r_o))
+    scale = max(np.abs(jc_o).max(), np.abs(jl_o).max())
+    assert np.max(np.abs(jcam - _interleave(jc_o))) < 1e-12 * scale
+    assert np.max(np.abs(jline - jl_o)) < 1e-12 * scale
+    kw = dict(max_iter=5, ftol=0.0, xtol=0.0, gtol=0.0)
+    res = ba.lm_solve(s.camera_params, s.points_3d, **kw)
+    rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(**kw))[3]
+    cost_d = np.array([t["cost_new"] for t in res.trace]); cost_o = np.array([t["cost_new"] for t in rep.trace])
+    assert np.all(np.abs(cost_d - cost_o) <= RTOL_TRAJ * cost_o)
+    ba.close()
+
+
+def test_non_speculative_path_matches(LineBA):
+    """reserved bit 0 disables the speculative trial Jacobian: same trajectory either way."""
+    s = synth(12, 200, 5, seed=1)
+    ba = make_ctx(LineBA, s)
+    a = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0)
+    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0, reserved=1)
+    assert [t["accepted"] for t in a.trace] == [t["accepted"] for t in b.trace]
+    assert np.allclose([t["cost_new"] for t in a.trace], [t["cost_new"] for t in b.trace], rtol=1e-12)
+    assert abs(a.cost - b.cost) <= 1e-12 * a.cost
+    ba.close()
+
+
 # ---------------------------------------------------------------- full size (config 4) properties
 @pytest.mark.parametrize("variant", ["A"])
 def test_config4_full_size_properties(LineBA, orc, variant):
