@@ -33,8 +33,12 @@ class LbaOptions(C.Structure):
         ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double),
         ("lambda0", C.c_double), ("lambda_min", C.c_double), ("lambda_max", C.c_double),
         ("pcg_tol", C.c_double), ("min_ratio", C.c_double),
-        ("verbose", C.c_int32), ("reserved", C.c_int32),
+        ("verbose", C.c_int32), ("flags", C.c_int32), ("loss", C.c_int32), ("pad", C.c_int32),
+        ("f_scale", C.c_double),
     ]
+
+
+LOSSES = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}  # LBA_LOSS_* in include/lba.h
 
 
 class LbaReport(C.Structure):

@@ -126,12 +126,13 @@ def run_bundle_adjustment(input_bundle_adjustment, loss_f, *, device=0, verbose=
 
     The reference's scipy ``least_squares`` call (:319) is replaced by the GPU
     Levenberg-Marquardt / Schur / PCG solver; keyword-only ``options`` are forwarded to
-    ``LineBA.lm_solve`` (``max_iter``, ``ftol``, ``xtol``, ``gtol``, ``pcg_tol`` ...).
+    ``LineBA.lm_solve`` (``max_iter``, ``ftol``, ``xtol``, ``gtol``, ``pcg_tol``, ``f_scale`` ...).
+    ``loss_f`` takes scipy's names ('linear', 'soft_l1', 'huber', 'cauchy', 'arctan') with scipy's
+    semantics (rho applied to the squared residual, rows rescaled as in
+    ``scale_for_robust_loss_function``).
     """
     if loss_f not in _KNOWN_LOSSES:
         raise ValueError("`loss` must be one of {0} or a callable.".format(_KNOWN_LOSSES))  # scipy's message
-    if loss_f != "linear":
-        raise NotImplementedError("robust losses are not implemented; every reference driver passes 'linear'")
     print("--------------------RUNING BUNDLE ADJUSTMENT ---------------------------")
     camera_params = np.asarray(input_bundle_adjustment['camera_params'], dtype=np.float64)
     lines_3d = input_bundle_adjustment['Lines_3d']
@@ -157,7 +158,7 @@ def run_bundle_adjustment(input_bundle_adjustment, loss_f, *, device=0, verbose=
     ba = _context(device)
     ba.set_problem(n_cameras, n_lines, camera_indices.astype(np.int64), line_indices.astype(np.int64), nn, p0, p1)
     t0 = time.time()
-    res = ba.lm_solve(camera_params, np.asarray(points_3d, dtype=np.float64), verbose=verbose, **options)
+    res = ba.lm_solve(camera_params, np.asarray(points_3d, dtype=np.float64), verbose=verbose, loss=loss_f, **options)
     t1 = time.time()
     if verbose:
         print(res.message)

@@ -124,6 +124,8 @@ struct lba_ctx {
   DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
   DBuf<unsigned int> tickets;
   bool pending_first = true;
+  int loss = 0;                // robust loss of the running lba_lm_solve (0 = linear)
+  double f_scale = 1.0;
   int line_scaling_mode = 2;   // consumed by the next k_line_factor: 0 keep, 1 running max, 2 first
   DBuf<CamRec> recs, recs_new;
   DBuf<double> r, r_new, jl, jl_new, jc, jc_new, w, wk, wr;
@@ -216,7 +218,10 @@ extern "C" void lba_default_options(lba_options* o) {
   o->pcg_tol = 1e-2;
   o->min_ratio = 1e-4;
   o->verbose = 0;
-  o->reserved = 0;
+  o->flags = 0;
+  o->loss = LBA_LOSS_LINEAR;
+  o->pad = 0;
+  o->f_scale = 1.0;
 }
 
 extern "C" int lba_create(int device, lba_ctx** out) {
@@ -680,6 +685,7 @@ static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, dou
   a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p;
   a.cost_partial = c->cost_partial.p;
   a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost; a.gbits = c->gbits.p;
+  a.loss = c->loss; a.f_scale = c->f_scale;
   return a;
 }
 
@@ -1006,7 +1012,8 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   lba_options o;
   if (opts_in) o = *opts_in; else lba_default_options(&o);
-  if (o.max_iter < 0 || o.pcg_max_iter < 1 || !(o.lambda0 > 0.0)) return fail(LBA_ERR_ARG, "bad options");
+  if (o.max_iter < 0 || o.pcg_max_iter < 1 || !(o.lambda0 > 0.0) || o.loss < 0 || o.loss > LBA_LOSS_ARCTAN || !(o.f_scale > 0.0))
+    return fail(LBA_ERR_ARG, "bad options");
   const auto t0 = std::chrono::steady_clock::now();
   lba_report local;
   if (!rep) rep = &local;
@@ -1014,6 +1021,8 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   lba_ctx* c = ctx;
   CKR(load_state(c, cams_api, pts_api));
   c->have_scaling = false;
+  c->loss = o.loss; c->f_scale = o.f_scale;
+  struct LossGuard { lba_ctx* c; ~LossGuard() { c->loss = 0; c->f_scale = 1.0; } } loss_guard{c};
   CK(cudaMemsetAsync(c->clamped.p, 0, 4, c->stream));
   CKR(run_jacobian(c, false));
   rep->n_jac = 1;
@@ -1026,7 +1035,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   double g_norm = gnorm_host(c);
   double lam = o.lambda0, nu = 2.0;
   int status = 0, it = 0, chunk_hint = 8;
-  const bool speculative = !(o.reserved & 1);
+  const bool speculative = !(o.flags & 1);
   if (o.verbose >= 2)
     printf("   Iteration     Total nfev        Cost      Cost reduction    Step norm     Optimality   \n");
   // One host synchronisation per LM iteration: the whole iteration (elimination, a predicted number
@@ -1106,7 +1115,14 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   rep->cost = cost;
   rep->chol_clamped = *c->h_clamped;
   CKR(store_state(c, cams_api, pts_api));
-  CKR(export_residuals(c, c->r.p, residuals));
+  if (c->loss != 0 && residuals) {
+    // with a robust loss the resident residuals are the rescaled ones; the caller gets fun itself (res.fun)
+    c->loss = 0;
+    CKR(run_residual(c, c->recs.p, c->pts.p, c->r_new.p));
+    CKR(export_residuals(c, c->r_new.p, residuals));
+  } else {
+    CKR(export_residuals(c, c->r.p, residuals));
+  }
   CK(cudaStreamSynchronize(c->stream));
   rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return c->launch_err ? LBA_ERR_CUDA : LBA_OK;

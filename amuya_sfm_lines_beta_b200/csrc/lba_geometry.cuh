@@ -94,6 +94,24 @@ __device__ __forceinline__ double endpoint_term(const double R[9], const double 
   return e;
 }
 
+// scipy.optimize.least_squares robust losses (scipy/optimize/_lsq/least_squares.py: soft_l1, huber,
+// cauchy, arctan): rho(z), rho'(z), rho''(z) for z = (r/f_scale)^2.  loss: 1 soft_l1, 2 huber, 3 cauchy, 4 arctan.
+__host__ __device__ inline void robust_rho(int loss, double z, double& r0, double& r1, double& r2) {
+  if (loss == 1) {
+    const double t = 1.0 + z, st = sqrt(t);
+    r0 = 2.0 * (st - 1.0); r1 = 1.0 / st; r2 = -0.5 / (t * st);
+  } else if (loss == 2) {
+    if (z <= 1.0) { r0 = z; r1 = 1.0; r2 = 0.0; }
+    else { const double sz = sqrt(z); r0 = 2.0 * sz - 1.0; r1 = 1.0 / sz; r2 = -0.5 / (z * sz); }
+  } else if (loss == 3) {
+    const double t = 1.0 + z;
+    r0 = log1p(z); r1 = 1.0 / t; r2 = -1.0 / (t * t);
+  } else {
+    const double t = 1.0 + z * z;
+    r0 = atan(z); r1 = 1.0 / t; r2 = -2.0 * z / (t * t);
+  }
+}
+
 // Packed symmetric 6x6: 21 doubles, upper triangle row-major: (0,0)(0,1)..(0,5)(1,1)..(5,5).
 __host__ __device__ constexpr int sym_idx(int a, int b) {
   return a <= b ? (a * (13 - a)) / 2 + (b - a) : (b * (13 - b)) / 2 + (a - b);

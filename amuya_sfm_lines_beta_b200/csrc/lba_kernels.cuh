@@ -319,6 +319,8 @@ struct EvalArgs {
   unsigned int* ticket;    // last-CTA reduction ticket
   double* cost_out;        // 0.5 * sum r^2
   unsigned long long* gbits;  // inf-norm of the gradient, as ordered bits
+  int loss;                // 0 linear, else scipy robust loss (cost 0.5 f_scale^2 sum rho((r/f_scale)^2))
+  double f_scale;
 };
 
 __constant__ int c_sym_a[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     const int cam = s_cam[t];
     const bool active = cam >= 0;
     const size_t i = (size_t)tile * kTile + t;
-    double r = 0.0;
+    double r = 0.0, rho_cost = 0.0;
     double jl[6] = {0, 0, 0, 0, 0, 0};
     if (active) {
       double n[3], m0[3], m1[3];
@@ -443,6 +445,26 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       const double e0 = endpoint_term<WITH_JAC>(R, c, X0, n, m0, jl, tq);
       const double e1 = endpoint_term<WITH_JAC>(R, c, X1, n, m1, jl + 3, tq);
       r = e0 + e1;
+      if (a.loss) {
+        // scipy's robust-loss handling (construct_loss_function / scale_for_robust_loss_function,
+        // _lsq/least_squares.py, _lsq/common.py:720): cost 0.5 fs^2 rho(z); with the Jacobian the row is
+        // scaled by sqrt(max(rho' + 2 rho'' z, eps)) and the residual becomes r rho' / that factor
+        const double rs = r / a.f_scale;
+        const double z = rs * rs;
+        double r0, r1, r2;
+        robust_rho(a.loss, z, r0, r1, r2);
+        rho_cost = a.f_scale * a.f_scale * r0;
+        if (WITH_JAC) {
+          double js = r1 + 2.0 * r2 * z;
+          js = sqrt(js < 2.220446049250313e-16 ? 2.220446049250313e-16 : js);
+          r = r * r1 / js;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) jl[k] *= js;
+          tq[0] *= js; tq[1] *= js; tq[2] *= js;
+        }
+      } else {
+        rho_cost = r * r;
+      }
       if (WITH_JAC) {
         double G[9];
         build_G(w, B, C, G);
@@ -454,7 +476,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       }
     }
     a.r[i] = r;
-    cost_acc += r * r;
+    cost_acc += rho_cost;
     if (WITH_JAC) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) a.jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];

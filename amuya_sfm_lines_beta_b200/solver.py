@@ -151,6 +151,10 @@ class LineBA:
         o = LbaOptions()
         self._lib.lba_default_options(C.byref(o))
         for k, v in kw.items():
+            if k == "loss" and isinstance(v, str):
+                if v not in _lib.LOSSES:
+                    raise ValueError("`loss` must be one of {0} or a callable.".format(tuple(_lib.LOSSES)))
+                v = _lib.LOSSES[v]
             if not hasattr(o, k):
                 raise TypeError(f"unknown option {k!r}")
             setattr(o, k, v)

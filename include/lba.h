@@ -59,8 +59,18 @@ typedef struct lba_options {
   double pcg_tol;         /* eta: stop PCG when |r|_{M^-1} <= eta |r0|_{M^-1} */
   double min_ratio;       /* accept a step when actual/predicted > min_ratio */
   int32_t verbose;        /* 2: print scipy-style iteration table to stdout */
-  int32_t reserved;
+  int32_t flags;          /* bit 0: evaluate the trial point without its Jacobian (non-speculative) */
+  int32_t loss;           /* LBA_LOSS_*: scipy least_squares `loss` (forwarded as loss_f at bundle_adjustment.py:319) */
+  int32_t pad;
+  double f_scale;         /* scipy `f_scale` (soft margin between inliers and outliers); 1.0 like the reference */
 } lba_options;
+
+/* scipy.optimize.least_squares robust losses, rho(z) with z = (r/f_scale)^2 (scipy/optimize/_lsq/least_squares.py) */
+#define LBA_LOSS_LINEAR 0
+#define LBA_LOSS_SOFT_L1 1
+#define LBA_LOSS_HUBER 2
+#define LBA_LOSS_CAUCHY 3
+#define LBA_LOSS_ARCTAN 4
 
 #define LBA_TRACE_MAX 512
 typedef struct lba_report {

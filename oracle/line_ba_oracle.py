@@ -279,6 +279,46 @@ def update_scaling(D_prev, diag):
     return np.maximum(D_prev, d)
 
 
+def robust_rho(loss, z):
+    """rho(z), rho'(z), rho''(z) of scipy's robust losses (scipy/optimize/_lsq/least_squares.py: soft_l1,
+    huber, cauchy, arctan) for z = (f/f_scale)^2."""
+    z = np.asarray(z, dtype=np.float64)
+    if loss == "soft_l1":
+        t = 1.0 + z
+        return 2.0 * (np.sqrt(t) - 1.0), t ** -0.5, -0.5 * t ** -1.5
+    if loss == "huber":
+        big = z > 1.0
+        zs = np.where(big, z, 1.0)
+        return (np.where(big, 2.0 * np.sqrt(zs) - 1.0, z), np.where(big, zs ** -0.5, 1.0),
+                np.where(big, -0.5 * zs ** -1.5, 0.0))
+    if loss == "cauchy":
+        t = 1.0 + z
+        return np.log1p(z), 1.0 / t, -1.0 / (t * t)
+    if loss == "arctan":
+        t = 1.0 + z * z
+        return np.arctan(z), 1.0 / t, -2.0 * z / (t * t)
+    raise ValueError(loss)
+
+
+def robust_cost(r, loss, f_scale=1.0):
+    """0.5 * f_scale^2 * sum rho((r/f_scale)^2)  (scipy construct_loss_function, cost_only)."""
+    if loss == "linear":
+        return 0.5 * float(np.dot(r, r))
+    return 0.5 * f_scale * f_scale * float(np.sum(robust_rho(loss, (r / f_scale) ** 2)[0]))
+
+
+def scale_for_robust_loss(r, jc, jl, loss, f_scale=1.0):
+    """scipy ``scale_for_robust_loss_function`` (scipy/optimize/_lsq/common.py:720): rows scaled by
+    sqrt(max(rho' + 2 rho'' z, eps)), residuals by rho' over that factor."""
+    if loss == "linear":
+        return r, jc, jl
+    z = (r / f_scale) ** 2
+    _, r1, r2 = robust_rho(loss, z)
+    js = r1 + 2.0 * r2 * z
+    js = np.sqrt(np.maximum(js, DBL_EPSILON))
+    return r * r1 / js, jc * js[:, None], jl * js[:, None]
+
+
 @dataclass
 class LMOptions:
     max_iter: int = 50
@@ -291,6 +331,8 @@ class LMOptions:
     pcg_tol: float = 1e-2    # eta: stop when |r|_Minv <= eta |r0|_Minv
     pcg_max_iter: int = 200
     min_ratio: float = 1e-4
+    loss: str = "linear"    # scipy least_squares `loss` (bundle_adjustment.py:319 forwards loss_f)
+    f_scale: float = 1.0
 
 
 @dataclass
@@ -404,9 +446,10 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
     idx = np.arange(6)
 
     rep = LMReport()
-    r, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
+    r_true, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
     rep.n_jac += 1
-    cost = 0.5 * float(np.dot(r, r))
+    cost = robust_cost(r_true, opts.loss, opts.f_scale)
+    r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
     rep.cost_init = cost
     U, gc, V, gl = normal_equations(r, jc, jl, ci, li, nc, nl)
     Dc = update_scaling(None, U[:, idx, idx])
@@ -430,7 +473,7 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
         pts_new = pts + dl
         r_new = residuals_jacobian(om_new, ce_new, pts_new, ci, li, n, m0, m1)[0]
         rep.n_res += 1
-        cost_new = 0.5 * float(np.dot(r_new, r_new))
+        cost_new = robust_cost(r_new, opts.loss, opts.f_scale)
         step_norm = math.sqrt(float(np.sum(dc * dc) + np.sum(dl * dl)))
         x_norm = math.sqrt(float(np.sum(omega * omega) + np.sum(centre * centre) + np.sum(pts * pts)))
         actual = cost - cost_new
@@ -448,7 +491,8 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
         if accepted:
             omega, centre, pts = om_new, ce_new, pts_new
             cost = cost_new
-            r, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
+            r_true, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
+            r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
             rep.n_jac += 1
             U, gc, V, gl = normal_equations(r, jc, jl, ci, li, nc, nl)
             Dc = update_scaling(Dc, U[:, idx, idx])
@@ -471,7 +515,7 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
     rep.status = status
     rep.cost = cost
     cams_out = join_camera_params(omega, centre)
-    return cams_out, pts.reshape(-1, 3), r, rep
+    return cams_out, pts.reshape(-1, 3), r_true, rep
 
 
 # ---------------------------------------------------------------------------
@@ -484,7 +528,7 @@ def _x_pack(camera_params, points_3d):
 
 
 def scipy_reference_port(camera_params, points_3d, ci, li, n, p0, p1, mode="as_shipped",
-                         max_nfev=None, verbose=0, ftol=1e-4):
+                         max_nfev=None, verbose=0, ftol=1e-4, loss="linear"):
     """``run_bundle_adjustment`` (bundle_adjustment.py:254-349) with ``fun`` vectorised.
 
     mode="as_shipped": 2-point finite differences with the shipped sparsity
@@ -512,7 +556,7 @@ def scipy_reference_port(camera_params, points_3d, ci, li, n, p0, p1, mode="as_s
     def f(x):
         return residuals(x[:6 * nc].reshape(nc, 6), x[6 * nc:].reshape(npts, 3), ci, li, n, p0, p1)
 
-    kwargs = dict(verbose=verbose, x_scale='jac', ftol=ftol, method='trf', loss='linear',
+    kwargs = dict(verbose=verbose, x_scale='jac', ftol=ftol, method='trf', loss=loss,
                   max_nfev=max_nfev)
     if mode == "as_shipped":
         cols = bundle_adjustment_sparsity_columns(nc, ci, li)

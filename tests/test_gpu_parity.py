@@ -398,6 +398,47 @@ def test_device_resident_inputs(LineBA):
     ba.close(); ba2.close()
 
 
+@pytest.mark.parametrize("loss,f_scale", [("soft_l1", 1e-3), ("huber", 1e-3), ("cauchy", 1e-3), ("arctan", 5e-3), ("cauchy", 1.0)])
+def test_robust_losses_follow_the_oracle(LineBA, orc, loss, f_scale):
+    """N4: scipy's robust losses (loss_f is forwarded to least_squares at bundle_adjustment.py:319).  The
+    oracle's rho / row scaling are pinned to scipy's own functions (CPU test); here the CUDA LM must follow
+    the oracle LM with the same loss on a scene with gross outliers."""
+    s = synth(12, 300, 6, seed=2)
+    rng = np.random.default_rng(5)
+    bad = rng.choice(s.n_obs, 60, replace=False)
+    s.n[bad] = np.roll(s.n[bad], 1, axis=1); s.p0[bad] = np.roll(s.p0[bad], 1, axis=1); s.p1[bad] = np.roll(s.p1[bad], 1, axis=1)
+    kw = dict(max_iter=8, ftol=0.0, xtol=0.0, gtol=0.0)
+    ba = make_ctx(LineBA, s)
+    res = ba.lm_solve(s.camera_params, s.points_3d, loss=loss, f_scale=f_scale, **kw)
+    cams_o, pts_o, r_o, rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(loss=loss, f_scale=f_scale, **kw))
+    assert abs(res.cost_init - rep.cost_init) <= 1e-12 * rep.cost_init
+    cost_d = np.array([t["cost_new"] for t in res.trace]); cost_o = np.array([t["cost_new"] for t in rep.trace])
+    assert [t["accepted"] for t in res.trace] == [t["accepted"] for t in rep.trace]
+    assert np.all(np.abs(cost_d - cost_o) <= RTOL_TRAJ * cost_o)
+    assert abs(res.cost - rep.cost) <= RTOL_FINAL * rep.cost
+    assert np.max(np.abs(res.points_3d - pts_o)) <= RTOL_FINAL * np.max(np.abs(pts_o))
+    # the returned residual vector is fun itself (scipy's res.fun), not the rescaled one
+    r_chk = orc.residuals(res.camera_params, res.points_3d, *s.arrays()[2:])
+    assert np.all(np.abs(res.residuals - r_chk) <= residual_tol(r_chk))
+    assert abs(res.cost - orc.robust_cost(r_chk, loss, f_scale)) <= 1e-10 * res.cost
+    ba.close()
+
+
+def test_dropin_forwards_loss_f(LineBA, capsys):
+    from amuya_sfm_lines_beta_b200.bundle_adjustment import run_bundle_adjustment
+    from test_cabi_and_host import _objects_from_golden
+    s, q = load("toy1_lv2")
+    lines_3d, lines_2d = _objects_from_golden(q)
+    inp = {"camera_params": q["camera_params"], "Lines_3d": lines_3d, "camera_indices": q["camera_indices"],
+           "lines_indices": q["lines_indices"], "lines_2d": lines_2d}
+    _, _, _, rep_lin = run_bundle_adjustment(inp, "linear", return_report=True, max_iter=5)
+    _, _, _, rep_hub = run_bundle_adjustment(inp, "soft_l1", return_report=True, max_iter=5, f_scale=1e-4)
+    capsys.readouterr()
+    assert rep_hub.cost_init < rep_lin.cost_init * 1.0000001 and rep_hub.cost_init != rep_lin.cost_init
+    with pytest.raises(ValueError, match="`loss` must be one of"):
+        run_bundle_adjustment(inp, "bogus")
+
+
 def test_many_cameras_take_the_global_gather_variant(LineBA, orc):
     """More cameras than the shared-memory camera table holds (~1.3k): the evaluation kernel falls back to
     the global-memory gather variant; results must not change."""
@@ -418,11 +459,11 @@ def test_many_cameras_take_the_global_gather_variant(LineBA, orc):
 
 
 def test_non_speculative_path_matches(LineBA):
-    """reserved bit 0 disables the speculative trial Jacobian: same trajectory either way."""
+    """flags bit 0 disables the speculative trial Jacobian: same trajectory either way."""
     s = synth(12, 200, 5, seed=1)
     ba = make_ctx(LineBA, s)
     a = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0)
-    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0, reserved=1)
+    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0, flags=1)
     assert [t["accepted"] for t in a.trace] == [t["accepted"] for t in b.trace]
     assert np.allclose([t["cost_new"] for t in a.trace], [t["cost_new"] for t in b.trace], rtol=1e-12)
     assert abs(a.cost - b.cost) <= 1e-12 * a.cost

@@ -183,3 +183,39 @@ def test_reference_port_reproduces_as_shipped_behaviour():
     assert moved[:half].all() and not moved[half:].any()
     ref_cost = 0.5 * float(np.sum(q["ref_ba_residual"] ** 2))
     assert abs(sres.cost - ref_cost) < 0.2 * ref_cost
+
+
+@pytest.mark.parametrize("loss", ["soft_l1", "huber", "cauchy", "arctan"])
+def test_robust_rho_matches_scipy(loss):
+    """rho, rho', rho'' against scipy's own implementations (the reference forwards loss_f to scipy,
+    bundle_adjustment.py:319) -- this pins the robust-loss arithmetic the CUDA kernel restates."""
+    import importlib
+    lsq = importlib.import_module("scipy.optimize._lsq.least_squares")
+    z = np.concatenate([np.linspace(0, 3, 61), [1.0, 1.0 + 1e-12, 25.0, 1e4]])
+    rho = np.empty((3, z.size))
+    lsq.IMPLEMENTED_LOSSES[loss](z.copy(), rho, cost_only=False)
+    r0, r1, r2 = orc.robust_rho(loss, z)
+    assert np.allclose(r0, rho[0], rtol=1e-14, atol=0) and np.allclose(r1, rho[1], rtol=1e-14) and np.allclose(r2, rho[2], rtol=1e-14)
+    # the scaled system reproduces the gradient of the robust cost: J~^T f~ = J^T (rho' f)
+    rng = np.random.default_rng(0)
+    f = rng.normal(0, 1.5, 50); J = rng.normal(size=(50, 6))
+    ft, Jt, _ = orc.scale_for_robust_loss(f, J, J, loss)
+    assert np.allclose(Jt.T @ ft, J.T @ (orc.robust_rho(loss, f * f)[1] * f), rtol=1e-12)
+    # and scipy's scale_for_robust_loss_function gives the same rows / residuals
+    from scipy.optimize._lsq.common import scale_for_robust_loss_function
+    rho3 = np.stack(orc.robust_rho(loss, f * f))
+    Js, fs = scale_for_robust_loss_function(J.copy(), f.copy(), rho3)
+    assert np.allclose(Js, Jt, rtol=1e-13) and np.allclose(fs, ft, rtol=1e-13)
+
+
+def test_robust_lm_downweights_outliers():
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    s = make_synthetic_scene(10, 120, 5, seed=3)
+    rng = np.random.default_rng(1)
+    bad = rng.choice(s.n_obs, 30, replace=False)           # gross outliers: wrong 2D lines
+    s.n[bad] = np.roll(s.n[bad], 1, axis=1); s.p0[bad] = np.roll(s.p0[bad], 1, axis=1); s.p1[bad] = np.roll(s.p1[bad], 1, axis=1)
+    lin = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(max_iter=15))
+    rob = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(max_iter=15, loss="cauchy", f_scale=1e-3))
+    good = np.setdiff1d(np.arange(s.n_obs), bad)
+    assert rob[3].cost < rob[3].cost_init
+    assert np.sum(rob[2][good] ** 2) < np.sum(lin[2][good] ** 2)   # inliers fit better with the robust loss
