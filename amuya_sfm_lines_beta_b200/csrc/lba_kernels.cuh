@@ -362,7 +362,6 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, WITH_JAC, S);
   double* s_stg = reinterpret_cast<double*>(sbase + (size_t)S * stage_bytes);  // [256][kEvRow], WITH_JAC only
   const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : a.recs;
-  const size_t M = (size_t)a.Mp;
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
 
@@ -682,19 +681,9 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
   }
 }
 
-// Marquardt scaling D = diag(J^T J), zeros -> 1, running max
-// (scipy compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at :319).
-__global__ void k_update_scaling(int nblocks, const double* __restrict__ S /*[n][21]*/, double* __restrict__ D,
-                                 int first) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nblocks * 6) return;
-  const int b = t / 6, k = t % 6;
-  double d = S[(size_t)b * 21 + sym_idx(k, k)];
-  if (d == 0.0) d = 1.0;
-  D[t] = first ? d : fmax(D[t], d);
-}
-
-// after the all-reduce of U|gc: camera scaling + gradient inf-norm in one launch
+// after the all-reduce of U|gc: camera scaling (Marquardt: D = diag(J^T J), zeros -> 1, running max --
+// scipy compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at :319) and the camera part of
+// the gradient inf-norm, in one launch
 __global__ void k_cam_post(int nc, const double* __restrict__ S, const double* __restrict__ gc, double* __restrict__ D,
                            int first, unsigned long long* __restrict__ gbits) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -822,15 +811,6 @@ __device__ __forceinline__ void make_tab_entry(const double* __restrict__ G, con
   tab[5] = a0 * c1 - a1 * c0 + v[5];
 }
 
-__global__ void k_make_table(int nc, const double* __restrict__ Gm, const double* __restrict__ cams,
-                             const double* __restrict__ v, double* __restrict__ tab) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  double vv[6];
-  for (int k = 0; k < 6; ++k) vv[k] = v[(size_t)c * 6 + k];
-  make_tab_entry(Gm + (size_t)c * 9, cams + (size_t)c * 6, vv, tab + (size_t)c * 6);
-}
-
 struct LinePassArgs {
   int Mp, ntiles, lmax;
   const TileIdx* tidx;   // [ntiles]
@@ -884,7 +864,6 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   const int stage_bytes = lp_stage_bytes(a.lmax, MODE);
   double* ul = reinterpret_cast<double*>(smem + (size_t)kLpStages * stage_bytes);
   double* s_stg = ul + a.lmax * 6;  // [256][kLpRow]
-  const size_t M = (size_t)a.Mp;
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
   const int t = threadIdx.x;
@@ -1285,19 +1264,6 @@ struct Scalars {            // device-resident LM scalars, copied to the host on
   int clamped, pad;
 };
 
-// out[col] = sum_g partial[g][col] (fixed order); one CTA.
-__global__ void __launch_bounds__(1024) k_reduce_partials(int n, int ncols, const double* __restrict__ partial,
-                                                           double* __restrict__ out, double scale) {
-  __shared__ double red[32];
-  for (int col = 0; col < ncols; ++col) {
-    double acc = 0.0;
-    for (int g = threadIdx.x; g < n; g += 1024) acc += partial[(size_t)g * ncols + col];
-    const double s = block_sum<1024>(acc, red);
-    if (threadIdx.x == 0) out[col] = s * scale;
-    __syncthreads();
-  }
-}
-
 // cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms
 // (grid-wide sums by the last CTA, fixed order).
 constexpr int kCamStepThreads = 128;
@@ -1330,21 +1296,6 @@ __global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const doub
   }
   const double sums[2] = {block_sum<kCamStepThreads>(d2, red), block_sum<kCamStepThreads>(x2, red)};
   last_cta_reduce<kCamStepThreads, 2>(sums, partial, ticket, out2, 1.0, red);
-}
-
-// inf-norm via order-preserving integer max on non-negative doubles (exact, order independent)
-__global__ void k_absmax(size_t n, const double* __restrict__ v, unsigned long long* __restrict__ out) {
-  double mx = 0.0;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-    const double a = fabs(v[t]);
-    mx = (a > mx || a != a) ? a : mx;  // NaN propagates
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
-    mx = (other > mx || other != other) ? other : mx;
-  }
-  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
 __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
