@@ -372,6 +372,16 @@ static inline size_t peer_slot_off(const lba_ctx* c, int region, unsigned long l
   return c->rgn_off[region] + (size_t)(seq & 1ULL) * c->rgn_cap[region];
 }
 
+// A fused producer -> consumer all-reduce on `region`: returns the slot the producer must write and fills
+// `pl` (pl.seq == 0 when the peer transport is not active: the caller then uses reduce_finish).
+static double* fused_link(lba_ctx* c, int region, size_t n, double* local, PeerLink* pl) {
+  memset(pl, 0, sizeof *pl);
+  if (!peer_fits(c, region, n)) return local;
+  pl->pa = c->peer_args; pl->region = region; pl->seq = ++c->rgn_seq[region];
+  pl->slot_off = peer_slot_off(c, region, pl->seq); pl->ticket = c->tickets.p + 3;
+  return reinterpret_cast<double*>((unsigned char*)c->peer_local + kPeerDataOff) + pl->slot_off;
+}
+
 // Where a producer kernel should write the partial sums that will be all-reduced into `local`:
 // straight into the symmetric slot of the NEXT call on that region when the peer path is active.
 static double* reduce_target(lba_ctx* c, int region, double* local, size_t n) {
@@ -779,17 +789,24 @@ static void accept_candidate(lba_ctx* c, bool have_new_eval) {
 static int run_blocks(lba_ctx* c, bool full) {
   if (c->nc > 0) {
     const size_t n27 = (size_t)c->nc * 27;
-    double* out = reduce_target(c, kRgnU, c->U.p, n27);
-    if (full)
+    PeerLink pl;
+    memset(&pl, 0, sizeof pl);
+    if (full) {
+      // API path: the complete blocks, reduced into U | gc by a separate reduce
+      double* out = reduce_target(c, kRgnU, c->U.p, n27);
       LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-             (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21);
-    else {
+             (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21, pl);
+      CKR(reduce_finish(c, kRgnU, c->U.p, n27));
+    } else {
+      // LM path: diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
+      double* out = reduce_target(c, kRgnU, c->U.p, n27);
       if (out != c->U.p) CK(cudaMemsetAsync(out, 0, n27 * 8, c->stream));   // k_cam_grad writes the diagonal only
-      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out, out + (size_t)c->nc * 21);
+      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out,
+             out + (size_t)c->nc * 21, pl);
+      CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     }
-    CKR(reduce_finish(c, kRgnU, c->U.p, n27));
-    LAUNCH(c, LBA_K_MISC, k_cam_post, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, gc_of(c), c->Dc.p,
-           c->pending_first ? 1 : 0, c->gbits.p);
+    LAUNCH(c, LBA_K_MISC, k_cam_post, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, gc_of(c), c->gc.p, c->Dc.p,
+           c->pending_first ? 1 : 0, c->gbits.p, pl);
   }
   c->have_scaling = true;
   CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
@@ -820,17 +837,22 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
   la.w = c->w.p;
   if (nc > 0) {
     const size_t n27 = (size_t)nc * 27;
+    // 27 values per camera and a thread-per-camera consumer: a separate, massively parallel reduce
+    // kernel (zero-copy producer) beats fusing the peer loads into k_cam_finish
+    PeerLink pl;
+    memset(&pl, 0, sizeof pl);
     double* out = reduce_target(c, kRgnM, c->Mpart.p, n27);
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-           (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21);
+           (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21, pl);
     CKR(reduce_finish(c, kRgnM, c->Mpart.p, n27));
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, gc_of(c), bpart_of(c), c->Minv.p, c->b.p, c->clamped.p);
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p, pl);
   }
   CgArgs& ca = sp->ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
   ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
   ca.partial = c->cg_partial.p; ca.gb = c->gridbar.p;
+  memset(&ca.pl, 0, sizeof ca.pl);
   LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, c->cg_ctas, kCgBlock, ca);
   sp->issued = 0;
   return LBA_OK;
@@ -840,11 +862,17 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
 static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
   for (int q = 0; q < n && sp->issued < sp->ca.max_iter; ++q, ++sp->issued) {
     if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
+    PeerLink pl;
+    memset(&pl, 0, sizeof pl);
     if (c->nc > 0) {
-      double* out = reduce_target(c, kRgnQ, c->qpart.p, (size_t)c->nc * 6);
-      LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p);
-      CKR(reduce_finish(c, kRgnQ, c->qpart.p, (size_t)c->nc * 6));
+      const size_t n6 = (size_t)c->nc * 6;
+      // fused all-reduce with the peer transport: k_pcg_cam writes this rank's slot and signals,
+      // k_cg_step waits and adds the slots of all ranks
+      double* out = fused_link(c, kRgnQ, n6, c->qpart.p, &pl);
+      LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), kCamThreads, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
+      if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
+    sp->ca.pl = pl;
     LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
   }
   CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
@@ -980,7 +1008,7 @@ extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double*
   CK(cudaSetDevice(ctx->device));
   CKR(run_blocks(ctx, true));
   if (U && ctx->nc) CK(cudaMemcpyAsync(U, ctx->U.p, (size_t)ctx->nc * 21 * 8, cudaMemcpyDefault, ctx->stream));
-  if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, gc_of(ctx), (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
+  if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, ctx->gc.p, (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
   if (V && ctx->nl) CK(cudaMemcpyAsync(V, ctx->V.p, (size_t)ctx->nl * 21 * 8, cudaMemcpyDefault, ctx->stream));
   if (gl && ctx->nl) CK(cudaMemcpyAsync(gl, ctx->gl.p, (size_t)ctx->nl * 6 * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -166,6 +166,81 @@ __device__ __forceinline__ void load6(const double* __restrict__ p, double v[6])
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
 }
 
+// ---- NVLink peer-memory primitives (see the all-reduce section near the end of this file) ----------
+constexpr int kMaxPeers = 8;
+enum { kRgnQ = 0, kRgnU, kRgnM, kRgnS, kRgnCount };
+constexpr int kPeerDataOff = 1024;   // flags: kRgnCount*2*kMaxPeers*8 = 512 B
+
+struct PeerArgs {
+  unsigned char* peer[kMaxPeers];   // peer[r] = base of rank r's symmetric buffer as mapped here
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_relaxed_sys2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// A fused producer epilogue / consumer prologue pair for one region of the symmetric buffers:
+// the LAST CTA of the producer grid (ticket) stores seq into flag[region][slot][my_rank] of every
+// rank; the consumer waits until its own flags of all ranks reach seq.
+struct PeerLink {
+  PeerArgs pa;
+  int region;
+  size_t slot_off;          // doubles, inside the data area, of (region, seq & 1)
+  unsigned long long seq;   // 0: peer path inactive (single GPU or NCCL transport)
+  unsigned int* ticket;
+};
+__device__ __forceinline__ void peer_signal_last_cta(const PeerLink& pl) {
+  __shared__ int s_last_peer;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last_peer = (atomicAdd(pl.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last_peer) return;
+  if (threadIdx.x == 0) { *pl.ticket = 0u; __threadfence_system(); }
+  __syncthreads();
+  if (threadIdx.x < pl.pa.world) {
+    const int fidx = (pl.region * 2 + (int)(pl.seq & 1ULL)) * kMaxPeers;
+    st_release_sys(reinterpret_cast<unsigned long long*>(pl.pa.peer[threadIdx.x]) + fidx + pl.pa.rank, pl.seq);
+  }
+}
+__device__ __forceinline__ void peer_wait(const PeerLink& pl) {
+  if (threadIdx.x < pl.pa.world) {
+    const int fidx = (pl.region * 2 + (int)(pl.seq & 1ULL)) * kMaxPeers;
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pl.pa.peer[pl.pa.rank]) + fidx + threadIdx.x;
+    while (ld_acquire_sys(f) < pl.seq) { }
+  }
+  __syncthreads();
+}
+// sum over ranks, in rank order, of element e of the region slot
+__device__ __forceinline__ double peer_sum(const PeerLink& pl, size_t e) {
+  double v[kMaxPeers];
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r)   // all W remote loads are in flight before the first add
+    v[r] = r < pl.pa.world ? ld_relaxed_sys(reinterpret_cast<const double*>(pl.pa.peer[r] + kPeerDataOff) + pl.slot_off + e) : 0.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) acc += v[r];
+  return acc;
+}
+
 // ---------------------------------------------------------------------------------
 // setup kernels
 // ---------------------------------------------------------------------------------
@@ -605,7 +680,8 @@ __global__ void k_project(const ProjectArgs a) {
 __global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict__ cam_ptr,
                                                            const int* __restrict__ cam_perm,
                                                            const double* __restrict__ jc, const double* __restrict__ r,
-                                                           double* __restrict__ S, double* __restrict__ v) {
+                                                           double* __restrict__ S, double* __restrict__ v,
+                                                           const PeerLink pl) {
   __shared__ double sm[kCamThreads / 32][12];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
@@ -634,6 +710,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict_
     if (threadIdx.x < 6) S[(size_t)c * 21 + sym_idx(threadIdx.x, threadIdx.x)] = s;
     else v[(size_t)c * 6 + threadIdx.x - 6] = s;
   }
+  if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_post) adds the ranks' slots
 }
 
 __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict__ cam_ptr,
@@ -641,7 +718,8 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
                                                             const double* __restrict__ jc,
                                                             const double* __restrict__ wa,
                                                             const double* __restrict__ wb,
-                                                            double* __restrict__ S, double* __restrict__ v) {
+                                                            double* __restrict__ S, double* __restrict__ v,
+                                                            const PeerLink pl) {
   __shared__ double sm[kCamThreads / 32][27];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
@@ -679,21 +757,26 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
     if (threadIdx.x < 21) S[(size_t)c * 21 + threadIdx.x] = s;
     else v[(size_t)c * 6 + threadIdx.x - 21] = s;
   }
+  if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_finish) adds the ranks' slots
 }
 
 // after the all-reduce of U|gc: camera scaling (Marquardt: D = diag(J^T J), zeros -> 1, running max --
 // scipy compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at :319) and the camera part of
 // the gradient inf-norm, in one launch
-__global__ void k_cam_post(int nc, const double* __restrict__ S, const double* __restrict__ gc, double* __restrict__ D,
-                           int first, unsigned long long* __restrict__ gbits) {
+__global__ void k_cam_post(int nc, const double* __restrict__ S, const double* __restrict__ gc_in, double* __restrict__ gc_out,
+                           double* __restrict__ D, int first, unsigned long long* __restrict__ gbits, const PeerLink pl) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double mx = 0.0;
+  if (pl.seq) peer_wait(pl);   // multi-GPU: S | gc live in the symmetric slots of all ranks
   if (t < nc * 6) {
     const int b = t / 6, k = t % 6;
-    double d = S[(size_t)b * 21 + sym_idx(k, k)];
+    const size_t ed = (size_t)b * 21 + sym_idx(k, k), eg = (size_t)nc * 21 + t;
+    double d = pl.seq ? peer_sum(pl, ed) : S[ed];
+    const double g = pl.seq ? peer_sum(pl, eg) : gc_in[t];
     if (d == 0.0) d = 1.0;
     D[t] = first ? d : fmax(D[t], d);
-    mx = fabs(gc[t]);
+    gc_out[t] = g;
+    mx = fabs(g);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -773,12 +856,13 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
 __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const double* __restrict__ Mpart,
                                                      const double* __restrict__ Dc, const double* __restrict__ gc,
                                                      const double* __restrict__ bpart, double* __restrict__ Minv,
-                                                     double* __restrict__ b, int* __restrict__ clamped) {
+                                                     double* __restrict__ b, int* __restrict__ clamped, const PeerLink pl) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl.seq) peer_wait(pl);   // multi-GPU: Mpart | bpart live in the symmetric slots of all ranks
   if (c >= nc) return;
   double S[21];
 #pragma unroll
-  for (int e = 0; e < 21; ++e) S[e] = Mpart[(size_t)c * 21 + e];
+  for (int e = 0; e < 21; ++e) S[e] = pl.seq ? peer_sum(pl, (size_t)c * 21 + e) : Mpart[(size_t)c * 21 + e];
 #pragma unroll
   for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * Dc[(size_t)c * 6 + k];
   const int cl = spd6_inverse(S);
@@ -786,7 +870,10 @@ __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const do
 #pragma unroll
   for (int e = 0; e < 21; ++e) Minv[(size_t)c * 21 + e] = S[e];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) b[(size_t)c * 6 + k] = bpart[(size_t)c * 6 + k] - gc[(size_t)c * 6 + k];
+  for (int k = 0; k < 6; ++k) {
+    const double bp = pl.seq ? peer_sum(pl, (size_t)nc * 21 + (size_t)c * 6 + k) : bpart[(size_t)c * 6 + k];
+    b[(size_t)c * 6 + k] = bp - gc[(size_t)c * 6 + k];
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1033,36 +1120,42 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
 }
 
 // Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}
-__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(const int* __restrict__ cam_ptr,
+__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int nc, const int* __restrict__ cam_ptr,
                                                           const int* __restrict__ cam_perm,
                                                           const double* __restrict__ jc, const double* __restrict__ w,
-                                                          double* __restrict__ qpart, const CgState* __restrict__ st) {
+                                                          double* __restrict__ qpart, const CgState* __restrict__ st,
+                                                          const PeerLink pl) {
   __shared__ double sm[kCamThreads / 32][6];
   if (st->done) return;
-  const int c = blockIdx.x;
-  const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
-  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = blockIdx.x; c < nc; c += gridDim.x) {
+    const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
-  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
-    const double wi = __ldg(w + cam_perm[j]);
-    double x[6];
-    load6(jc + (size_t)j * 6, x);
+    for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+      const double wi = __ldg(w + cam_perm[j]);
+      double x[6];
+      load6(jc + (size_t)j * 6, x);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) acc[k] += wi * x[k];
-  }
-  const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
+      for (int k = 0; k < 6; ++k) acc[k] += wi * x[k];
+    }
+    const int wp = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (l == 0) sm[wp][k] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    double s = 0.0;
+    for (int k = 0; k < 6; ++k) {
+      const double s = warp_sum(acc[k]);
+      if (l == 0) sm[wp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
-    qpart[(size_t)c * 6 + threadIdx.x] = s;
+      for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+      qpart[(size_t)c * 6 + threadIdx.x] = s;
+    }
+    __syncthreads();
   }
+  // multi-GPU, peer transport: qpart IS this rank's slot of the symmetric buffer; the last CTA tells
+  // every rank that it is complete (the consumer, k_cg_step, adds the slots of all ranks itself)
+  if (pl.seq) peer_signal_last_cta(pl);
 }
 
 struct GridBar;
@@ -1080,6 +1173,7 @@ struct CgArgs {
   CgState* st;
   double* partial;   // [2][kCgMaxCtas] block sums of the grid-wide reductions
   GridBar* gb;
+  PeerLink pl;       // seq != 0: S p is the sum over ranks of the peer slots (fused all-reduce)
 };
 
 // The CG vector work runs on a small co-resident grid (<= one CTA per SM): every camera owns 8
@@ -1195,13 +1289,16 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
   const int gt = blockIdx.x * kCgBlock + threadIdx.x;
   const int k = gt & 7;
   const int groups = gridDim.x * kCgBlock / 8;
+  const bool fused = a.pl.seq != 0ULL;
+  if (fused) peer_wait(a.pl);   // every rank's partial S p is complete
   double acc = 0.0;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
     const int c = c0 + (gt >> 3);
     if (c < a.nc && k < 6) {
       const size_t e = (size_t)c * 6 + k;
       const double pp = a.p[e];
-      const double q = a.qpart[e] + a.lam * a.Dc[e] * pp;
+      const double qsum = fused ? peer_sum(a.pl, e) : a.qpart[e];
+      const double q = qsum + a.lam * a.Dc[e] * pp;
       a.z[e] = q;  // z is free until the preconditioner is applied below; reuse it to keep q
       acc += pp * q;
     }
@@ -1341,29 +1438,6 @@ __global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, cons
 // so all ranks end with identical bits.  A slot is rewritten two calls later, after every peer has
 // signalled the call in between, i.e. has finished reading it.
 // ---------------------------------------------------------------------------------
-constexpr int kMaxPeers = 8;
-enum { kRgnQ = 0, kRgnU, kRgnM, kRgnS, kRgnCount };
-constexpr int kPeerDataOff = 1024;   // flags: kRgnCount*2*kMaxPeers*8 = 512 B
-
-struct PeerArgs {
-  unsigned char* peer[kMaxPeers];   // peer[r] = base of rank r's symmetric buffer as mapped here
-  int rank, world;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double2 ld_relaxed_sys2(const double* p) {
-  double2 v;
-  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-  return v;
-}
-
 // slot_off: offset in doubles of (region, slot) inside the data area; n must be even (padded by the host)
 // src != nullptr: single-CTA mode that first copies n doubles from local memory into the own slot.
 template <bool MAX_U64>

@@ -105,11 +105,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_scene(n_gpus, scale=1.0, seed=0, cams=0):
+def make_scene(n_gpus, scale=1.0, seed=0, cams=0, variant="A"):
     from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
     n_lines = int(PER_GPU_LINES * n_gpus * scale)
     n_cams = cams or max(OBS_PER_LINE, int(N_CAMERAS * n_gpus * scale))
-    return make_synthetic_scene(n_cams, n_lines, OBS_PER_LINE, seed=seed, variant="A")
+    return make_synthetic_scene(n_cams, n_lines, OBS_PER_LINE, seed=seed, variant=variant)
 
 
 def cpu_reference_run(steps, warmup, full_obs, mode="analytic"):
@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-mode", default="analytic", choices=["analytic", "as_shipped"])
     ap.add_argument("--cams", type=int, default=0, help="debug: override the camera count")
+    ap.add_argument("--variant", default="A", choices=["A", "B"], help="visibility: A uniform random, B contiguous camera window")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +150,8 @@ def main():
     full_obs = int(PER_GPU_LINES * args.gpus * args.scale) * OBS_PER_LINE
     n_cams_total = args.cams or max(OBS_PER_LINE, int(N_CAMERAS * args.gpus * args.scale))
     workload = (f"synthetic line-SfM scene, {n_cams_total} cameras / {full_obs // OBS_PER_LINE} 3D lines / {full_obs} "
-                f"line observations (10 views per line, uniform random visibility), seed 0")
+                f"line observations (10 views per line, "
+                f"{'uniform random visibility' if args.variant == 'A' else 'contiguous camera-window visibility'}), seed 0")
     config = {"workload": workload, "obs_per_gpu": full_obs // max(args.gpus, 1), "parallelism": f"obs-shard x{args.gpus}",
               "l2": "working set per LM iteration (~0.5 GB/GPU) exceeds the 126 MB L2; no flush needed"}
 
@@ -173,7 +175,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    s = make_scene(args.gpus, args.scale, cams=args.cams)
+    s = make_scene(args.gpus, args.scale, cams=args.cams, variant=args.variant)
     shard = plan_shards(s.lines_indices, s.n_lines, world)[rank]
     ci, li, n, p0, p1, pts_local = local_problem(shard, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1, s.points_3d)
     m_local = ci.shape[0]
