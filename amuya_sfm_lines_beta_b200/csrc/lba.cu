@@ -118,7 +118,7 @@ struct lba_ctx {
   int grid_eval_j = 1, grid_eval_r = 1, grid_lp[3] = {1, 1, 1};
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
   bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
-  int eval_stages_j = 3, eval_stages_r = 3;
+  int eval_stages_j = 3, eval_stages_r = 3, eval_stg_bufs = 1;
 
   // state
   DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
@@ -628,20 +628,37 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     };
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    // preferred: 2 sub-groups per CTA sharing a shared-memory camera table (1 CTA / SM)
+    // does a kernel variant fit on an SM with this much dynamic shared memory?
+    auto fits = [&](auto kern, int threads, int smem) -> bool {
+      if (smem > max_smem) return false;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, (size_t)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (dbg) fprintf(stderr, "[lba_set_problem] fits? threads %d smem %d -> %d block(s)/SM\n", threads, smem, nb);
+      return nb >= 1;
+    };
+    // preferred: 2 sub-groups per CTA sharing a shared-memory camera table (1 CTA / SM), with two
+    // staging buffers (one barrier per tile) when shared memory allows
     ctx->eval_tab_smem = false;
-    if (nc > 0 && eval_smem_bytes(lmax, true, 2, 2, nc) + 4096 <= max_smem) {
+    ctx->eval_stg_bufs = 1;
+    const bool tab_r = nc > 0 && fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, false, 2, 2, nc, 1));
+    if (tab_r && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, true, 2, 2, nc, 2))) {
+      ctx->eval_tab_smem = true; ctx->eval_stg_bufs = 2;
+    } else if (tab_r && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, true, 2, 2, nc, 1))) {
       ctx->eval_tab_smem = true;
+    }
+    if (ctx->eval_tab_smem) {
       ctx->eval_stages_j = 2;
-      ctx->eval_stages_r = eval_smem_bytes(lmax, false, 3, 2, nc) + 4096 <= max_smem ? 3 : 2;
-      ctx->smem_eval_j = eval_smem_bytes(lmax, true, ctx->eval_stages_j, 2, nc);
-      ctx->smem_eval_r = eval_smem_bytes(lmax, false, ctx->eval_stages_r, 2, nc);
+      ctx->eval_stages_r = fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, false, 3, 2, nc, 1)) ? 3 : 2;
+      ctx->smem_eval_j = eval_smem_bytes(lmax, true, ctx->eval_stages_j, 2, nc, ctx->eval_stg_bufs);
+      ctx->smem_eval_r = eval_smem_bytes(lmax, false, ctx->eval_stages_r, 2, nc, 1);
       CKR(plan(k_eval<true, 2, true>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 2, true>, 2 * kTile, ctx->smem_eval_r, 2, &ctx->grid_eval_r));
     } else {
       ctx->eval_stages_j = ctx->eval_stages_r = 3;
-      ctx->smem_eval_j = eval_smem_bytes(lmax, true, 3, 1, 0);
-      ctx->smem_eval_r = eval_smem_bytes(lmax, false, 3, 1, 0);
+      ctx->eval_stg_bufs = 2;
+      ctx->smem_eval_j = eval_smem_bytes(lmax, true, 3, 1, 0, 2);
+      ctx->smem_eval_r = eval_smem_bytes(lmax, false, 3, 1, 0, 1);
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
@@ -690,7 +707,7 @@ static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc *
 
 static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
   EvalArgs a;
-  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3;
+  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3; a.stg_bufs = 1;
   a.tidx = c->tidx.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
   a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p;
   a.cost_partial = c->cost_partial.p;
@@ -753,6 +770,7 @@ static int run_jacobian(lba_ctx* c, bool into_new) {
     if (into_new) { a.jl = c->jl_new.p; a.jc = c->jc_new.p; a.V = c->V_new.p; a.gl = c->gl_new.p; }
     a.gbits = gb;
     a.nstages = c->eval_stages_j;
+    a.stg_bufs = c->eval_stg_bufs;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
   } else {

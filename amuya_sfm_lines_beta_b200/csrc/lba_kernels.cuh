@@ -381,6 +381,7 @@ __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, c
 struct EvalArgs {
   int Mp, ntiles, lmax;    // lmax: max lines per tile rounded up to 8 (sizes the smem stage)
   int nc, nstages;         // cameras (size of the shared-memory table), pipeline depth (<= kMaxStages)
+  int stg_bufs;            // 1 or 2 staging buffers for the per-line sums (2: one barrier per tile instead of two)
   const TileIdx* tidx;     // [ntiles]
   const double* cst;       // [ntiles][9][256]
   const CamRec* recs;
@@ -413,13 +414,13 @@ __device__ __forceinline__ void sub_sync(int sub) {
 constexpr int kEvOffIdx = 9 * kTile * 8;
 constexpr int kEvOffPts = kEvOffIdx + (int)sizeof(TileIdx);
 __host__ __device__ inline int eval_stage_bytes(int lmax) { return (kEvOffPts + lmax * 48 + 127) & ~127; }
-constexpr int kEvRow = 9;  // staging row stride in doubles: (jl[6], r, pad) -> 72 B, conflict-free per half-warp
-__host__ __device__ inline int eval_sub_bytes(int lmax, bool with_jac, int nstages) {
-  return nstages * eval_stage_bytes(lmax) + (with_jac ? kTile * kEvRow * 8 : 0);
+constexpr int kEvRow = 7;  // staging row: (jl[6], r) = 56 B, an odd number of 8 B words: conflict-free per half-warp
+__host__ __device__ inline int eval_sub_bytes(int lmax, bool with_jac, int nstages, int stg_bufs) {
+  return nstages * eval_stage_bytes(lmax) + (with_jac ? stg_bufs * kTile * kEvRow * 8 : 0);
 }
 __host__ __device__ inline int eval_tab_bytes(int nc) { return (nc * (int)sizeof(CamRec) + 127) & ~127; }
-__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac, int nstages, int nsub, int nc_tab) {
-  return eval_tab_bytes(nc_tab) + nsub * eval_sub_bytes(lmax, with_jac, nstages) + 128;
+__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac, int nstages, int nsub, int nc_tab, int stg_bufs) {
+  return eval_tab_bytes(nc_tab) + nsub * eval_sub_bytes(lmax, with_jac, nstages, stg_bufs) + 128;
 }
 
 // Fused residual (+ Jacobian + per-line blocks) over the tiles.  A CTA is NSUB independent
@@ -434,8 +435,12 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   const int stage_bytes = eval_stage_bytes(a.lmax);
   const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile;
   const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
-  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, WITH_JAC, S);
-  double* s_stg = reinterpret_cast<double*>(sbase + (size_t)S * stage_bytes);  // [256][kEvRow], WITH_JAC only
+  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, WITH_JAC, S, a.stg_bufs);
+  double* s_stg0 = reinterpret_cast<double*>(sbase + (size_t)S * stage_bytes);  // stg_bufs x [256][kEvRow], WITH_JAC only
+  // With two staging buffers the only barrier of a tile is the one between staging the rows and the
+  // per-line sums; the stage of tile it-1 is then refilled right after the barrier of tile it (every
+  // warp has passed the sums of tile it-1 by then).
+  const bool deferred = WITH_JAC && a.stg_bufs == 2;
   const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : a.recs;
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
@@ -482,10 +487,14 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     const unsigned char* s_ll = s_idx->ll;
     const TileMeta* s_meta = &s_idx->meta;
     const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
+    double* s_stg = s_stg0 + (deferred ? (size_t)(it & 1) * kTile * kEvRow : 0);
     int cur_l0 = 0, cur_nl = 0;
-    if (t == 0 && it + S + 1 < my_n) {  // prefetch the scalars for the issue after next
-      const TileMeta* mt = &a.tidx[first + (it + S + 1) * stride].meta;
-      cur_l0 = mt->l0; cur_nl = mt->nl;
+    {  // prefetch the scalars for the issue after next
+      const int nxt = deferred ? it + S : it + S + 1;
+      if (t == 0 && nxt < my_n && (!deferred || it >= 1)) {
+        const TileMeta* mt = &a.tidx[first + nxt * stride].meta;
+        cur_l0 = mt->l0; cur_nl = mt->nl;
+      }
     }
     mbar_wait(&full[sub][it % S], (it / S) & 1);
 
@@ -558,7 +567,12 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
 #pragma unroll
       for (int k = 0; k < 6; ++k) s_stg[t * kEvRow + k] = jl[k];
       s_stg[t * kEvRow + 6] = r;
+      if (deferred) fence_proxy_async();
       sub_sync<NSUB>(sub);
+      if (deferred && t == 0 && it >= 1) {   // every warp is done with tile it-1: refill its stage
+        if (it - 1 + S < my_n) issue(it - 1 + S, nx_nl, nx_l0);
+        nx_l0 = cur_l0; nx_nl = cur_nl;
+      }
       // per-line blocks V_l = sum jl jl^T (21) and g_l = sum jl r (6): four register-blocked work
       // items per line (rows {0}, {1}, {2,5}, {3,4} of the upper triangle: 7/6/7/7 FMAs per
       // observation on 7/6/5/4 shared-memory loads), fixed summation order
@@ -616,11 +630,13 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
         gmax = (ab1 > gmax || ab1 != ab1) ? ab1 : gmax;
       }
     }
-    fence_proxy_async();
-    sub_sync<NSUB>(sub);  // the stage is free: refill it with tile it + S
-    if (t == 0) {
-      if (it + S < my_n) issue(it + S, nx_nl, nx_l0);
-      nx_l0 = cur_l0; nx_nl = cur_nl;
+    if (!deferred) {
+      fence_proxy_async();
+      sub_sync<NSUB>(sub);  // the stage is free: refill it with tile it + S
+      if (t == 0) {
+        if (it + S < my_n) issue(it + S, nx_nl, nx_l0);
+        nx_l0 = cur_l0; nx_nl = cur_nl;
+      }
     }
   }
   if (WITH_JAC) {
