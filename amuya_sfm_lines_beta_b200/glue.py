@@ -1,0 +1,93 @@
+"""Array-native glue between the reference's ``Domain`` objects and the GPU solver.
+
+The reference rebuilds the BA input with Python loops after every registered view and walks 2 m ``Line``
+objects again inside ``run_bundle_adjustment`` (``src/seq_utils.py:138-208``, ``src/bundle_adjustment.py:194-250``).
+These helpers produce the same arrays in one vectorised pass, keep one ``LineBA`` context alive across the
+incremental loop (device buffers are reused, only grown) and write the result back exactly as
+``update_structure_motion`` does (``src/seq_utils.py:211-252``).
+
+They operate on the reference's own objects (``domain.views[i].P.R / .c``, ``domain.tracker.ids / .bin``,
+``domain.lines2d[j].n / .points[e].p``, ``domain.lines3d[L].points[e].coord``) and need ``cv2`` for the two
+``cv2.Rodrigues`` conversions the reference itself performs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .solver import LineBA
+
+
+def input_arrays_from_domain(domain, last_view=2):
+    """Vectorised ``input_bundle_adj(domain, "Rodrigues", last_view)`` (seq_utils.py:138-208).
+
+    Returns ``dict(camera_params (Nc,6) f64 interleaved, points_3d (2Nl,3), camera_indices (m,) int64,
+    lines_indices (m,) int64, n, p0, p1 (m,3) f64, line_ids (m,) int64)`` -- the same values, order and dtypes
+    the reference's dict leads to after ``point_wise_input``.
+    """
+    import cv2
+
+    views = domain.views[:last_view + 1]
+    cams = np.empty((len(views), 3, 2), dtype=np.float64)
+    for i, v in enumerate(views):
+        cams[i, :, 0] = cv2.Rodrigues(np.asarray(v.P.R))[0].ravel()          # :179
+        cams[i, :, 1] = np.asarray(v.P.c, dtype=np.float64).ravel()           # :172
+    bin_ = np.asarray(domain.tracker.bin)
+    ids_ = np.asarray(domain.tracker.ids)
+    check = bin_.sum(axis=1)
+    n_tracks = int(np.count_nonzero(check > 1))                               # :188-189
+    t_idx, v_idx = np.where(bin_[:n_tracks] == 1)                             # :190  (track-major, view-ascending)
+    line_ids = ids_[t_idx, v_idx].astype(np.int64)                            # :192
+    lines2d = domain.lines2d
+    n = np.array([lines2d[j].n for j in line_ids], dtype=np.float64).reshape(-1, 3)
+    p0 = np.array([lines2d[j].points[0].p for j in line_ids], dtype=np.float64).reshape(-1, 3)
+    p1 = np.array([lines2d[j].points[1].p for j in line_ids], dtype=np.float64).reshape(-1, 3)
+    pts = np.array([np.asarray(L.points[e].coord)[:3] for L in domain.lines3d for e in (0, 1)])  # bundle_adjustment.py:231-233
+    return dict(camera_params=cams.reshape(len(views), 6), points_3d=pts,
+                camera_indices=v_idx.astype(np.int64), lines_indices=t_idx.astype(np.int64),
+                n=n, p0=p0, p1=p1, line_ids=line_ids)
+
+
+def update_domain_from_arrays(domain, op_camera_params, op_points_3d, last_view=2, camera_cls=None):
+    """``update_structure_motion`` (seq_utils.py:211-252) from the solver's output arrays."""
+    import cv2
+
+    if camera_cls is None:
+        camera_cls = type(domain.views[0].P)
+    K = np.asarray(domain.K)
+    for i, v in enumerate(domain.views):
+        if i == last_view + 1:
+            break
+        cam = np.asarray(op_camera_params[i]).reshape(3, 2)
+        R = np.array(cv2.Rodrigues(cam[:, 0])[0])                                # :240-241
+        c = cam[:, 1]
+        t = np.array([np.dot(R, -c)]).reshape((3, 1))                            # :243
+        Pi = camera_cls(K @ np.concatenate((R, t), axis=1))
+        Pi.factor()
+        Pi.center()
+        v.P = Pi
+    for i, L in enumerate(domain.lines3d):
+        L.points[0].coord = op_points_3d[2 * i]                                  # :250-252
+        L.points[1].coord = op_points_3d[2 * i + 1]
+
+
+class IncrementalBA:
+    """One GPU context for the whole incremental reconstruction (src/main.py:111-133 re-runs BA after every
+    added view on a growing problem)."""
+
+    def __init__(self, device=0):
+        self.ba = LineBA(device)
+        self.last = None
+
+    def solve(self, domain, last_view, loss_f="linear", write_back=True, **options):
+        a = input_arrays_from_domain(domain, last_view)
+        nc = a["camera_params"].shape[0]
+        nl = a["points_3d"].shape[0] // 2
+        self.ba.set_problem(nc, nl, a["camera_indices"], a["lines_indices"], a["n"], a["p0"], a["p1"])
+        res = self.ba.lm_solve(a["camera_params"], np.asarray(a["points_3d"], dtype=np.float64), loss=loss_f, **options)
+        if write_back:
+            update_domain_from_arrays(domain, res.camera_params, res.points_3d, last_view)
+        self.last = res
+        return res.camera_params, res.points_3d, res.residuals
+
+    def close(self):
+        self.ba.close()
