@@ -1143,8 +1143,10 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
       if (!speculative) { CKR(run_jacobian(c, false)); rep->n_jac += 1; }
       CKR(run_blocks(c, false));   // camera gradient / scaling of the new state; its norm is read at the next sync
       g_pending = true;
-      lam = lam * std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * ratio - 1.0, 3.0));
-      lam = std::min(std::max(lam, o.lambda_min), o.lambda_max);
+      // damping update from the gain ratio; thresholds shifted down because the residual is itself a
+      // squared distance, so good Gauss-Newton steps have ratios ~0.3-0.5 (same rule in the oracle)
+      const double fac = ratio >= 0.7 ? 1.0 / 3.0 : (ratio >= 0.4 ? 1.0 / 1.5 : (ratio >= 0.15 ? 1.0 : 2.0));
+      lam = std::min(std::max(lam * fac, o.lambda_min), o.lambda_max);
       nu = 2.0;
     } else {
       lam = std::min(lam * nu, o.lambda_max);

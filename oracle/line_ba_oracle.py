@@ -335,6 +335,21 @@ class LMOptions:
     f_scale: float = 1.0
 
 
+def damping_factor(ratio):
+    """Damping update after an ACCEPTED step, from the gain ratio rho = actual / predicted reduction.
+    The residual of this problem is itself a squared distance, so even good Gauss-Newton steps have
+    rho ~ 0.3-0.5; the classic thresholds are therefore shifted down a little:
+    rho >= 0.7 -> lambda/3, 0.4 <= rho < 0.7 -> lambda/1.5, 0.15 <= rho < 0.4 -> unchanged,
+    rho < 0.15 -> 2 lambda.  (Rejected steps: lambda *= nu, nu *= 2.)"""
+    if ratio >= 0.7:
+        return 1.0 / 3.0
+    if ratio >= 0.4:
+        return 1.0 / 1.5
+    if ratio >= 0.15:
+        return 1.0
+    return 2.0
+
+
 @dataclass
 class LMReport:
     iterations: int = 0
@@ -497,8 +512,7 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
             U, gc, V, gl = normal_equations(r, jc, jl, ci, li, nc, nl)
             Dc = update_scaling(Dc, U[:, idx, idx])
             Dl = update_scaling(Dl, V[:, idx, idx])
-            lam = lam * max(1.0 / 3.0, 1.0 - (2.0 * ratio - 1.0) ** 3)
-            lam = min(max(lam, opts.lambda_min), opts.lambda_max)
+            lam = min(max(lam * damping_factor(ratio), opts.lambda_min), opts.lambda_max)
             nu = 2.0
         else:
             lam = min(lam * nu, opts.lambda_max)

@@ -301,6 +301,26 @@ def test_p5_dropin_beats_reference_run(LineBA, capsys):
     assert 0.5 * float(res @ res) < ref_cost
 
 
+def test_p5_final_cost_vs_reference_on_every_fixture(LineBA, capsys):
+    """Default options on every fixture: the CUDA solver ends below the final cost of the reference's scipy
+    call as shipped; the cost of scipy with the analytic Jacobian at 15 Jacobian evaluations is printed
+    beside it (tests/golden/p5_costs.json)."""
+    import json
+    p5 = json.load(open(os.path.join(GOLDEN, "p5_costs.json")))["fixtures"]
+    lines = []
+    for name, ref in p5.items():
+        s = synth(12, 200, 5, seed=1) if name.startswith("synth") else load(name)[0]
+        ba = make_ctx(LineBA, s)
+        res = ba.lm_solve(s.camera_params, s.points_3d)
+        ba.close()
+        lines.append(f"[P5] {name:16s} init {res.cost_init:.3e}  ours {res.cost:.3e} ({res.iterations} it)  "
+                     f"reference as shipped {ref['as_shipped_cost']:.3e}  scipy+analytic J @15 {ref['analytic_cost']:.3e}")
+        assert abs(res.cost_init - ref["cost_init"]) <= 1e-9 * ref["cost_init"]
+        assert res.cost < ref["as_shipped_cost"], lines[-1]
+    with capsys.disabled():
+        print("\n" + "\n".join(lines))
+
+
 # ---------------------------------------------------------------- edge cases
 def test_unsorted_observations_give_identical_results(LineBA):
     s = synth(10, 150, 5, seed=7)

@@ -219,3 +219,16 @@ def test_robust_lm_downweights_outliers():
     good = np.setdiff1d(np.arange(s.n_obs), bad)
     assert rob[3].cost < rob[3].cost_init
     assert np.sum(rob[2][good] ** 2) < np.sum(lin[2][good] ** 2)   # inliers fit better with the robust loss
+
+
+def test_p5_oracle_lm_ends_below_the_reference_on_every_fixture():
+    """Default options (max_iter 50, ftol 1e-4): final cost below what the reference's scipy call reaches as
+    shipped (tests/golden/p5_costs.json, generated by tests/golden/make_p5_costs.py)."""
+    import json
+    from amuya_sfm_lines_beta_b200.scenes import scene_from_npz, make_synthetic_scene
+    p5 = json.load(open(os.path.join(GOLDEN, "p5_costs.json")))["fixtures"]
+    for name, ref in p5.items():
+        s = make_synthetic_scene(12, 200, 5, seed=1) if name.startswith("synth") else scene_from_npz(os.path.join(GOLDEN, name + ".npz"))
+        rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions())[3]
+        assert abs(rep.cost_init - ref["cost_init"]) <= 1e-9 * ref["cost_init"]
+        assert rep.cost < ref["as_shipped_cost"], (name, rep.cost, ref)
