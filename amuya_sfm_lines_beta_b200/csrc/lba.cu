@@ -138,6 +138,8 @@ struct lba_ctx {
   DBuf<GridBar> gridbar;
   DBuf<double> cg_partial;
   int cg_ctas = 1;
+  bool use_pdl = true;     // programmatic dependent launch between kernels (LBA_PDL=0|1|2, see lba_create)
+  int cam_threads = 128;   // CTA size of the one-CTA-per-camera kernels (128/256/512: enough threads to fill the GPU)
   DBuf<unsigned long long> gbits, gbits_new;
   DBuf<int> clamped;
   Scalars* h_scal = nullptr;   // pinned
@@ -187,11 +189,37 @@ struct lba_ctx {
   }
 };
 
-#define LAUNCH(ctx, cls, kern, grid, block, ...)                 \
-  do {                                                           \
-    (ctx)->pre(cls);                                             \
-    kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
-    (ctx)->post(cls);                                            \
+// Every kernel of this library starts with pdl_prologue(), so all of them may be launched with the
+// programmatic-stream-serialization attribute (off while profiling: the class events sit between launches).
+template <typename... KArgs, typename... Args>
+static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (c->use_pdl && !c->profiling) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+#define LAUNCH_DYN(ctx, cls, kern, grid, block, smem, ...)                      \
+  do {                                                                          \
+    (ctx)->pre(cls);                                                            \
+    launch_kernel((ctx), kern, dim3(grid), dim3(block), (smem), __VA_ARGS__);   \
+    (ctx)->post(cls);                                                           \
+  } while (0)
+#define LAUNCH(ctx, cls, kern, grid, block, ...) LAUNCH_DYN(ctx, cls, kern, grid, block, 0, __VA_ARGS__)
+
+// launch a camera-order kernel template with the CTA size chosen for this problem
+#define LAUNCH_CAM(ctx, cls, kern, grid, ...)                                        \
+  do {                                                                               \
+    if ((ctx)->cam_threads == 512) LAUNCH(ctx, cls, kern<512>, grid, 512, __VA_ARGS__);      \
+    else if ((ctx)->cam_threads == 256) LAUNCH(ctx, cls, kern<256>, grid, 256, __VA_ARGS__); \
+    else LAUNCH(ctx, cls, kern<128>, grid, 128, __VA_ARGS__);                        \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -235,6 +263,15 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaSetDevice(device));
   lba_ctx* c = new lba_ctx();
   c->device = device;
+  {  // LBA_PDL=0: plain launches; 1 (default): programmatic stream serialization, dependents released when the
+     // CTAs of a kernel exit (+6% LM it/s on config 4); 2: dependents triggered at kernel start (measured 12% slower:
+     // the parked CTAs of kernel N+1 take shared memory and L1 away from kernel N)
+    const char* e = getenv("LBA_PDL");
+    const int mode = e ? atoi(e) : 1;
+    c->use_pdl = mode > 0;
+    const int early = mode > 1;
+    CK(cudaMemcpyToSymbol(g_pdl_early_trigger, &early, sizeof(int)));
+  }
   cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
@@ -662,6 +699,15 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
+    {  // one CTA per camera: 128 threads measured best once there are >= 4 CTAs per SM (the kernels are
+       // HBM-bound on the jc stream; larger CTAs only serialise their reductions); few cameras -> wider CTAs
+      ctx->cam_threads = nc < 2 * ctx->n_sm ? 512 : (nc < 4 * ctx->n_sm ? 256 : 128);
+      if (const char* e = getenv("LBA_CAM_THREADS")) {  // tuning knob
+        const int v = atoi(e);
+        if (v == 128 || v == 256 || v == 512) ctx->cam_threads = v;
+      }
+      if (dbg) fprintf(stderr, "[lba_set_problem] camera-kernel CTA size %d\n", ctx->cam_threads);
+    }
     {  // CG vector kernels spin on a grid barrier: the grid must be co-resident
       int nb = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cg_step, kCgBlock, 0));
@@ -715,13 +761,6 @@ static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, dou
   a.loss = c->loss; a.f_scale = c->f_scale;
   return a;
 }
-
-#define LAUNCH_DYN(ctx, cls, kern, grid, block, smem, ...)            \
-  do {                                                                \
-    (ctx)->pre(cls);                                                  \
-    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
-    (ctx)->post(cls);                                                 \
-  } while (0)
 
 static int load_state(lba_ctx* c, const double* cams_api, const double* pts_api) {
   if (!c->have_problem) return fail(LBA_ERR_STATE, "lba_set_problem has not been called");
@@ -812,15 +851,15 @@ static int run_blocks(lba_ctx* c, bool full) {
     if (full) {
       // API path: the complete blocks, reduced into U | gc by a separate reduce
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
-      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-             (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21, pl);
+      LAUNCH_CAM(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+                 (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21, pl);
       CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     } else {
       // LM path: diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
       if (out != c->U.p) CK(cudaMemsetAsync(out, 0, n27 * 8, c->stream));   // k_cam_grad writes the diagonal only
-      LAUNCH(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out,
-             out + (size_t)c->nc * 21, pl);
+      LAUNCH_CAM(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out,
+                 out + (size_t)c->nc * 21, pl);
       CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     }
     LAUNCH(c, LBA_K_MISC, k_cam_post, cdiv((long long)c->nc * 6, 256), 256, c->nc, c->U.p, gc_of(c), c->gc.p, c->Dc.p,
@@ -860,8 +899,8 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
     double* out = reduce_target(c, kRgnM, c->Mpart.p, n27);
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, kCamThreads, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-           (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21, pl);
+    LAUNCH_CAM(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+               (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21, pl);
     CKR(reduce_finish(c, kRgnM, c->Mpart.p, n27));
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p, pl);
   }
@@ -887,7 +926,7 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
       // fused all-reduce with the peer transport: k_pcg_cam writes this rank's slot and signals,
       // k_cg_step waits and adds the slots of all ranks
       double* out = fused_link(c, kRgnQ, n6, c->qpart.p, &pl);
-      LAUNCH(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), kCamThreads, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
+      LAUNCH_CAM(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
       if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
     sp->ca.pl = pl;

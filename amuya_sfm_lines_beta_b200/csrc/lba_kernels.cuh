@@ -76,6 +76,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// Programmatic dependent launch: every kernel waits for its stream predecessor before touching global
+// memory, then lets its successor be scheduled, so at most one not-yet-started grid sits resident behind
+// the running one and the launch latency of kernel N+1 hides under kernel N.  A no-op for plain launches.
+__constant__ int g_pdl_early_trigger = 0;
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (g_pdl_early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -250,6 +258,7 @@ __device__ __forceinline__ double peer_sum(const PeerLink& pl, size_t e) {
 __global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, const double* __restrict__ n,
                                   const double* __restrict__ p0, const double* __restrict__ p1,
                                   double* __restrict__ cst) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
@@ -270,12 +279,14 @@ __global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, cons
 
 // (Nc,6) interleaved [w0,c0,w1,c1,w2,c2] <-> internal [w,c]
 __global__ void k_cams_from_api(int nc, const double* __restrict__ api, double* __restrict__ cams) {
+  pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nc * 6) return;
   const int c = t / 6, k = t % 6;  // k = 2*axis + {0: w, 1: centre}
   cams[c * 6 + (k & 1) * 3 + (k >> 1)] = api[t];
 }
 __global__ void k_cams_to_api(int nc, const double* __restrict__ cams, double* __restrict__ api) {
+  pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nc * 6) return;
   const int c = t / 6, k = t % 6;
@@ -284,6 +295,7 @@ __global__ void k_cams_to_api(int nc, const double* __restrict__ cams, double* _
 
 __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* __restrict__ recs,
                               double* __restrict__ Gm) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   CamRec rec;
@@ -303,6 +315,7 @@ __global__ void k_cam_prepare(int nc, const double* __restrict__ cams, CamRec* _
 __global__ void k_index_scan(int m, int nc, int nl, const long long* __restrict__ cam, const long long* __restrict__ line,
                              int* __restrict__ line_cnt, int* __restrict__ flags /* [0] bad cam, [1] bad line, [2] unsorted */,
                              int* __restrict__ keys /* optional: line as int, for the stable sort of unsorted input */) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const long long c = cam[i], l = line[i];
@@ -313,6 +326,7 @@ __global__ void k_index_scan(int m, int nc, int nl, const long long* __restrict_
   if (keys) keys[i] = (int)l;
 }
 __global__ void k_iota(int n, int* __restrict__ v) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
 }
@@ -321,6 +335,7 @@ __global__ void k_fill_slots(int m, const int* __restrict__ order, const long lo
                              const long long* __restrict__ line, const int* __restrict__ line_ptr,
                              const int* __restrict__ line_slot /* first slot of each line */, int* __restrict__ slot_src,
                              TileIdx* __restrict__ tidx) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int src = order ? order[i] : i;
@@ -333,6 +348,7 @@ __global__ void k_fill_slots(int m, const int* __restrict__ order, const long lo
 }
 // TileIdx records start as {meta from the host, ll = 0, cam = -1, pos = 0}
 __global__ void k_init_tidx(int ntiles, const TileMeta* __restrict__ meta, TileIdx* __restrict__ tidx) {
+  pdl_prologue();
   const int g = blockIdx.x, t = threadIdx.x;
   if (g >= ntiles) return;
   TileIdx& ti = tidx[g];
@@ -342,6 +358,7 @@ __global__ void k_init_tidx(int ntiles, const TileMeta* __restrict__ meta, TileI
 
 // ---- camera order on the device: stable radix sort of (camera, slot), then these two kernels ----
 __global__ void k_cam_keys(int Mp, int nc, const TileIdx* __restrict__ tidx, int* __restrict__ keys, int* __restrict__ vals) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int c = tidx[i / kTile].cam[i % kTile];
@@ -351,6 +368,7 @@ __global__ void k_cam_keys(int Mp, int nc, const TileIdx* __restrict__ tidx, int
 // sorted (key, slot) -> cam_pos[slot] = j, cam_ptr[c] = first j with key >= c
 __global__ void k_cam_index(int Mp, int m, int nc, const int* __restrict__ keys, const int* __restrict__ slots,
                             TileIdx* __restrict__ tidx, int* __restrict__ cam_ptr) {
+  pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mp) return;
   const int k = keys[j];
@@ -364,6 +382,7 @@ __global__ void k_cam_index(int Mp, int m, int nc, const int* __restrict__ keys,
 // point_wise_input (:235-243) integer expansion, in the caller's observation order.
 __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, const TileIdx* __restrict__ tidx,
                                      long long* __restrict__ cam_pt, long long* __restrict__ pt_idx) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
@@ -449,6 +468,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     for (int s = 0; s < S; ++s) mbar_init(&full[sub][s], 1);
     fence_barrier_init();
   }
+  pdl_prologue();
   if (TAB_SMEM) {
     const double2* src = reinterpret_cast<const double2*>(a.recs);
     double2* dst = reinterpret_cast<double2*>(smem);
@@ -661,6 +681,7 @@ struct ProjectArgs {
   double* proj;
 };
 __global__ void k_project(const ProjectArgs a) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.Mp) return;
   const int src = a.slot_src[i];
@@ -693,19 +714,21 @@ __global__ void k_project(const ProjectArgs a) {
 // One CTA per camera; 27 register accumulators per thread, warp-shuffle + smem reduce.
 // ---------------------------------------------------------------------------------
 // diag(U_c) and g_c only (all the LM loop needs from U): 12 accumulators instead of 27
-__global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict__ cam_ptr,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_cam_grad(const int* __restrict__ cam_ptr,
                                                            const int* __restrict__ cam_perm,
                                                            const double* __restrict__ jc, const double* __restrict__ r,
                                                            double* __restrict__ S, double* __restrict__ v,
                                                            const PeerLink pl) {
-  __shared__ double sm[kCamThreads / 32][12];
+  pdl_prologue();
+  __shared__ double sm[THREADS / 32][12];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
   double acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.0;
 #pragma unroll 4
-  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+  for (int j = j0 + threadIdx.x; j < j1; j += THREADS) {
     double x[6];
     load6(jc + (size_t)j * 6, x);
     const double b = __ldg(r + cam_perm[j]);
@@ -722,28 +745,30 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_grad(const int* __restrict_
   if (threadIdx.x < 12) {
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+    for (int q = 0; q < THREADS / 32; ++q) s += sm[q][threadIdx.x];
     if (threadIdx.x < 6) S[(size_t)c * 21 + sym_idx(threadIdx.x, threadIdx.x)] = s;
     else v[(size_t)c * 6 + threadIdx.x - 6] = s;
   }
   if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_post) adds the ranks' slots
 }
 
-__global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict__ cam_ptr,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ cam_ptr,
                                                             const int* __restrict__ cam_perm,
                                                             const double* __restrict__ jc,
                                                             const double* __restrict__ wa,
                                                             const double* __restrict__ wb,
                                                             double* __restrict__ S, double* __restrict__ v,
                                                             const PeerLink pl) {
-  __shared__ double sm[kCamThreads / 32][27];
+  pdl_prologue();
+  __shared__ double sm[THREADS / 32][27];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
 #pragma unroll 2
-  for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+  for (int j = j0 + threadIdx.x; j < j1; j += THREADS) {
     const int i = cam_perm[j];
     double x[6];
     load6(jc + (size_t)j * 6, x);
@@ -769,7 +794,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
   if (threadIdx.x < 27) {
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+    for (int q = 0; q < THREADS / 32; ++q) s += sm[q][threadIdx.x];
     if (threadIdx.x < 21) S[(size_t)c * 21 + threadIdx.x] = s;
     else v[(size_t)c * 6 + threadIdx.x - 21] = s;
   }
@@ -781,6 +806,7 @@ __global__ void __launch_bounds__(kCamThreads) k_cam_accum(const int* __restrict
 // the gradient inf-norm, in one launch
 __global__ void k_cam_post(int nc, const double* __restrict__ S, const double* __restrict__ gc_in, double* __restrict__ gc_out,
                            double* __restrict__ D, int first, unsigned long long* __restrict__ gbits, const PeerLink pl) {
+  pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   double mx = 0.0;
   if (pl.seq) peer_wait(pl);   // multi-GPU: S | gc live in the symmetric slots of all ranks
@@ -813,6 +839,7 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
                                                            double* __restrict__ Dl, const double* __restrict__ gl,
                                                            double* __restrict__ Vinv, double* __restrict__ y,
                                                            int* __restrict__ clamped, int scaling_mode) {
+  pdl_prologue();
   // the per-line records are AoS (21 / 6 / 22 doubles): move them through shared memory so that
   // global traffic is fully coalesced and each thread reads its own row conflict-free (odd strides)
   __shared__ double sV[kLfLines * kVinvStride];
@@ -873,6 +900,7 @@ __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const do
                                                      const double* __restrict__ Dc, const double* __restrict__ gc,
                                                      const double* __restrict__ bpart, double* __restrict__ Minv,
                                                      double* __restrict__ b, int* __restrict__ clamped, const PeerLink pl) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl.seq) peer_wait(pl);   // multi-GPU: Mpart | bpart live in the symmetric slots of all ranks
   if (c >= nc) return;
@@ -963,7 +991,6 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kTile / 32];
   __shared__ uint64_t full[kLpStages];
-  if (MODE == kModeMatvec && a.st->done) return;
   const int stage_bytes = lp_stage_bytes(a.lmax, MODE);
   double* ul = reinterpret_cast<double*>(smem + (size_t)kLpStages * stage_bytes);
   double* s_stg = ul + a.lmax * 6;  // [256][kLpRow]
@@ -976,6 +1003,8 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     for (int s = 0; s < kLpStages; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
+  pdl_prologue();
+  if (MODE == kModeMatvec && a.st->done) return;  // uniform over the grid
   __syncthreads();
 
   auto issue = [&](int it, int nl, int l0) {
@@ -1136,18 +1165,20 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
 }
 
 // Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}
-__global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int nc, const int* __restrict__ cam_ptr,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pcg_cam(int nc, const int* __restrict__ cam_ptr,
                                                           const int* __restrict__ cam_perm,
                                                           const double* __restrict__ jc, const double* __restrict__ w,
                                                           double* __restrict__ qpart, const CgState* __restrict__ st,
                                                           const PeerLink pl) {
-  __shared__ double sm[kCamThreads / 32][6];
+  pdl_prologue();
+  __shared__ double sm[THREADS / 32][6];
   if (st->done) return;
   for (int c = blockIdx.x; c < nc; c += gridDim.x) {
     const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
     double acc[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
-    for (int j = j0 + threadIdx.x; j < j1; j += kCamThreads) {
+    for (int j = j0 + threadIdx.x; j < j1; j += THREADS) {
       const double wi = __ldg(w + cam_perm[j]);
       double x[6];
       load6(jc + (size_t)j * 6, x);
@@ -1164,7 +1195,7 @@ __global__ void __launch_bounds__(kCamThreads) k_pcg_cam(int nc, const int* __re
     if (threadIdx.x < 6) {
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < kCamThreads / 32; ++q) s += sm[q][threadIdx.x];
+      for (int q = 0; q < THREADS / 32; ++q) s += sm[q][threadIdx.x];
       qpart[(size_t)c * 6 + threadIdx.x] = s;
     }
     __syncthreads();
@@ -1266,6 +1297,7 @@ __device__ __forceinline__ void group_table(const double* __restrict__ G, const 
 
 // x = 0, r = b, z = Minv r, p = z, rz0 = r.z ; table(p)
 __global__ void __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
+  pdl_prologue();
   __shared__ double red[kCgBlock / 32];
   const unsigned long long base = a.gb->base;
   const int gt = blockIdx.x * kCgBlock + threadIdx.x;
@@ -1297,6 +1329,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
 // gather table of the SOLUTION x is written instead of that of the next direction, ready for the
 // back-substitution pass.
 __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
+  pdl_prologue();
   __shared__ double red[kCgBlock / 32];
   if (a.st->done) return;   // uniform over the whole grid (written by the previous launch)
   const double rz = a.st->rz, rz0 = a.st->rz0;
@@ -1385,6 +1418,7 @@ __global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const doub
                                                                CamRec* __restrict__ recs_new, double* __restrict__ Gm_new,
                                                                double* __restrict__ partial, unsigned int* ticket,
                                                                double* __restrict__ out2 /* dc2, x2_cams */) {
+  pdl_prologue();
   __shared__ double red[kCamStepThreads / 32];
   double d2 = 0.0, x2 = 0.0;
   const int c = blockIdx.x * kCamStepThreads + threadIdx.x;
@@ -1412,6 +1446,7 @@ __global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const doub
 }
 
 __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  pdl_prologue();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = a[t] - b[t];
 }
@@ -1419,6 +1454,7 @@ __global__ void k_sub(size_t n, const double* __restrict__ a, const double* __re
 // slot order -> caller's observation order
 __global__ void k_slots_to_caller(int Mp, const int* __restrict__ slot_src, const double* __restrict__ src,
                                   double* __restrict__ dst) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int o = slot_src[i];
@@ -1429,6 +1465,7 @@ __global__ void k_slots_to_caller(int Mp, const int* __restrict__ slot_src, cons
 __global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, const TileIdx* __restrict__ tidx,
                                   const double* __restrict__ jl, const double* __restrict__ jc,
                                   double* __restrict__ jcam, double* __restrict__ jline) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
@@ -1460,6 +1497,7 @@ template <bool MAX_U64>
 __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int region, size_t slot_off, size_t n,
                                                       unsigned long long seq, const double* __restrict__ src,
                                                       double* __restrict__ dst) {
+  pdl_prologue();
   const int slot = (int)(seq & 1ULL);
   const int t = threadIdx.x;
   if (src) {
