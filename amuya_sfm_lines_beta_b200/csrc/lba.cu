@@ -160,6 +160,19 @@ struct lba_ctx {
   size_t rgn_off[kRgnCount] = {0}, rgn_cap[kRgnCount] = {0};   // in doubles (cap per slot)
   unsigned long long rgn_seq[kRgnCount] = {0};
 
+  // L2 residency: part of the two streams every PCG iteration re-reads (jl in line order, jc in camera order)
+  // is kept in a persisting L2 carve-out; win_* is the access-policy window of the NEXT launch (0 = none)
+  size_t l2_persist = 0, l2_max_window = 0;
+  const void* win_ptr = nullptr;
+  size_t win_bytes = 0;
+  float win_ratio = 0.f;
+  void window(const void* p, size_t bytes, size_t share) {
+    if (!l2_persist || !bytes) return;
+    win_ptr = p;
+    win_bytes = std::min(bytes, l2_max_window);
+    win_ratio = (float)std::min(1.0, (double)share / (double)win_bytes);
+  }
+
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
@@ -198,11 +211,25 @@ static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (c->use_pdl && !c->profiling) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (c->win_bytes) {
+    at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(c->win_ptr);
+    at[na].val.accessPolicyWindow.num_bytes = c->win_bytes;
+    at[na].val.accessPolicyWindow.hitRatio = c->win_ratio;
+    at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
+    c->win_bytes = 0;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = (c->use_pdl && !c->profiling) ? 1 : 0;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -220,6 +247,13 @@ static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, 
     if ((ctx)->cam_threads == 512) LAUNCH(ctx, cls, kern<512>, grid, 512, __VA_ARGS__);      \
     else if ((ctx)->cam_threads == 256) LAUNCH(ctx, cls, kern<256>, grid, 256, __VA_ARGS__); \
     else LAUNCH(ctx, cls, kern<128>, grid, 128, __VA_ARGS__);                        \
+  } while (0)
+// same for a camera-order kernel with one more (bool) template argument
+#define LAUNCH_CAM2(ctx, cls, kern, flag, grid, ...)                                         \
+  do {                                                                                       \
+    if ((ctx)->cam_threads == 512) LAUNCH(ctx, cls, (kern<512, flag>), grid, 512, __VA_ARGS__);      \
+    else if ((ctx)->cam_threads == 256) LAUNCH(ctx, cls, (kern<256, flag>), grid, 256, __VA_ARGS__); \
+    else LAUNCH(ctx, cls, (kern<128, flag>), grid, 128, __VA_ARGS__);                        \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -263,6 +297,17 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaSetDevice(device));
   lba_ctx* c = new lba_ctx();
   c->device = device;
+  if (const char* e = getenv("LBA_L2_PERSIST_MB")) {
+    int max_persist = 0, max_win = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    c->l2_persist = std::min((size_t)atoi(e) << 20, (size_t)max_persist);
+    c->l2_max_window = (size_t)max_win;
+    if (c->l2_persist) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist));
+    if (getenv("LBA_DEBUG_TIMING"))
+      fprintf(stderr, "[lba_create] L2 persisting carve-out %zu MB (max %d MB), max window %d MB\n", c->l2_persist >> 20,
+              max_persist >> 20, max_win >> 20);
+  }
   {  // LBA_PDL=0: plain launches; 1 (default): programmatic stream serialization, dependents released when the
      // CTAs of a kernel exit (+6% LM it/s on config 4); 2: dependents triggered at kernel start (measured 12% slower:
      // the parked CTAs of kernel N+1 take shared memory and L1 away from kernel N)
@@ -483,12 +528,12 @@ extern "C" int lba_comm_peer_attach(lba_ctx* ctx, const void* handles, int32_t r
   memset(&ctx->peer_args, 0, sizeof ctx->peer_args);
   for (int r = 0; r < world; ++r) ctx->peer_args.peer[r] = (unsigned char*)ctx->peer_mapped[r];
   ctx->peer_args.rank = rank; ctx->peer_args.world = world;
-  // regions: scalars (16), S*p partial (6 Nc), U|gc (27 Nc), M|b (27 Nc); two slots each
+  // regions: scalars (16), S*p partial (6 Nc), U|gc (27 Nc), M|b|diag U|gc (39 Nc); two slots each
   const size_t total = (ctx->peer_bytes - kPeerDataOff) / 8;
-  const size_t ncap = (total - 2 * 16) / (2 * (6 + 27 + 27));
+  const size_t ncap = (total - 2 * 16) / (2 * (6 + 27 + 39));
   ctx->peer_cams = ncap;
   size_t off = 0;
-  const size_t caps[kRgnCount] = {6 * ncap, 27 * ncap, 27 * ncap, 16};
+  const size_t caps[kRgnCount] = {6 * ncap, 27 * ncap, 39 * ncap, 16};
   for (int g = 0; g < kRgnCount; ++g) { ctx->rgn_off[g] = off; ctx->rgn_cap[g] = caps[g] & ~(size_t)1; off += 2 * ctx->rgn_cap[g]; ctx->rgn_seq[g] = 0; }
   ctx->peer_ready = true;
   return LBA_OK;
@@ -735,7 +780,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->V_new.alloc(NL * 21)); CKR(ctx->gl_new.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
   CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6));
   CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
-  CKR(ctx->Mpart.alloc(NC * 27)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
+  CKR(ctx->Mpart.alloc(NC * 39)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
   CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
   CKR(ctx->tab.alloc(NC * 6)); CKR(ctx->qpart.alloc(NC * 6));
   CKR(ctx->cost_partial.alloc(NG)); CKR(ctx->bs_partial.alloc(NG * 4));
@@ -851,8 +896,9 @@ static int run_blocks(lba_ctx* c, bool full) {
     if (full) {
       // API path: the complete blocks, reduced into U | gc by a separate reduce
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
-      LAUNCH_CAM(c, LBA_K_CAM_BLOCKS, k_cam_accum, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-                 (const double*)nullptr, c->r.p, out, out + (size_t)c->nc * 21, pl);
+      LAUNCH_CAM2(c, LBA_K_CAM_BLOCKS, k_cam_accum, false, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+                  (const double*)nullptr, c->r.p, (const double*)nullptr, out, out + (size_t)c->nc * 21,
+                  (double*)nullptr, c->nc, pl);
       CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     } else {
       // LM path: diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
@@ -879,7 +925,7 @@ struct SolvePlan {
 };
 
 // (1) Schur elimination set-up for damping lam and the first CG state
-static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, SolvePlan* sp) {
+static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, SolvePlan* sp, bool with_grad = false) {
   const int nc = c->nc, nl = c->nl;
   if (nl > 0) {
     LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, kLfLines), kLfLines, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode);
@@ -893,16 +939,29 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
   if (nc > 0) {
-    const size_t n27 = (size_t)nc * 27;
-    // 27 values per camera and a thread-per-camera consumer: a separate, massively parallel reduce
-    // kernel (zero-copy producer) beats fusing the peer loads into k_cam_finish
+    // 27 (39 with the gradient sums) values per camera and a thread-per-camera consumer: a separate,
+    // massively parallel reduce kernel (zero-copy producer) beats fusing the peer loads into k_cam_finish
+    const size_t nred = (size_t)nc * (with_grad ? 39 : 27);
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
-    double* out = reduce_target(c, kRgnM, c->Mpart.p, n27);
-    LAUNCH_CAM(c, LBA_K_CAM_PRECOND, k_cam_accum, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-               (const double*)c->wk.p, c->wr.p, out, out + (size_t)nc * 21, pl);
-    CKR(reduce_finish(c, kRgnM, c->Mpart.p, n27));
-    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c), c->Minv.p, c->b.p, c->clamped.p, pl);
+    double* out = reduce_target(c, kRgnM, c->Mpart.p, nred);
+    if (with_grad) {
+      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, true, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+                  (const double*)c->wk.p, c->wr.p, (const double*)c->r.p, out, out + (size_t)nc * 21,
+                  out + (size_t)nc * 27, nc, pl);
+    } else {
+      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, false, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
+                  (const double*)c->wk.p, c->wr.p, (const double*)nullptr, out, out + (size_t)nc * 21,
+                  (double*)nullptr, nc, pl);
+    }
+    CKR(reduce_finish(c, kRgnM, c->Mpart.p, nred));
+    LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c),
+           with_grad ? (const double*)(c->Mpart.p + (size_t)nc * 27) : (const double*)nullptr, c->gbits.p, c->Minv.p,
+           c->b.p, c->clamped.p, pl);
+    if (with_grad) {
+      c->have_scaling = true;
+      CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
+    }
   }
   CgArgs& ca = sp->ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
@@ -918,7 +977,10 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
 // (2) n more PCG iterations (kernels return at once when the device-side `done` flag is set)
 static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
   for (int q = 0; q < n && sp->issued < sp->ca.max_iter; ++q, ++sp->issued) {
-    if (c->ntiles > 0) LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
+    if (c->ntiles > 0) {
+      c->window(c->jl.p, (size_t)c->ntiles * 6 * kTile * 8, c->l2_persist / 2);
+      LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
+    }
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
     if (c->nc > 0) {
@@ -926,6 +988,7 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
       // fused all-reduce with the peer transport: k_pcg_cam writes this rank's slot and signals,
       // k_cg_step waits and adds the slots of all ranks
       double* out = fused_link(c, kRgnQ, n6, c->qpart.p, &pl);
+      c->window(c->jc.p, (size_t)c->m * 48, c->l2_persist / 2);
       LAUNCH_CAM(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
       if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
@@ -1132,7 +1195,8 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   while (it < o.max_iter) {
     if (!g_pending && g_norm < o.gtol) { status = 1; break; }
     SolvePlan sp;
-    CKR(solve_setup(c, lam, o.pcg_tol, o.pcg_max_iter, &sp));
+    // after an accepted step the camera gradient / scaling of the new state ride on the preconditioner pass
+    CKR(solve_setup(c, lam, o.pcg_tol, o.pcg_max_iter, &sp, g_pending));
     int launch = std::max(1, std::min(chunk_hint, o.pcg_max_iter));
     bool trial_done = false;
     while (true) {
@@ -1180,8 +1244,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
       accept_candidate(c, speculative);
       cost = cost_new;
       if (!speculative) { CKR(run_jacobian(c, false)); rep->n_jac += 1; }
-      CKR(run_blocks(c, false));   // camera gradient / scaling of the new state; its norm is read at the next sync
-      g_pending = true;
+      g_pending = true;   // camera gradient / scaling of the new state: computed by the next solve_setup, read at its sync
       // damping update from the gain ratio; thresholds shifted down because the residual is itself a
       // squared distance, so good Gauss-Newton steps have ratios ~0.3-0.5 (same rule in the oracle)
       const double fac = ratio >= 0.7 ? 1.0 / 3.0 : (ratio >= 0.4 ? 1.0 / 1.5 : (ratio >= 0.15 ? 1.0 : 2.0));
@@ -1196,7 +1259,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     else if (xtol_ok) status = 3;
     if (status) break;
   }
-  if (g_pending) { CKR(fetch_scalars(c)); g_norm = gnorm_host(c); }
+  if (g_pending) { CKR(run_blocks(c, false)); CKR(fetch_scalars(c)); g_norm = gnorm_host(c); }
   rep->iterations = it;
   rep->status = status;
   rep->cost = cost;

@@ -752,21 +752,27 @@ __global__ void __launch_bounds__(THREADS) k_cam_grad(const int* __restrict__ ca
   if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_post) adds the ranks' slots
 }
 
-template <int THREADS>
+// Per camera: S = sum a_i jc_i jc_i^T (21, a = 1 when wa is NULL) and v = sum b_i jc_i (6).  With GRAD the same
+// pass over jc also gives diag(U) = sum jc_i^2 (6) and g_c = sum r_i jc_i (6) at dg / dg + 6 nc, so that an LM
+// iteration reads the camera-order Jacobian once for the Schur blocks, the scaling and the gradient.
+template <int THREADS, bool GRAD>
 __global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ cam_ptr,
                                                             const int* __restrict__ cam_perm,
                                                             const double* __restrict__ jc,
                                                             const double* __restrict__ wa,
                                                             const double* __restrict__ wb,
+                                                            const double* __restrict__ rr,
                                                             double* __restrict__ S, double* __restrict__ v,
+                                                            double* __restrict__ dg, int nc,
                                                             const PeerLink pl) {
   pdl_prologue();
-  __shared__ double sm[THREADS / 32][27];
+  constexpr int NA = GRAD ? 39 : 27;
+  __shared__ double sm[THREADS / 32][NA];
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
-  double acc[27];
+  double acc[NA];
 #pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0;
 #pragma unroll 2
   for (int j = j0 + threadIdx.x; j < j1; j += THREADS) {
     const int i = cam_perm[j];
@@ -774,6 +780,7 @@ __global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ c
     load6(jc + (size_t)j * 6, x);
     const double a = wa ? __ldg(wa + i) : 1.0;
     const double b = __ldg(wb + i);
+    const double ri = GRAD ? __ldg(rr + i) : 0.0;
     int e = 0;
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
@@ -783,20 +790,29 @@ __global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ c
     }
 #pragma unroll
     for (int p = 0; p < 6; ++p) acc[21 + p] += b * x[p];
+    if (GRAD) {
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        acc[27 + p] += x[p] * x[p];
+        acc[33 + p] += ri * x[p];
+      }
+    }
   }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 27; ++k) {
+  for (int k = 0; k < NA; ++k) {
     const double s = warp_sum(acc[k]);
     if (l == 0) sm[w][k] = s;
   }
   __syncthreads();
-  if (threadIdx.x < 27) {
+  if (threadIdx.x < NA) {
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < THREADS / 32; ++q) s += sm[q][threadIdx.x];
     if (threadIdx.x < 21) S[(size_t)c * 21 + threadIdx.x] = s;
-    else v[(size_t)c * 6 + threadIdx.x - 21] = s;
+    else if (threadIdx.x < 27) v[(size_t)c * 6 + threadIdx.x - 21] = s;
+    else if (threadIdx.x < 33) dg[(size_t)c * 6 + threadIdx.x - 27] = s;
+    else dg[(size_t)nc * 6 + (size_t)c * 6 + threadIdx.x - 33] = s;
   }
   if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_finish) adds the ranks' slots
 }
@@ -895,20 +911,53 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
   }
 }
 
-// per camera: Minv = (lam Dc + Mpart)^-1 (block-Jacobi), b = -gc + bpart (Schur rhs)
+// per camera: Minv = (lam Dc + Mpart)^-1 (block-Jacobi), b = -gc + bpart (Schur rhs).  When the accumulation
+// pass also produced diag(U) | g_c (dg != NULL, all-reduced with Mpart | bpart) this kernel first does what
+// k_cam_post does for the stand-alone gradient pass: Marquardt scaling Dc = max(Dc, diag U) (zeros -> 1),
+// g_c, and the camera part of the gradient inf-norm.
 __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const double* __restrict__ Mpart,
-                                                     const double* __restrict__ Dc, const double* __restrict__ gc,
-                                                     const double* __restrict__ bpart, double* __restrict__ Minv,
+                                                     double* __restrict__ Dc, double* __restrict__ gc,
+                                                     const double* __restrict__ bpart, const double* __restrict__ dg,
+                                                     unsigned long long* __restrict__ gbits,
+                                                     double* __restrict__ Minv,
                                                      double* __restrict__ b, int* __restrict__ clamped, const PeerLink pl) {
   pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl.seq) peer_wait(pl);   // multi-GPU: Mpart | bpart live in the symmetric slots of all ranks
+  double mx = 0.0;
+  double D[6], g[6];
+  if (c < nc) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      D[k] = Dc[(size_t)c * 6 + k];
+      if (dg) {
+        double d = dg[(size_t)c * 6 + k];
+        if (d == 0.0) d = 1.0;
+        D[k] = fmax(D[k], d);
+        Dc[(size_t)c * 6 + k] = D[k];
+        g[k] = dg[(size_t)nc * 6 + (size_t)c * 6 + k];
+        gc[(size_t)c * 6 + k] = g[k];
+        const double ab = fabs(g[k]);
+        mx = (ab > mx || ab != ab) ? ab : mx;   // NaN propagates
+      } else {
+        g[k] = gc[(size_t)c * 6 + k];
+      }
+    }
+  }
+  if (dg) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+      mx = (other > mx || other != other) ? other : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && mx != 0.0) atomicMax(gbits, (unsigned long long)__double_as_longlong(mx));
+  }
   if (c >= nc) return;
   double S[21];
 #pragma unroll
   for (int e = 0; e < 21; ++e) S[e] = pl.seq ? peer_sum(pl, (size_t)c * 21 + e) : Mpart[(size_t)c * 21 + e];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * Dc[(size_t)c * 6 + k];
+  for (int k = 0; k < 6; ++k) S[sym_idx(k, k)] += lam * D[k];
   const int cl = spd6_inverse(S);
   if (cl) atomicAdd(clamped, cl);
 #pragma unroll
@@ -916,7 +965,7 @@ __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const do
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const double bp = pl.seq ? peer_sum(pl, (size_t)nc * 21 + (size_t)c * 6 + k) : bpart[(size_t)c * 6 + k];
-    b[(size_t)c * 6 + k] = bp - gc[(size_t)c * 6 + k];
+    b[(size_t)c * 6 + k] = bp - g[k];
   }
 }
 

@@ -275,7 +275,8 @@ def main():
         roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": read_traffic(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_OBS[dom] * m_local,
-                "algorithmic_bytes_per_obs": BYTES_PER_OBS[dom], "per_kernel": per_kernel, "time_shares": shares}
+                "algorithmic_bytes_per_obs": BYTES_PER_OBS[dom], "per_kernel": per_kernel, "time_shares": shares,
+                "class_avg_us": {k: round(v["ms"] / v["launches"] * 1e3, 2) for k, v in prof.items() if v["launches"]}}
 
     fp64_tf = ba.measure_fp64_peak()
     copy_gbs = ba.measure_copy_bandwidth(1 << 30)
