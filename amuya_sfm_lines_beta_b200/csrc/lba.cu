@@ -139,7 +139,8 @@ struct lba_ctx {
   DBuf<double> cg_partial;
   int cg_ctas = 1;
   bool use_pdl = true;     // programmatic dependent launch between kernels (LBA_PDL=0|1|2, see lba_create)
-  int cam_threads = 128;   // CTA size of the one-CTA-per-camera kernels (128/256/512: enough threads to fill the GPU)
+  // CTA sizes of the one-CTA-per-camera kernels: block sums (k_cam_accum / k_cam_grad) and the PCG product
+  int cam_threads = 128, pcg_threads = 128, cam_threads_sel = 128;
   DBuf<unsigned long long> gbits, gbits_new;
   DBuf<int> clamped;
   Scalars* h_scal = nullptr;   // pinned
@@ -244,16 +245,24 @@ static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, 
 // launch a camera-order kernel template with the CTA size chosen for this problem
 #define LAUNCH_CAM(ctx, cls, kern, grid, ...)                                        \
   do {                                                                               \
-    if ((ctx)->cam_threads == 512) LAUNCH(ctx, cls, kern<512>, grid, 512, __VA_ARGS__);      \
-    else if ((ctx)->cam_threads == 256) LAUNCH(ctx, cls, kern<256>, grid, 256, __VA_ARGS__); \
-    else LAUNCH(ctx, cls, kern<128>, grid, 128, __VA_ARGS__);                        \
+    switch ((ctx)->cam_threads_sel) {                                                \
+      case 512: LAUNCH(ctx, cls, kern<512>, grid, 512, __VA_ARGS__); break;          \
+      case 256: LAUNCH(ctx, cls, kern<256>, grid, 256, __VA_ARGS__); break;          \
+      case 64: LAUNCH(ctx, cls, kern<64>, grid, 64, __VA_ARGS__); break;             \
+      case 32: LAUNCH(ctx, cls, kern<32>, grid, 32, __VA_ARGS__); break;             \
+      default: LAUNCH(ctx, cls, kern<128>, grid, 128, __VA_ARGS__);                  \
+    }                                                                                \
   } while (0)
 // same for a camera-order kernel with one more (bool) template argument
 #define LAUNCH_CAM2(ctx, cls, kern, flag, grid, ...)                                         \
   do {                                                                                       \
-    if ((ctx)->cam_threads == 512) LAUNCH(ctx, cls, (kern<512, flag>), grid, 512, __VA_ARGS__);      \
-    else if ((ctx)->cam_threads == 256) LAUNCH(ctx, cls, (kern<256, flag>), grid, 256, __VA_ARGS__); \
-    else LAUNCH(ctx, cls, (kern<128, flag>), grid, 128, __VA_ARGS__);                        \
+    switch ((ctx)->cam_threads_sel) {                                                        \
+      case 512: LAUNCH(ctx, cls, (kern<512, flag>), grid, 512, __VA_ARGS__); break;          \
+      case 256: LAUNCH(ctx, cls, (kern<256, flag>), grid, 256, __VA_ARGS__); break;          \
+      case 64: LAUNCH(ctx, cls, (kern<64, flag>), grid, 64, __VA_ARGS__); break;             \
+      case 32: LAUNCH(ctx, cls, (kern<32, flag>), grid, 32, __VA_ARGS__); break;             \
+      default: LAUNCH(ctx, cls, (kern<128, flag>), grid, 128, __VA_ARGS__);                  \
+    }                                                                                        \
   } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -498,6 +507,20 @@ static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRed
   return LBA_OK;
 }
 static int allreduce_sum(lba_ctx* c, double* buf, size_t n) { return allreduce(c, buf, n, ncclDouble, ncclSum); }
+// the end-of-iteration scalars (sum) and, when `gbits` is given, the gradient inf-norm bits (max) in ONE exchange
+static int allreduce_scalars(lba_ctx* c, double* buf, size_t n, unsigned long long* gbits) {
+  if (c->world <= 1) return LBA_OK;
+  if (!gbits) return allreduce_sum(c, buf, n);
+  if (n > 8 || !peer_fits(c, kRgnS, 10)) {
+    CKR(allreduce_sum(c, buf, n));
+    return allreduce(c, gbits, 1, ncclUint64, ncclMax);
+  }
+  const unsigned long long seq = ++c->rgn_seq[kRgnS];
+  c->pre(LBA_K_COMM);
+  k_peer_reduce<false><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, buf, gbits);
+  c->post(LBA_K_COMM);
+  return LBA_OK;
+}
 
 extern "C" int lba_comm_peer_local(lba_ctx* ctx, void* handle64, int64_t bytes) {
   if (!ctx || !handle64 || bytes < 4096) return fail(LBA_ERR_ARG, "bad argument");
@@ -744,14 +767,22 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
-    {  // one CTA per camera: 128 threads measured best once there are >= 4 CTAs per SM (the kernels are
-       // HBM-bound on the jc stream; larger CTAs only serialise their reductions); few cameras -> wider CTAs
-      ctx->cam_threads = nc < 2 * ctx->n_sm ? 512 : (nc < 4 * ctx->n_sm ? 256 : 128);
-      if (const char* e = getenv("LBA_CAM_THREADS")) {  // tuning knob
-        const int v = atoi(e);
-        if (v == 128 || v == 256 || v == 512) ctx->cam_threads = v;
-      }
-      if (dbg) fprintf(stderr, "[lba_set_problem] camera-kernel CTA size %d\n", ctx->cam_threads);
+    {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
+       // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
+       // they get narrow CTAs (measured, accumulate + finish: 1000 cameras x 2000 obs 31 us at 64 threads vs 35 at 128;
+       // 8000 cameras x 250 obs 39 us at 32 threads vs 52 at 128)
+      ctx->pcg_threads = nc < 2 * ctx->n_sm ? 512 : (nc < 4 * ctx->n_sm ? 256 : 128);
+      const long long per_cam = nc > 0 ? m / nc : 0;
+      ctx->cam_threads = nc < 4 * ctx->n_sm ? ctx->pcg_threads : (per_cam >= 512 ? 64 : 32);
+      auto knob = [](const char* name, int* v) {
+        if (const char* e = getenv(name)) {
+          const int x = atoi(e);
+          if (x == 32 || x == 64 || x == 128 || x == 256 || x == 512) *v = x;
+        }
+      };
+      knob("LBA_CAM_THREADS", &ctx->cam_threads);
+      knob("LBA_PCG_THREADS", &ctx->pcg_threads);
+      if (dbg) fprintf(stderr, "[lba_set_problem] camera-kernel CTA sizes: sums %d, PCG %d\n", ctx->cam_threads, ctx->pcg_threads);
     }
     {  // CG vector kernels spin on a grid barrier: the grid must be co-resident
       int nb = 0;
@@ -896,6 +927,7 @@ static int run_blocks(lba_ctx* c, bool full) {
     if (full) {
       // API path: the complete blocks, reduced into U | gc by a separate reduce
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
+      c->cam_threads_sel = c->cam_threads;
       LAUNCH_CAM2(c, LBA_K_CAM_BLOCKS, k_cam_accum, false, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
                   (const double*)nullptr, c->r.p, (const double*)nullptr, out, out + (size_t)c->nc * 21,
                   (double*)nullptr, c->nc, pl);
@@ -904,6 +936,7 @@ static int run_blocks(lba_ctx* c, bool full) {
       // LM path: diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
       if (out != c->U.p) CK(cudaMemsetAsync(out, 0, n27 * 8, c->stream));   // k_cam_grad writes the diagonal only
+      c->cam_threads_sel = c->cam_threads;
       LAUNCH_CAM(c, LBA_K_CAM_BLOCKS, k_cam_grad, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->r.p, out,
                  out + (size_t)c->nc * 21, pl);
       CKR(reduce_finish(c, kRgnU, c->U.p, n27));
@@ -945,6 +978,7 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
     double* out = reduce_target(c, kRgnM, c->Mpart.p, nred);
+    c->cam_threads_sel = c->cam_threads;
     if (with_grad) {
       LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, true, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
                   (const double*)c->wk.p, c->wr.p, (const double*)c->r.p, out, out + (size_t)nc * 21,
@@ -958,10 +992,7 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c),
            with_grad ? (const double*)(c->Mpart.p + (size_t)nc * 27) : (const double*)nullptr, c->gbits.p, c->Minv.p,
            c->b.p, c->clamped.p, pl);
-    if (with_grad) {
-      c->have_scaling = true;
-      CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
-    }
+    if (with_grad) c->have_scaling = true;   // the caller all-reduces gbits (max) together with its next scalars
   }
   CgArgs& ca = sp->ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
@@ -989,6 +1020,7 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
       // k_cg_step waits and adds the slots of all ranks
       double* out = fused_link(c, kRgnQ, n6, c->qpart.p, &pl);
       c->window(c->jc.p, (size_t)c->m * 48, c->l2_persist / 2);
+      c->cam_threads_sel = c->pcg_threads;
       LAUNCH_CAM(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
       if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
@@ -1198,12 +1230,15 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     // after an accepted step the camera gradient / scaling of the new state ride on the preconditioner pass
     CKR(solve_setup(c, lam, o.pcg_tol, o.pcg_max_iter, &sp, g_pending));
     int launch = std::max(1, std::min(chunk_hint, o.pcg_max_iter));
-    bool trial_done = false;
+    bool trial_done = false, g_reduced = false;
     while (true) {
       CKR(solve_iterate(c, &sp, launch));
       CKR(solve_finish(c, &sp));
       if (speculative) CKR(run_jacobian(c, true)); else CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
-      CKR(allreduce_sum(c, &c->scal.p->cost, 5));  // cost, rjd, jd2, dl2, x2_lines are contiguous
+      // cost, rjd, jd2, dl2, x2_lines are contiguous; the gradient norm of the state this solve started from
+      // (camera part written by its set-up) goes out in the same exchange, once
+      CKR(allreduce_scalars(c, &c->scal.p->cost, 5, (g_pending && !g_reduced) ? c->gbits.p : nullptr));
+      g_reduced = true;
       CKR(fetch_scalars(c));
       trial_done = c->h_cgst->done || sp.issued >= o.pcg_max_iter;
       if (trial_done) break;

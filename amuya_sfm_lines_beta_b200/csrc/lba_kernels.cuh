@@ -805,14 +805,14 @@ __global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ c
     if (l == 0) sm[w][k] = s;
   }
   __syncthreads();
-  if (threadIdx.x < NA) {
+  for (int k = threadIdx.x; k < NA; k += THREADS) {
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < THREADS / 32; ++q) s += sm[q][threadIdx.x];
-    if (threadIdx.x < 21) S[(size_t)c * 21 + threadIdx.x] = s;
-    else if (threadIdx.x < 27) v[(size_t)c * 6 + threadIdx.x - 21] = s;
-    else if (threadIdx.x < 33) dg[(size_t)c * 6 + threadIdx.x - 27] = s;
-    else dg[(size_t)nc * 6 + (size_t)c * 6 + threadIdx.x - 33] = s;
+    for (int q = 0; q < THREADS / 32; ++q) s += sm[q][k];
+    if (k < 21) S[(size_t)c * 21 + k] = s;
+    else if (k < 27) v[(size_t)c * 6 + k - 21] = s;
+    else if (k < 33) dg[(size_t)c * 6 + k - 27] = s;
+    else dg[(size_t)nc * 6 + (size_t)c * 6 + k - 33] = s;
   }
   if (pl.seq) peer_signal_last_cta(pl);   // fused all-reduce: the consumer (k_cam_finish) adds the ranks' slots
 }
@@ -1545,13 +1545,16 @@ __global__ void k_export_jacobian(int Mp, const int* __restrict__ slot_src, cons
 template <bool MAX_U64>
 __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int region, size_t slot_off, size_t n,
                                                       unsigned long long seq, const double* __restrict__ src,
-                                                      double* __restrict__ dst) {
+                                                      double* __restrict__ dst,
+                                                      unsigned long long* __restrict__ maxp = nullptr) {
   pdl_prologue();
   const int slot = (int)(seq & 1ULL);
   const int t = threadIdx.x;
+  constexpr int kMaxAt = 8;   // maxp (single-CTA mode, n <= 8): one more word, max-reduced as u64, rides at this index
   if (src) {
     double* mine = reinterpret_cast<double*>(pa.peer[pa.rank] + kPeerDataOff) + slot_off;
     for (size_t i = t; i < n; i += blockDim.x) mine[i] = src[i];
+    if (maxp && t == 0) mine[kMaxAt] = __longlong_as_double((long long)*maxp);
     __syncthreads();
   }
   const int fidx = (region * 2 + slot) * kMaxPeers;
@@ -1587,6 +1590,15 @@ __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int regi
     }
     if (2 * i2 + 1 < n) *reinterpret_cast<double2*>(dst + 2 * i2) = acc;
     else dst[2 * i2] = acc.x;
+  }
+  if (maxp && blockIdx.x == 0 && t == 0) {
+    unsigned long long m = 0ULL;
+    for (int r = 0; r < pa.world; ++r) {
+      const double2 v = ld_relaxed_sys2(reinterpret_cast<const double*>(pa.peer[r] + kPeerDataOff) + slot_off + kMaxAt);
+      const unsigned long long a = (unsigned long long)__double_as_longlong(v.x);
+      m = a > m ? a : m;
+    }
+    *maxp = m;
   }
 }
 

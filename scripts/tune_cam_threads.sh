@@ -1,10 +1,7 @@
-for t in 128 256 512; do
+#!/bin/bash
+# usage: scripts/tune_cam_threads.sh "32 64 128" [bench args] -- sweep the CTA size of the per-camera block-sum kernels
+sizes=$1; shift
+for t in $sizes; do
   echo "== LBA_CAM_THREADS=$t"
-  LBA_CAM_THREADS=$t python bench.py --no-cpu-baseline --steps 20 --warmup 3 | python -c "
-import json,sys
-d=json.loads(sys.stdin.readlines()[-1])
-print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1))
-print(d['roofline']['time_shares'])
-print({k:v['avg_us'] for k,v in d['roofline']['per_kernel'].items()})
-"
+  LBA_CAM_THREADS=$t bash scripts/bench_shares.sh "$@" | grep -v "^shares\|^per_kernel"
 done
