@@ -161,6 +161,10 @@ struct lba_ctx {
   size_t rgn_off[kRgnCount] = {0}, rgn_cap[kRgnCount] = {0};   // in doubles (cap per slot)
   unsigned long long rgn_seq[kRgnCount] = {0};
 
+  // second stream + event: the 72 B/observation constants cross PCIe while the index arrays are processed
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done = nullptr;
+
   // L2 residency: part of the two streams every PCG iteration re-reads (jl in line order, jc in camera order)
   // is kept in a persisting L2 carve-out; win_* is the access-policy window of the NEXT launch (0 = none)
   size_t l2_persist = 0, l2_max_window = 0;
@@ -331,6 +335,8 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   c->own_stream = true;
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_scal, sizeof(Scalars)));
   CK(cudaMallocHost(&c->h_cgst, sizeof(CgState)));
   CK(cudaMallocHost(&c->h_gbits, sizeof(unsigned long long)));
@@ -381,6 +387,8 @@ extern "C" int lba_destroy(lba_ctx* ctx) {
   if (ctx->h_gbits) cudaFreeHost(ctx->h_gbits);
   if (ctx->h_clamped) cudaFreeHost(ctx->h_clamped);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -607,6 +615,27 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     if (is_device_ptr(line_idx)) line_dev = (const long long*)line_idx;
     else CK(cudaMemcpyAsync(d_line, line_idx, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
+  // the observation constants (n, p0, p1: 72 B per observation, the bulk of the input) start crossing PCIe now,
+  // on the copy stream, behind the index arrays; k_setup_constants waits for them with an event
+  const double* cst_src[3] = {n, p0, p1};
+  const double* cst_dev[3] = {n, p0, p1};
+  // whatever way this function returns, the caller's arrays are no longer being read
+  struct CopyGuard { cudaStream_t s; ~CopyGuard() { cudaStreamSynchronize(s); } } copy_guard{ctx->copy_stream};
+  if (m > 0) {
+    size_t need = 0;
+    for (int k = 0; k < 3; ++k) if (!is_device_ptr(cst_src[k])) need += (size_t)3 * m;
+    CKR(ctx->h2d_stage.alloc(need));
+    CK(cudaEventRecord(ctx->copy_done, ctx->stream));            // index copies first on the link
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
+    size_t off = 0;
+    for (int k = 0; k < 3; ++k) {
+      if (is_device_ptr(cst_src[k])) continue;
+      CK(cudaMemcpyAsync(ctx->h2d_stage.p + off, cst_src[k], (size_t)3 * m * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      cst_dev[k] = ctx->h2d_stage.p + off;
+      off += (size_t)3 * m;
+    }
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  }
   CKR(ctx->line_tmp.alloc((size_t)3 * nl + 8));   // line_cnt | line_ptr | line_slot
   int* d_line_cnt = ctx->line_tmp.p; int* d_line_ptr = d_line_cnt + nl + 1; int* d_line_slot = d_line_ptr + nl + 1;
   int* d_flags = d_line_slot + nl + 1;
@@ -702,20 +731,8 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   // observation constants: AoS (m,3) -> SoA over slots, m_e = n x p_e
   CKR(ctx->cst.alloc((size_t)9 * Mp));
   if (m > 0) {
-    const double* src[3] = {n, p0, p1};
-    const double* dev[3];
-    size_t need = 0;
-    for (int k = 0; k < 3; ++k) if (!is_device_ptr(src[k])) need += (size_t)3 * m;
-    CKR(ctx->h2d_stage.alloc(need));
-    lap("staging alloc");
-    size_t off = 0;
-    for (int k = 0; k < 3; ++k) {
-      if (is_device_ptr(src[k])) { dev[k] = src[k]; continue; }
-      CK(cudaMemcpyAsync(ctx->h2d_stage.p + off, src[k], (size_t)3 * m * 8, cudaMemcpyHostToDevice, ctx->stream));
-      dev[k] = ctx->h2d_stage.p + off;
-      off += (size_t)3 * m;
-    }
-    LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(Mp, 256), 256, Mp, ctx->slot_src.p, dev[0], dev[1], dev[2], ctx->cst.p);
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    LAUNCH(ctx, LBA_K_MISC, k_setup_constants, cdiv(Mp, 256), 256, Mp, ctx->slot_src.p, cst_dev[0], cst_dev[1], cst_dev[2], ctx->cst.p);
     CK(cudaStreamSynchronize(ctx->stream));  // the host vectors (tile table, line offsets) go out of scope
   } else {
     CK(cudaStreamSynchronize(ctx->stream));
