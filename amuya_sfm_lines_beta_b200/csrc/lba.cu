@@ -14,6 +14,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -143,8 +144,12 @@ struct lba_ctx {
   int cam_threads = 128, pcg_threads = 128, cam_threads_sel = 128;
   DBuf<unsigned long long> gbits, gbits_new;
   DBuf<int> clamped;
-  Scalars* h_scal = nullptr;   // pinned
-  CgState* h_cgst = nullptr;   // pinned
+  // pinned, device-mapped mirror of the per-iteration scalars (written by k_publish); h_* point into it
+  HostMirror* h_mirror = nullptr;
+  HostMirror* d_mirror = nullptr;   // the same memory through the device's address
+  unsigned long long publish_seq = 0;
+  Scalars* h_scal = nullptr;
+  CgState* h_cgst = nullptr;
   unsigned long long* h_gbits = nullptr;
   int* h_clamped = nullptr;
 
@@ -337,10 +342,11 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaEventCreate(&c->ev1));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
-  CK(cudaMallocHost(&c->h_scal, sizeof(Scalars)));
-  CK(cudaMallocHost(&c->h_cgst, sizeof(CgState)));
-  CK(cudaMallocHost(&c->h_gbits, sizeof(unsigned long long)));
-  CK(cudaMallocHost(&c->h_clamped, sizeof(int)));
+  CK(cudaHostAlloc(&c->h_mirror, sizeof(HostMirror), cudaHostAllocMapped));
+  memset(c->h_mirror, 0, sizeof(HostMirror));
+  CK(cudaHostGetDevicePointer(&c->d_mirror, c->h_mirror, 0));
+  c->h_scal = &c->h_mirror->scal; c->h_cgst = &c->h_mirror->cg;
+  c->h_gbits = &c->h_mirror->gbits; c->h_clamped = &c->h_mirror->clamped;
   CKR(c->scal.alloc(1));
   CKR(c->cgst.alloc(1));
   CKR(c->gridbar.alloc(1));
@@ -382,10 +388,7 @@ extern "C" int lba_destroy(lba_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   lba_comm_destroy(ctx);
-  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
-  if (ctx->h_cgst) cudaFreeHost(ctx->h_cgst);
-  if (ctx->h_gbits) cudaFreeHost(ctx->h_gbits);
-  if (ctx->h_clamped) cudaFreeHost(ctx->h_clamped);
+  if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1044,7 +1047,6 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
     sp->ca.pl = pl;
     LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
   }
-  CK(cudaMemcpyAsync(c->h_cgst, c->cgst.p, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
   return LBA_OK;
 }
 
@@ -1064,6 +1066,8 @@ static int solve_finish(lba_ctx* c, SolvePlan* sp) {
   return LBA_OK;
 }
 
+static int fetch_scalars(lba_ctx* c);
+
 // the three pieces with a host check of the CG flag in between (stand-alone lba_schur_solve)
 static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
                      int* breakdown_out) {
@@ -1072,7 +1076,7 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
   while (true) {
     CKR(solve_iterate(c, &sp, chunk));
-    CK(cudaStreamSynchronize(c->stream));
+    CKR(fetch_scalars(c));
     if (c->h_cgst->done || sp.issued >= pcg_max_iter) break;
     chunk = 4;
   }
@@ -1082,11 +1086,28 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   return solve_finish(c, &sp);
 }
 
+// The host's one look per iteration at the device scalars (LM scalars, CG state, gradient-norm bits, clamp count):
+// k_publish writes them into mapped pinned memory followed by a sequence number; the host spins on that word
+// and only falls back to the stream when the device reports an error.
 static int fetch_scalars(lba_ctx* c) {
-  CK(cudaMemcpyAsync(c->h_scal, c->scal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->h_gbits, c->gbits.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(c->h_clamped, c->clamped.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  const unsigned long long seq = ++c->publish_seq;
+  LAUNCH(c, LBA_K_MISC, k_publish, 1, 32, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p,
+         (const unsigned long long*)c->gbits.p, (const int*)c->clamped.p, c->d_mirror, seq);
+  volatile unsigned long long* flag = &c->h_mirror->seq;
+  for (unsigned spins = 0; *flag != seq; ++spins) {
+    if ((spins & 0x3ff) == 0x3ff) {
+      const cudaError_t e = cudaStreamQuery(c->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return fail(LBA_ERR_CUDA, "device error while waiting for the iteration scalars: %s", cudaGetErrorString(e));
+      if (e == cudaSuccess && *flag != seq) {   // stream drained: the write has landed by now
+        CK(cudaStreamSynchronize(c->stream));
+        break;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   if (c->launch_err) return LBA_ERR_CUDA;
   return LBA_OK;
 }

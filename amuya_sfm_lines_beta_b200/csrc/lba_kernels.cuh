@@ -1459,6 +1459,29 @@ struct Scalars {            // device-resident LM scalars, copied to the host on
   int clamped, pad;
 };
 
+// What the host reads once per LM iteration, in pinned host memory the device writes directly: one tiny
+// kernel posts the values and then a sequence number the host spins on (no copy-engine round trips).
+struct HostMirror {
+  Scalars scal;
+  CgState cg;
+  unsigned long long gbits;
+  int clamped, pad;
+  unsigned long long seq;
+};
+__global__ void k_publish(const Scalars* __restrict__ s, const CgState* __restrict__ cg,
+                          const unsigned long long* __restrict__ gbits, const int* __restrict__ clamped,
+                          HostMirror* __restrict__ h, unsigned long long seq) {
+  pdl_prologue();
+  if (threadIdx.x == 0) {
+    h->scal = *s;
+    h->cg = *cg;
+    h->gbits = *gbits;
+    h->clamped = *clamped;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&h->seq) = seq;
+  }
+}
+
 // cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms
 // (grid-wide sums by the last CTA, fixed order).
 constexpr int kCamStepThreads = 128;
