@@ -165,6 +165,11 @@ struct lba_ctx {
   size_t peer_cams = 0;                     // camera capacity of the per-camera regions
   size_t rgn_off[kRgnCount] = {0}, rgn_cap[kRgnCount] = {0};   // in doubles (cap per slot)
   unsigned long long rgn_seq[kRgnCount] = {0};
+  // two-phase (reduce-scatter + all-gather) peer reduce from this many ranks / doubles on;
+  // LBA_PEER_TWO_PHASE_MIN=<doubles> overrides the size and drops the rank threshold to 2 (tests), -1 disables
+  int peer_rs_world = 4;
+  size_t peer_rs_min = 16384;
+  DBuf<unsigned long long> peer_trace;   // LBA_PEER_TRACE: device-side wait/total times of the exchanges
 
   // second stream + event: the 72 B/observation constants cross PCIe while the index arrays are processed
   cudaStream_t copy_stream = nullptr;
@@ -366,6 +371,19 @@ extern "C" int lba_create(int device, lba_ctx** out) {
 extern "C" int lba_comm_destroy(lba_ctx* ctx) {
   if (ctx && ctx->peer_local) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->peer_trace.p) {
+      unsigned long long h[32];
+      cudaMemcpy(h, ctx->peer_trace.p, sizeof h, cudaMemcpyDeviceToHost);
+      static const char* nm[kRgnCount] = {"S*p (unfused)", "U|gc", "M|b|diag|gc", "scalars", "(results)"};
+      for (int g = 0; g < kRgnCount; ++g)
+        if (h[g * 4])
+          fprintf(stderr, "[lba peer trace r%d] %-14s %6llu calls: wait %7.2f us, total %7.2f us per call\n", ctx->rank, nm[g],
+                  h[g * 4], h[g * 4 + 1] * 1e-3 / h[g * 4], h[g * 4 + 2] * 1e-3 / h[g * 4]);
+      if (h[24])
+        fprintf(stderr, "[lba peer trace r%d] %-14s %6llu calls: wait %7.2f us per call\n", ctx->rank, "S*p (fused)", h[24],
+                h[25] * 1e-3 / h[24]);
+      ctx->peer_args.trace = nullptr;
+    }
     for (int r = 0; r < kMaxPeers; ++r)
       if (ctx->peer_mapped[r] && ctx->peer_mapped[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     cudaFree(ctx->peer_local);
@@ -497,9 +515,18 @@ static int reduce_finish(lba_ctx* c, int region, double* local, size_t n) {
   if (!peer_fits(c, region, n)) return nccl_allreduce(c, local, n, ncclDouble, ncclSum);
   const unsigned long long seq = ++c->rgn_seq[region];
   const int grid = (int)std::max<size_t>(1, std::min<size_t>(32, (n / 2 + 511) / 512));
+  if (c->world >= c->peer_rs_world && n >= c->peer_rs_min && n <= c->rgn_cap[kRgnR]) {
+    // large exchange, many ranks: reduce-scatter + all-gather through the result region
+    const unsigned long long rseq = ++c->rgn_seq[kRgnR];
+    c->pre(LBA_K_COMM);
+    launch_kernel(c, k_peer_reduce_rs, dim3(grid), dim3(512), 0, c->peer_args, region, peer_slot_off(c, region, seq),
+                  peer_slot_off(c, kRgnR, rseq), n, seq, rseq, local, c->tickets.p + 4);
+    c->post(LBA_K_COMM);
+    return LBA_OK;
+  }
   c->pre(LBA_K_COMM);
-  k_peer_reduce<false><<<grid, 512, 0, c->stream>>>(c->peer_args, region, peer_slot_off(c, region, seq), n, seq,
-                                                    (const double*)nullptr, local);
+  launch_kernel(c, k_peer_reduce<false>, dim3(grid), dim3(512), 0, c->peer_args, region, peer_slot_off(c, region, seq), n, seq,
+                (const double*)nullptr, local, (unsigned long long*)nullptr);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -511,9 +538,11 @@ static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRed
   const unsigned long long seq = ++c->rgn_seq[kRgnS];
   c->pre(LBA_K_COMM);
   if (op == ncclMax)
-    k_peer_reduce<true><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, (double*)buf);
+    launch_kernel(c, k_peer_reduce<true>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
+                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr);
   else
-    k_peer_reduce<false><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, (double*)buf);
+    launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
+                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -528,7 +557,8 @@ static int allreduce_scalars(lba_ctx* c, double* buf, size_t n, unsigned long lo
   }
   const unsigned long long seq = ++c->rgn_seq[kRgnS];
   c->pre(LBA_K_COMM);
-  k_peer_reduce<false><<<1, 512, 0, c->stream>>>(c->peer_args, kRgnS, peer_slot_off(c, kRgnS, seq), n, seq, (const double*)buf, buf, gbits);
+  launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
+                (const double*)buf, buf, gbits);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -562,12 +592,23 @@ extern "C" int lba_comm_peer_attach(lba_ctx* ctx, const void* handles, int32_t r
   memset(&ctx->peer_args, 0, sizeof ctx->peer_args);
   for (int r = 0; r < world; ++r) ctx->peer_args.peer[r] = (unsigned char*)ctx->peer_mapped[r];
   ctx->peer_args.rank = rank; ctx->peer_args.world = world;
-  // regions: scalars (16), S*p partial (6 Nc), U|gc (27 Nc), M|b|diag U|gc (39 Nc); two slots each
+  if (const char* e = getenv("LBA_PEER_TWO_PHASE_MIN")) {
+    const long long v = atoll(e);
+    if (v < 0) ctx->peer_rs_world = kMaxPeers + 1;
+    else { ctx->peer_rs_world = 2; ctx->peer_rs_min = (size_t)v; }
+  }
+  if (getenv("LBA_PEER_TRACE")) {
+    CKR(ctx->peer_trace.alloc(32));
+    CK(cudaMemset(ctx->peer_trace.p, 0, 32 * 8));
+    ctx->peer_args.trace = ctx->peer_trace.p;
+  }
+  // regions: scalars (16), S*p partial (6 Nc), U|gc (27 Nc), M|b|diag U|gc (39 Nc), two-phase results (39 Nc);
+  // two slots each
   const size_t total = (ctx->peer_bytes - kPeerDataOff) / 8;
-  const size_t ncap = (total - 2 * 16) / (2 * (6 + 27 + 39));
+  const size_t ncap = (total - 2 * 16) / (2 * (6 + 27 + 39 + 39));
   ctx->peer_cams = ncap;
   size_t off = 0;
-  const size_t caps[kRgnCount] = {6 * ncap, 27 * ncap, 39 * ncap, 16};
+  const size_t caps[kRgnCount] = {6 * ncap, 27 * ncap, 39 * ncap, 16, 39 * ncap};
   for (int g = 0; g < kRgnCount; ++g) { ctx->rgn_off[g] = off; ctx->rgn_cap[g] = caps[g] & ~(size_t)1; off += 2 * ctx->rgn_cap[g]; ctx->rgn_seq[g] = 0; }
   ctx->peer_ready = true;
   return LBA_OK;

@@ -176,13 +176,19 @@ __device__ __forceinline__ void load6(const double* __restrict__ p, double v[6])
 
 // ---- NVLink peer-memory primitives (see the all-reduce section near the end of this file) ----------
 constexpr int kMaxPeers = 8;
-enum { kRgnQ = 0, kRgnU, kRgnM, kRgnS, kRgnCount };
-constexpr int kPeerDataOff = 1024;   // flags: kRgnCount*2*kMaxPeers*8 = 512 B
+enum { kRgnQ = 0, kRgnU, kRgnM, kRgnS, kRgnR, kRgnCount };   // kRgnR: results of the two-phase reduce
+constexpr int kPeerDataOff = 1024;   // flags: kRgnCount*2*kMaxPeers*8 = 640 B
 
 struct PeerArgs {
   unsigned char* peer[kMaxPeers];   // peer[r] = base of rank r's symmetric buffer as mapped here
   int rank, world;
+  unsigned long long* trace;        // optional (LBA_PEER_TRACE): per exchange type {calls, ns waiting for peers, ns total}
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -1388,7 +1394,14 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
   const int k = gt & 7;
   const int groups = gridDim.x * kCgBlock / 8;
   const bool fused = a.pl.seq != 0ULL;
+  const bool tracing = fused && a.pl.pa.trace != nullptr && gt == 0;
+  unsigned long long tr0 = 0;
+  if (tracing) tr0 = global_ns();
   if (fused) peer_wait(a.pl);   // every rank's partial S p is complete
+  if (tracing) {
+    atomicAdd(a.pl.pa.trace + 24, 1ULL);
+    atomicAdd(a.pl.pa.trace + 25, global_ns() - tr0);
+  }
   double acc = 0.0;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
     const int c = c0 + (gt >> 3);
@@ -1581,6 +1594,9 @@ __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int regi
     __syncthreads();
   }
   const int fidx = (region * 2 + slot) * kMaxPeers;
+  const bool tracing = pa.trace != nullptr && blockIdx.x == 0 && t == 0;
+  unsigned long long tr0 = 0, tr1 = 0;
+  if (tracing) tr0 = global_ns();
   if (blockIdx.x == 0 && t < pa.world)
     st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + fidx + pa.rank, seq);
   if (t < pa.world) {
@@ -1588,6 +1604,7 @@ __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int regi
     while (ld_acquire_sys(f) < seq) { }
   }
   __syncthreads();
+  if (tracing) tr1 = global_ns();
   const size_t gsz = (size_t)gridDim.x * blockDim.x;
   for (size_t i2 = (size_t)blockIdx.x * blockDim.x + t; 2 * i2 < n; i2 += gsz) {
     double2 v[kMaxPeers];
@@ -1622,6 +1639,80 @@ __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int regi
       m = a > m ? a : m;
     }
     *maxp = m;
+  }
+  if (tracing) {
+    atomicAdd(pa.trace + region * 4 + 0, 1ULL);
+    atomicAdd(pa.trace + region * 4 + 1, tr1 - tr0);
+    atomicAdd(pa.trace + region * 4 + 2, global_ns() - tr0);
+  }
+}
+
+// Two-phase variant for the large per-camera exchanges at >= 4 ranks (reduce-scatter + all-gather over peer
+// memory): rank r sums only its 1/W slice of the elements (reading W-1 remote slices instead of W-1 whole
+// slots), stores the sums into the result slot of EVERY rank (remote stores are posted), signals, and each
+// rank then copies its now complete local result slot to `dst`.  Per rank (W-1)/W * n doubles cross NVLink in
+// each direction instead of (W-1) * n inbound.  One rank adds each element, in rank order: identical bits
+// everywhere.  The grid (<= 32 CTAs) is co-resident; `ticket` counts the CTAs that finished phase one.
+__global__ void __launch_bounds__(512) k_peer_reduce_rs(const PeerArgs pa, int region, size_t slot_off, size_t res_off,
+                                                         size_t n, unsigned long long seq, unsigned long long rseq,
+                                                         double* __restrict__ dst, unsigned int* __restrict__ ticket) {
+  pdl_prologue();
+  __shared__ int s_last;
+  const int t = threadIdx.x;
+  // the result region is shared by the exchanges that use this kernel, so it has its own sequence (rseq)
+  const int fidx = (region * 2 + (int)(seq & 1ULL)) * kMaxPeers, ridx = (kRgnR * 2 + (int)(rseq & 1ULL)) * kMaxPeers;
+  const bool tracing = pa.trace != nullptr && blockIdx.x == 0 && t == 0;
+  unsigned long long tr0 = 0, tr1 = 0;
+  if (tracing) tr0 = global_ns();
+  if (blockIdx.x == 0 && t < pa.world)
+    st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + fidx + pa.rank, seq);
+  if (t < pa.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + fidx + t;
+    while (ld_acquire_sys(f) < seq) { }
+  }
+  __syncthreads();
+  if (tracing) tr1 = global_ns();
+  // phase one: my slice, summed over the ranks' slots, stored to every rank's result slot
+  const size_t n2 = (n + 1) / 2, chunk = (n2 + pa.world - 1) / pa.world;
+  const size_t lo = (size_t)pa.rank * chunk, hi = lo + chunk < n2 ? lo + chunk : n2;
+  const size_t gsz = (size_t)gridDim.x * blockDim.x;
+  for (size_t i2 = lo + (size_t)blockIdx.x * blockDim.x + t; i2 < hi; i2 += gsz) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pa.world) v[r] = ld_relaxed_sys2(reinterpret_cast<const double*>(pa.peer[r] + kPeerDataOff) + slot_off + 2 * i2);
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pa.world) { acc.x += v[r].x; acc.y += v[r].y; }
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pa.world) *reinterpret_cast<double2*>(reinterpret_cast<double*>(pa.peer[r] + kPeerDataOff) + res_off + 2 * i2) = acc;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (t == 0) *ticket = 0u;
+    if (t < pa.world) st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + ridx + pa.rank, rseq);
+  }
+  // phase two: every rank's slice of the result has landed in my result slot
+  if (t < pa.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + ridx + t;
+    while (ld_acquire_sys(f) < rseq) { }
+  }
+  __syncthreads();
+  const double* res = reinterpret_cast<const double*>(pa.peer[pa.rank] + kPeerDataOff) + res_off;
+  for (size_t i2 = (size_t)blockIdx.x * blockDim.x + t; i2 < n2; i2 += gsz) {
+    const double2 v = ld_relaxed_sys2(res + 2 * i2);
+    if (2 * i2 + 1 < n) *reinterpret_cast<double2*>(dst + 2 * i2) = v;
+    else dst[2 * i2] = v.x;
+  }
+  if (tracing) {
+    atomicAdd(pa.trace + region * 4 + 0, 1ULL);
+    atomicAdd(pa.trace + region * 4 + 1, tr1 - tr0);
+    atomicAdd(pa.trace + region * 4 + 2, global_ns() - tr0);
   }
 }
 

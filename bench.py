@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="debug: skip the per-class event profile (roofline = null)")
     ap.add_argument("--ref-mode", default="analytic", choices=["analytic", "as_shipped"])
     ap.add_argument("--cams", type=int, default=0, help="debug: override the camera count")
     ap.add_argument("--variant", default="A", choices=["A", "B"], help="visibility: A uniform random, B contiguous camera window")
@@ -255,11 +256,13 @@ def main():
     d2h = out_c.numel() * 8 + out_p.numel() * 8 + m_local * 8
 
     # -- roofline: per-kernel-class device time from CUDA events on the launching stream ---------------------
-    reset_state()
-    ba.set_profiling(True)
-    ba.lm_solve(None, None, out=(cams_buf, pts_buf), want_residuals=False, max_iter=min(args.steps, 10), **lm_kw)
-    prof = ba.get_profile()
-    ba.set_profiling(False)
+    prof = {}
+    if not args.no_profile:
+        reset_state()
+        ba.set_profiling(True)
+        ba.lm_solve(None, None, out=(cams_buf, pts_buf), want_residuals=False, max_iter=min(args.steps, 10), **lm_kw)
+        prof = ba.get_profile()
+        ba.set_profiling(False)
     peak, peak_src = read_peaks()
     tot = sum(v["ms"] for v in prof.values()) or 1.0
     shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["launches"]}

@@ -514,10 +514,12 @@ def test_config4_full_size_properties(LineBA, orc, variant):
     ba.close()
 
 
-def test_multi_gpu_sharded_solve_matches_single_gpu():
+@pytest.mark.parametrize("transport", ["peer", "peer_two_phase", "nccl"])
+def test_multi_gpu_sharded_solve_matches_single_gpu(transport):
     """N > 1: run tests/run_multigpu_parity.py under torchrun when the box has at least two GPUs
-    (observations sharded at line boundaries, per-camera partial sums all-reduced over NVLink peer
-    memory; sharded trajectory must equal the single-GPU one)."""
+    (observations sharded at line boundaries, per-camera partial sums all-reduced; the sharded trajectory
+    must equal the single-GPU one).  Transports: NVLink peer memory (one-phase reduce), the same with the
+    reduce-scatter + all-gather kernel forced for every per-camera exchange, and the NCCL fallback."""
     import subprocess
     import sys
     import torch
@@ -525,8 +527,15 @@ def test_multi_gpu_sharded_solve_matches_single_gpu():
     if n < 2:
         pytest.skip("needs at least two GPUs")
     world = 2 if n < 4 else 4
+    env = dict(os.environ)
+    env.pop("LBA_NO_PEER", None)
+    env.pop("LBA_PEER_TWO_PHASE_MIN", None)
+    if transport == "peer_two_phase":
+        env["LBA_PEER_TWO_PHASE_MIN"] = "0"
+    elif transport == "nccl":
+        env["LBA_NO_PEER"] = "1"
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_multigpu_parity.py")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", script],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
