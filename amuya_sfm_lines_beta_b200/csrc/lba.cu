@@ -514,12 +514,16 @@ static int reduce_finish(lba_ctx* c, int region, double* local, size_t n) {
   if (c->world <= 1 || n == 0) return LBA_OK;
   if (!peer_fits(c, region, n)) return nccl_allreduce(c, local, n, ncclDouble, ncclSum);
   const unsigned long long seq = ++c->rgn_seq[region];
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(32, (n / 2 + 511) / 512));
+  // one double2 per thread per pass: the loop over a slot is a chain of NVLink round trips (~2.5 us each), so the
+  // grid is sized to make it one or two passes (measured at 8 ranks: 30 us with 32 CTAs)
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)2 * c->n_sm, (n / 2 + 511) / 512));
   if (c->world >= c->peer_rs_world && n >= c->peer_rs_min && n <= c->rgn_cap[kRgnR]) {
     // large exchange, many ranks: reduce-scatter + all-gather through the result region
     const unsigned long long rseq = ++c->rgn_seq[kRgnR];
     c->pre(LBA_K_COMM);
-    launch_kernel(c, k_peer_reduce_rs, dim3(grid), dim3(512), 0, c->peer_args, region, peer_slot_off(c, region, seq),
+    // (all CTAs of this kernel must be co-resident, they wait for each other's ranks: at most one per SM)
+    const int grid_rs = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->n_sm, (n / 2 + 1023) / 1024));
+    launch_kernel(c, k_peer_reduce_rs, dim3(grid_rs), dim3(512), 0, c->peer_args, region, peer_slot_off(c, region, seq),
                   peer_slot_off(c, kRgnR, rseq), n, seq, rseq, local, c->tickets.p + 4);
     c->post(LBA_K_COMM);
     return LBA_OK;

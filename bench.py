@@ -67,33 +67,41 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """Clocks / throttle reasons DURING the timed region: ONE `nvidia-smi -lms` process (the profiling recipe's
+    clocks line) started before the region and stopped after it, on rank 0 only, for the GPUs of this job.
+    A disabled sampler (other ranks) does nothing."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index=0):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def __init__(self, indices=(0,), enabled=True, period_ms=50):
+        self.indices, self.enabled, self.period_ms = list(indices), enabled, period_ms
+        self.samples, self._p = [], None
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            try:
+                self._p = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                                            f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                            "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                           text=True)
+            except Exception:
+                self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=10)
+        if self._p is None:
+            return
+        self._p.terminate()
+        try:
+            out, _ = self._p.communicate(timeout=10)
+        except Exception:
+            self._p.kill()
+            out, _ = self._p.communicate()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7 and f[1].replace(".", "", 1).isdigit():
+                self.samples.append(f[1:])
+        self._p = None
 
     def summary(self):
         if not self.samples:
@@ -101,8 +109,8 @@ class ClockSampler:
         sm = sorted(float(s[0]) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(sm), "gpus": self.indices}
 
 
 def make_scene(n_gpus, scale=1.0, seed=0, cams=0, variant="A"):
@@ -225,7 +233,7 @@ def main():
 
     # clocks / throttle reasons are sampled from the warm-up to the end of the e2e leg (the timed regions
     # themselves last only milliseconds)
-    clk = ClockSampler(local_rank)
+    clk = ClockSampler(range(world), enabled=(rank == 0))
     clk.__enter__()
     # -- warm-up: W untimed LM iterations --------------------------------------------------------------
     reset_state()
