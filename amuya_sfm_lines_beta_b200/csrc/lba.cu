@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace lba;
@@ -1203,6 +1204,62 @@ extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, 
   CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+// Two-view endpoint triangulation of n_tracks line tracks (seq_utils.py:75-135): independent of the BA problem
+// held by the context; uses its stream and device.  `seconds_kernel` (optional) returns the device time of the
+// kernel alone (CUDA events on the stream), for the measurement row of DESIGN.md.
+extern "C" int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_views, const double* P, const int64_t* view0,
+                                     const int64_t* view1, const float* pts0, const float* pts1, float* X, float* Xh,
+                                     double* seconds_kernel) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_tracks < 0 || n_views < 0 || n_tracks > (1LL << 40)) return fail(LBA_ERR_ARG, "bad sizes (n_tracks=%lld n_views=%lld)", (long long)n_tracks, (long long)n_views);
+  if (seconds_kernel) *seconds_kernel = 0.0;
+  if (n_tracks == 0) return LBA_OK;
+  if (!P || !view0 || !pts0 || !pts1 || !X) return fail(LBA_ERR_ARG, "NULL array");
+  if (n_views < 2) return fail(LBA_ERR_ARG, "triangulation needs at least two views");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)n_tracks;
+  // inputs that are not already on the device are staged; outputs are produced on the device and copied out
+  DBuf<double> sP; DBuf<long long> sv0, sv1; DBuf<float> sp0, sp1, dX, dXh; DBuf<int> dbad;
+  auto on_device = [&](auto& staging, const auto* src, size_t count, auto** out) -> int {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+    if (is_device_ptr(src)) { *out = src; return LBA_OK; }
+    CKR(staging.alloc(count));
+    CK(cudaMemcpyAsync(staging.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = staging.p;
+    return LBA_OK;
+  };
+  const double* dP = nullptr; const long long *dv0 = nullptr, *dv1 = nullptr; const float *dp0 = nullptr, *dp1 = nullptr;
+  CKR(on_device(sP, P, (size_t)n_views * 12, &dP));
+  CKR(on_device(sv0, reinterpret_cast<const long long*>(view0), n, &dv0));
+  if (view1) CKR(on_device(sv1, reinterpret_cast<const long long*>(view1), n, &dv1));
+  CKR(on_device(sp0, pts0, n * 4, &dp0));
+  CKR(on_device(sp1, pts1, n * 4, &dp1));
+  const bool x_dev = is_device_ptr(X), xh_dev = Xh && is_device_ptr(Xh);
+  float* outX = X; float* outXh = Xh;
+  if (!x_dev) { CKR(dX.alloc(n * 6)); outX = dX.p; }
+  if (Xh && !xh_dev) { CKR(dXh.alloc(n * 8)); outXh = dXh.p; }
+  CKR(dbad.alloc(1));
+  CK(cudaMemsetAsync(dbad.p, 0, 4, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  const long long n2 = 2 * (long long)n;
+  LAUNCH(ctx, LBA_K_MISC, k_triangulate, cdiv(n2, 256), 256, n2, (int)n_views, dP, dv0, dv1, reinterpret_cast<const float2*>(dp0),
+         reinterpret_cast<const float2*>(dp1), outX, reinterpret_cast<float4*>(outXh), dbad.p);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!x_dev) CK(cudaMemcpyAsync(X, outX, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (Xh && !xh_dev) CK(cudaMemcpyAsync(Xh, outXh, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, dbad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (seconds_kernel) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *seconds_kernel = ms * 1e-3;
+  }
+  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (bad) return fail(LBA_ERR_ARG, "%d track(s) name a view outside [0, %lld)", bad, (long long)n_views);
+  return LBA_OK;
 }
 
 extern "C" int lba_residuals(lba_ctx* ctx, const double* cams, const double* pts, double* residuals, double* cost) {

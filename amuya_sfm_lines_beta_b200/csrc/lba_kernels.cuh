@@ -34,6 +34,7 @@
 // every sum has a fixed order, so results are bit-reproducible run to run.
 #pragma once
 #include "lba_geometry.cuh"
+#include "lba_triangulate.cuh"
 #include <stddef.h>
 #include <stdint.h>
 
@@ -1714,6 +1715,40 @@ __global__ void __launch_bounds__(512) k_peer_reduce_rs(const PeerArgs pa, int r
     atomicAdd(pa.trace + region * 4 + 1, tr1 - tr0);
     atomicAdd(pa.trace + region * 4 + 2, global_ns() - tr0);
   }
+}
+
+// ---------------------------------------------------------------------------------
+// N3: two-view endpoint triangulation, one thread per (track, endpoint)  (seq_utils.py:105-127)
+// ---------------------------------------------------------------------------------
+// P [n_views][12] row-major 3x4; view0/view1 [n] (view1 NULL: view0 + 1, the reference's consecutive pairs);
+// pts0/pts1 [n][2][2] float32 = [track][endpoint][x,y]; X [n][2][3] float32; Xh [n][2][4] float32 or NULL.
+// FP64-bound (about 2.5 kflop of Jacobi rotations per point against 28 B of traffic); the camera matrices
+// (96 B each) are served by L1/L2.  bad[0] counts tracks whose view index is out of range (their X is NaN).
+__global__ void __launch_bounds__(256) k_triangulate(long long n2, int n_views, const double* __restrict__ P,
+                                                      const long long* __restrict__ view0,
+                                                      const long long* __restrict__ view1,
+                                                      const float2* __restrict__ pts0, const float2* __restrict__ pts1,
+                                                      float* __restrict__ X, float4* __restrict__ Xh,
+                                                      int* __restrict__ bad) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 2 * track + endpoint
+  if (i >= n2) return;
+  const long long t = i >> 1;
+  const long long a = view0[t], b = view1 ? view1[t] : a + 1;
+  float xh[4], x[3];
+  if (a < 0 || a >= n_views || b < 0 || b >= n_views) {
+    if ((i & 1) == 0) atomicAdd(bad, 1);
+    const float nanv = __int_as_float(0x7fc00000);
+    xh[0] = xh[1] = xh[2] = xh[3] = x[0] = x[1] = x[2] = nanv;
+  } else {
+    double P0[12], P1[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { P0[k] = __ldg(P + a * 12 + k); P1[k] = __ldg(P + b * 12 + k); }
+    const float2 q0 = pts0[i], q1 = pts1[i];
+    triangulate_dlt(P0, P1, q0.x, q0.y, q1.x, q1.y, xh, x);
+  }
+  X[i * 3 + 0] = x[0]; X[i * 3 + 1] = x[1]; X[i * 3 + 2] = x[2];
+  if (Xh) Xh[i] = make_float4(xh[0], xh[1], xh[2], xh[3]);
 }
 
 // ---------------------------------------------------------------------------------

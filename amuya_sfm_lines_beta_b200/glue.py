@@ -1,4 +1,4 @@
-"""Array-native glue between the reference's ``Domain`` objects and the GPU solver (SURVEY.md 8f, row N1).
+"""Array-native glue between the reference's ``Domain`` objects and the GPU solver (SURVEY.md 8f, rows N1, N3).
 
 The reference rebuilds the BA input with Python loops after every registered view and walks 2 m ``Line``
 objects again inside ``run_bundle_adjustment`` (``src/seq_utils.py:138-208``, ``src/bundle_adjustment.py:194-250``).
@@ -68,6 +68,54 @@ def update_domain_from_arrays(domain, op_camera_params, op_points_3d, last_view=
     for i, L in enumerate(domain.lines3d):
         L.points[0].coord = op_points_3d[2 * i]                                  # :250-252
         L.points[1].coord = op_points_3d[2 * i + 1]
+
+
+def triangulation_arrays_from_domain(domain, last_view):
+    """The arrays the reference's ``triangulate_model`` loop feeds to OpenCV (seq_utils.py:105-117): for every new
+    track of every consecutive view pair, the pair's first view and the two float32 endpoint arrays.
+    Returns ``dict(P (V,3,4) f64, view0 (n,) int64, pts0, pts1 (n,2,2) f32)``."""
+    P = np.array([np.asarray(v.P.P, dtype=np.float64) for v in domain.views[:last_view + 1]])
+    ids = np.asarray(domain.tracker.ids)
+    view0, l0, l1 = [], [], []
+    tr = 0
+    for i in range(last_view):                                               # :105-112
+        k = int(domain.tracker.n_new_tracks[i])
+        pair = ids[tr:tr + k, i:i + 2].astype(np.int64)
+        view0.append(np.full(k, i, dtype=np.int64)); l0.append(pair[:, 0]); l1.append(pair[:, 1])
+        tr += k
+    view0 = np.concatenate(view0) if view0 else np.empty(0, dtype=np.int64)
+    l0 = np.concatenate(l0) if l0 else np.empty(0, dtype=np.int64)
+    l1 = np.concatenate(l1) if l1 else np.empty(0, dtype=np.int64)
+    lines2d = domain.lines2d
+    pts0 = np.array([[p.coord for p in lines2d[j].points] for j in l0], dtype=np.float32).reshape(-1, 2, 2)   # :114-115
+    pts1 = np.array([[p.coord for p in lines2d[j].points] for j in l1], dtype=np.float32).reshape(-1, 2, 2)   # :116-117
+    return dict(P=P, view0=view0, pts0=pts0, pts1=pts1)
+
+
+def triangulate_model(domain, last_view, ba=None, point3d_cls=None, line3d_cls=None):
+    """``triangulate_model(domain, last_view)`` (seq_utils.py:75-135) with the per-line ``cv2.triangulatePoints``
+    loop replaced by one batched GPU call: rebuilds ``domain.points3d`` / ``domain.lines3d`` with the same ids,
+    order and float32 coordinates.  ``point3d_cls`` / ``line3d_cls`` default to the reference's ``Point3D`` /
+    ``Line3D`` (``point.py:14``, ``line.py:50``; they must be importable, as they are inside the reference)."""
+    if point3d_cls is None:
+        from point import Point3D as point3d_cls
+    if line3d_cls is None:
+        from line import Line3D as line3d_cls
+    a = triangulation_arrays_from_domain(domain, last_view)
+    own = ba is None
+    ba = LineBA(0) if own else ba
+    try:
+        X = ba.triangulate_lines(a["P"], a["view0"], a["pts0"], a["pts1"])
+    finally:
+        if own:
+            ba.close()
+    domain.lines3d, domain.points3d = [], []
+    for t in range(X.shape[0]):                                               # :122-131
+        p_ini = point3d_cls(2 * t, X[t, 0])
+        p_fin = point3d_cls(2 * t + 1, X[t, 1])
+        domain.points3d += [p_ini, p_fin]
+        domain.lines3d.append(line3d_cls(t, [p_ini, p_fin]))
+    return X
 
 
 class IncrementalBA:

@@ -109,6 +109,36 @@ class LineBA:
         check(self._lib.lba_point_wise_indices(self._h, cam_pt.ctypes.data, pt_idx.ctypes.data))
         return cam_pt, pt_idx
 
+    # -- two-view endpoint triangulation (independent of set_problem) ------
+    def triangulate_lines(self, P, view0, pts0, pts1, view1=None, want_homogeneous=False, out=None):
+        """``cv2.triangulatePoints`` + float32 dehomogenisation for every endpoint of every track
+        (reference ``triangulate_model``, src/seq_utils.py:105-127).  ``P`` (V,3,4) f64; ``view0`` (n,) int64
+        (``view1`` defaults to ``view0 + 1``); ``pts0``, ``pts1`` (n,2,2) f32 ``[track][endpoint][x,y]``.
+        Returns ``X`` (n,2,3) float32 (and ``Xh`` (n,2,4) when asked).  numpy or torch (CPU / CUDA) inputs;
+        ``out`` may be a preallocated float32 array / CUDA tensor of n*6 elements.  The device time of the
+        kernel is left in ``self.last_triangulate_seconds``."""
+        n = int(view0.shape[0])
+        n_views = int(P.shape[0])
+        pP, k0 = _as_ptr(P, np.float64, "float64", 12 * n_views)
+        pv0, k1 = _as_ptr(view0, np.int64, "int64", n)
+        pv1, k2 = _as_ptr(view1, np.int64, "int64", n)
+        pa, k3 = _as_ptr(pts0, np.float32, "float32", 4 * n)
+        pb, k4 = _as_ptr(pts1, np.float32, "float32", 4 * n)
+        if out is None:
+            X = np.empty((n, 2, 3), dtype=np.float32)
+            pX = X.ctypes.data
+        else:
+            X = out
+            pX = out.data_ptr() if _is_torch(out) else out.ctypes.data
+            if (out.numel() if _is_torch(out) else out.size) != 6 * n:
+                raise ValueError(f"out must hold {6 * n} float32 values")
+        Xh = np.empty((n, 2, 4), dtype=np.float32) if want_homogeneous else None
+        sec = C.c_double()
+        check(self._lib.lba_triangulate_lines(self._h, n, n_views, pP, pv0, pv1, pa, pb, pX,
+                                              Xh.ctypes.data if Xh is not None else None, C.byref(sec)))
+        self.last_triangulate_seconds = sec.value
+        return (X, Xh) if want_homogeneous else X
+
     # -- evaluation -----------------------------------------------------------------
     def project(self, camera_params, points_3d):
         pc, pp, keep = self._params(camera_params, points_3d)

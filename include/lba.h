@@ -140,6 +140,18 @@ int lba_point_wise_indices(lba_ctx* ctx, int64_t* camera_indices_pt, int64_t* pt
 /* project (:23-74): p_hat for every endpoint-observation, (2m,3) f64, row 2i+e. */
 int lba_project(lba_ctx* ctx, const double* camera_params, const double* points_3d, double* proj);
 
+/* Two-view endpoint triangulation of n_tracks matched line segments ("next" row N3): replaces the per-line
+ * loop of triangulate_model / triangulate_model2 (src/seq_utils.py:75-135, :11-72), i.e. for each endpoint
+ *     X = cv2.triangulatePoints(P[view0], P[view1], x0, x1);  X = X[:3] / X[3]        (:119-121)
+ * with OpenCV's DLT matrix and one-sided Jacobi SVD restated in fp64 and the float32 conversion / division of
+ * the reference.  P (n_views,3,4) f64 row-major; view0, view1 (n_tracks,) int64 (view1 may be NULL: view0 + 1,
+ * the reference's consecutive pairs); pts0, pts1 (n_tracks,2,2) f32 = [track][endpoint][x,y];
+ * X (n_tracks,2,3) f32 out; Xh (n_tracks,2,4) f32 out or NULL (homogeneous, unit 4-vector up to sign);
+ * seconds_kernel out or NULL (device time of the kernel).  Independent of lba_set_problem. */
+int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_views, const double* P,
+                          const int64_t* view0, const int64_t* view1, const float* pts0, const float* pts1,
+                          float* X, float* Xh, double* seconds_kernel);
+
 /* fun (:78-139): residuals (m,) in the caller's observation order; cost = 0.5*sum r^2
  * (either output may be NULL). */
 int lba_residuals(lba_ctx* ctx, const double* camera_params, const double* points_3d,
