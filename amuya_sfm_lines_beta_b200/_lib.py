@@ -24,7 +24,7 @@ EXPORTS = [
     "lba_residuals_jacobian", "lba_normal_equations", "lba_schur_solve", "lba_lm_solve",
     "lba_comm_unique_id", "lba_comm_init", "lba_comm_destroy", "lba_comm_peer_local", "lba_comm_peer_attach", "lba_launch_count", "lba_set_profiling",
     "lba_get_profile", "lba_kernel_class_name", "lba_measure_fp64_peak", "lba_measure_copy_bandwidth",
-    "lba_triangulate_lines",
+    "lba_triangulate_lines", "lba_track_table",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     lib.lba_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
     lib.lba_measure_copy_bandwidth.argtypes = [vp, i64, C.POINTER(dbl)]
     lib.lba_triangulate_lines.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(dbl)]
+    lib.lba_track_table.argtypes = [vp, i32, i64, vp, vp, vp, vp, dbl, vp, i64, vp, vp, vp, C.POINTER(i64), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("lba_version",):

@@ -10,6 +10,7 @@
 #include "lba_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -1203,6 +1204,107 @@ extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, 
   LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(ctx->Mp, 256), 256, a);
   CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+}
+
+// Track table of `n_views` consecutive views (tracker.py:11-96 with verify_duplet, utils.py:1807-1944): the view
+// pairs are processed in order on the context's stream, each pair data-parallel, with no host synchronisation
+// until the tables are copied out.  match_ptr is read on the host (launch sizes).
+extern "C" int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d, const double* endpoints,
+                               const int64_t* match_ptr, const int64_t* matches, const double* F, double threshold,
+                               const uint8_t* flags_in, int64_t cap_rows, int64_t* ids, int64_t* bin,
+                               int64_t* n_new_tracks, int64_t* n_tracks, uint8_t* flags_out) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_views < 2 || n_lines2d < 1) return fail(LBA_ERR_ARG, "need at least two views and one 2D line");
+  if (!endpoints || !match_ptr || !F || !ids || !bin || !n_new_tracks || !n_tracks) return fail(LBA_ERR_ARG, "NULL array");
+  if (is_device_ptr(match_ptr) || is_device_ptr(n_new_tracks) || is_device_ptr(n_tracks))
+    return fail(LBA_ERR_ARG, "match_ptr, n_new_tracks and n_tracks are host arrays");
+  const int V = n_views, NP = n_views - 1;
+  if (match_ptr[0] != 0) return fail(LBA_ERR_ARG, "match_ptr[0] must be 0");
+  for (int v = 0; v < NP; ++v)
+    if (match_ptr[v + 1] < match_ptr[v]) return fail(LBA_ERR_ARG, "match_ptr must be non-decreasing");
+  const long long M = match_ptr[NP];
+  if (M > 0x7fffffffLL || n_lines2d > 0x7fffffffLL) return fail(LBA_ERR_ARG, "too many matches or lines");
+  if (M > 0 && !matches) return fail(LBA_ERR_ARG, "NULL matches");
+  if (cap_rows < M) return fail(LBA_ERR_ARG, "cap_rows (%lld) must be at least the number of matches (%lld)", (long long)cap_rows, M);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st_ = ctx->stream;
+  long long kmax = 0;
+  for (int v = 0; v < NP; ++v) kmax = std::max<long long>(kmax, match_ptr[v + 1] - match_ptr[v]);
+
+  DBuf<double> sE, sF; DBuf<long long> sM, d_inl, d_st, d_ids, d_bin, d_nnew; DBuf<unsigned char> sFl, d_present, d_fl8;
+  DBuf<int> d_flag, d_pos, d_newflag, d_newpos, d_last, d_bad; DBuf<unsigned char> d_tmp;
+  auto on_device = [&](auto& staging, const auto* src, size_t count, auto** out) -> int {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+    if (is_device_ptr(src)) { *out = src; return LBA_OK; }
+    CKR(staging.alloc(count));
+    CK(cudaMemcpyAsync(staging.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st_));
+    *out = staging.p;
+    return LBA_OK;
+  };
+  const double *dE = nullptr, *dF = nullptr; const long long* dM = nullptr; const unsigned char* dFl = nullptr;
+  CKR(on_device(sE, endpoints, (size_t)n_lines2d * 4, &dE));
+  CKR(on_device(sF, F, (size_t)NP * 9, &dF));
+  if (M > 0) CKR(on_device(sM, reinterpret_cast<const long long*>(matches), (size_t)M * 2, &dM));
+  if (flags_in && M > 0) CKR(on_device(sFl, flags_in, (size_t)M, &dFl));
+  const size_t tab = (size_t)cap_rows * V;
+  const bool ids_dev = is_device_ptr(ids), bin_dev = is_device_ptr(bin);
+  long long* o_ids = reinterpret_cast<long long*>(ids); long long* o_bin = reinterpret_cast<long long*>(bin);
+  if (!ids_dev) { CKR(d_ids.alloc(tab)); o_ids = d_ids.p; }
+  if (!bin_dev) { CKR(d_bin.alloc(tab)); o_bin = d_bin.p; }
+  CK(cudaMemsetAsync(o_ids, 0, tab * 8, st_));
+  CK(cudaMemsetAsync(o_bin, 0, tab * 8, st_));
+  CKR(d_flag.alloc((size_t)M)); CKR(d_pos.alloc((size_t)kmax)); CKR(d_newflag.alloc((size_t)kmax)); CKR(d_newpos.alloc((size_t)kmax));
+  CKR(d_inl.alloc((size_t)kmax)); CKR(d_present.alloc((size_t)n_lines2d)); CKR(d_last.alloc((size_t)n_lines2d));
+  CKR(d_st.alloc(4)); CKR(d_nnew.alloc((size_t)NP)); CKR(d_bad.alloc(1));
+  CK(cudaMemsetAsync(d_st.p, 0, 32, st_));
+  CK(cudaMemsetAsync(d_nnew.p, 0, (size_t)NP * 8, st_));
+  CK(cudaMemsetAsync(d_bad.p, 0, 4, st_));
+  size_t tmp_bytes = 0;
+  if (kmax > 0) {
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.p, d_pos.p, (int)kmax, st_));
+    CKR(d_tmp.alloc(tmp_bytes));
+  }
+  const int row_grid = ctx->n_sm * 4;
+  for (int v = 0; v < NP; ++v) {
+    const long long off = match_ptr[v], k = match_ptr[v + 1] - off;
+    if (k == 0) continue;   // n_new_tracks[v] stays 0
+    const int grid = cdiv(k, 256);
+    int* flag = d_flag.p + off;
+    LAUNCH(ctx, LBA_K_MISC, k_tt_verify, grid, 256, k, (long long)n_lines2d, dM + 2 * off, dE, dF + 9 * v, threshold,
+           dFl ? dFl + off : (const unsigned char*)nullptr, flag, d_bad.p);
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, flag, d_pos.p, (int)k, st_));
+    if (v > 0) {
+      CK(cudaMemsetAsync(d_present.p, 0, (size_t)n_lines2d, st_));
+      CK(cudaMemsetAsync(d_last.p, 0xff, (size_t)n_lines2d * 4, st_));
+      LAUNCH(ctx, LBA_K_MISC, k_tt_present, row_grid, 256, (const long long*)d_st.p, V, v, (const long long*)o_ids, d_present.p);
+    }
+    LAUNCH(ctx, LBA_K_MISC, k_tt_last, grid, 256, k, v, dM + 2 * off, (const int*)flag, (const int*)d_pos.p,
+           (const unsigned char*)d_present.p, d_inl.p, d_last.p, d_newflag.p);
+    if (v > 0)
+      LAUNCH(ctx, LBA_K_MISC, k_tt_extend, row_grid, 256, (const long long*)d_st.p, V, v, o_ids, o_bin, (const int*)d_last.p,
+             (const long long*)d_inl.p);
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_newflag.p, d_newpos.p, (int)k, st_));
+    LAUNCH(ctx, LBA_K_MISC, k_tt_append, grid, 256, k, V, v, (const long long*)d_st.p, dM + 2 * off, (const int*)d_newflag.p,
+           (const int*)d_newpos.p, o_ids, o_bin);
+    LAUNCH(ctx, LBA_K_MISC, k_tt_advance, 1, 32, k, v, d_st.p, (const int*)d_newflag.p, (const int*)d_newpos.p, d_nnew.p);
+  }
+  long long rows = 0; int bad = 0;
+  CK(cudaMemcpyAsync(&rows, d_st.p, 8, cudaMemcpyDeviceToHost, st_));
+  CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st_));
+  CK(cudaMemcpyAsync(n_new_tracks, d_nnew.p, (size_t)NP * 8, cudaMemcpyDeviceToHost, st_));
+  CK(cudaStreamSynchronize(st_));
+  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (bad) return fail(LBA_ERR_ARG, "%d match(es) name a 2D line outside [0, %lld)", bad, (long long)n_lines2d);
+  *n_tracks = rows;
+  if (!ids_dev && rows > 0) CK(cudaMemcpyAsync(ids, o_ids, (size_t)rows * V * 8, cudaMemcpyDeviceToHost, st_));
+  if (!bin_dev && rows > 0) CK(cudaMemcpyAsync(bin, o_bin, (size_t)rows * V * 8, cudaMemcpyDeviceToHost, st_));
+  if (flags_out && M > 0) {
+    CKR(d_fl8.alloc((size_t)M));
+    LAUNCH(ctx, LBA_K_MISC, k_tt_flags_u8, cdiv(M, 256), 256, M, (const int*)d_flag.p, d_fl8.p);
+    CK(cudaMemcpyAsync(flags_out, d_fl8.p, (size_t)M, cudaMemcpyDefault, st_));
+  }
+  CK(cudaStreamSynchronize(st_));
   return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
 }
 

@@ -35,6 +35,7 @@
 #pragma once
 #include "lba_geometry.cuh"
 #include "lba_triangulate.cuh"
+#include "lba_tracks.cuh"
 #include <stddef.h>
 #include <stdint.h>
 
@@ -1715,6 +1716,93 @@ __global__ void __launch_bounds__(512) k_peer_reduce_rs(const PeerArgs pa, int r
     atomicAdd(pa.trace + region * 4 + 1, tr1 - tr0);
     atomicAdd(pa.trace + region * 4 + 2, global_ns() - tr0);
   }
+}
+
+// ---------------------------------------------------------------------------------
+// N2: track table (tracker.py:11-96) one view pair at a time, data-parallel inside a pair.
+//   ids / bin: [cap][V] int64, zero-filled; st[0] = rows so far, st[1] = inliers of the pair, st[2] = new tracks
+//   of the pair.  Per pair v: verify -> exclusive scans (CUB) -> presence table over column v -> last-writer
+//   table over the inlier matches -> extension of the existing rows -> ordered append of the new tracks.
+// ---------------------------------------------------------------------------------
+// flag[j] = 1 when match j of the pair passes verify_duplet; endpoints [n_lines2d][2][2]; line ids range-checked
+__global__ void k_tt_verify(long long k, long long n_lines, const long long* __restrict__ matches,
+                            const double* __restrict__ endpoints, const double* __restrict__ F, double threshold,
+                            const unsigned char* __restrict__ flags_in, int* __restrict__ flag, int* __restrict__ bad) {
+  pdl_prologue();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const long long l0 = matches[2 * j], l1 = matches[2 * j + 1];
+  if (l0 < 0 || l0 >= n_lines || l1 < 0 || l1 >= n_lines) { atomicAdd(bad, 1); flag[j] = 0; return; }
+  if (flags_in) { flag[j] = flags_in[j] ? 1 : 0; return; }
+  double Fm[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) Fm[q] = __ldg(F + q);
+  const double* a = endpoints + l0 * 4;
+  const double* b = endpoints + l1 * 4;
+  const double a0[2] = {a[0], a[1]}, a1[2] = {a[2], a[3]}, b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+  flag[j] = duplet_inlier(Fm, a0, a1, b0, b1, threshold) ? 1 : 0;
+}
+// present[x] = 1 for every value x in column v of the existing rows (the zeros of absent entries included, as in
+// the reference's `l in Tr_ij[:, v]`)
+__global__ void k_tt_present(const long long* __restrict__ st, int V, int v, const long long* __restrict__ ids,
+                             unsigned char* __restrict__ present) {
+  pdl_prologue();
+  const long long rows = st[0];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    present[ids[r * V + v]] = 1;
+}
+// inlier matches: inl_l1[pos] = second line; last[l0] = largest inlier rank among the matches of a present line
+// (the reference applies them in order, so the last one wins); newflag = inlier && line not present
+__global__ void k_tt_last(long long k, int v, const long long* __restrict__ matches, const int* __restrict__ flag,
+                          const int* __restrict__ pos, const unsigned char* __restrict__ present,
+                          long long* __restrict__ inl_l1, int* __restrict__ last, int* __restrict__ newflag) {
+  pdl_prologue();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  int nf = 0;
+  if (flag[j]) {
+    const long long l0 = matches[2 * j];
+    inl_l1[pos[j]] = matches[2 * j + 1];
+    if (v > 0 && present[l0]) atomicMax(last + l0, pos[j]);
+    else nf = 1;
+  }
+  newflag[j] = nf;
+}
+__global__ void k_tt_extend(const long long* __restrict__ st, int V, int v, long long* __restrict__ ids,
+                            long long* __restrict__ bin, const int* __restrict__ last,
+                            const long long* __restrict__ inl_l1) {
+  pdl_prologue();
+  const long long rows = st[0];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const int j = last[ids[r * V + v]];
+    if (j >= 0) { ids[r * V + v + 1] = inl_l1[j]; bin[r * V + v + 1] = 1; }
+  }
+}
+__global__ void k_tt_append(long long k, int V, int v, const long long* __restrict__ st, const long long* __restrict__ matches,
+                            const int* __restrict__ newflag, const int* __restrict__ newpos, long long* __restrict__ ids,
+                            long long* __restrict__ bin) {
+  pdl_prologue();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k || !newflag[j]) return;
+  const long long r = st[0] + newpos[j];
+  ids[r * V + v] = matches[2 * j]; ids[r * V + v + 1] = matches[2 * j + 1];
+  bin[r * V + v] = 1; bin[r * V + v + 1] = 1;
+}
+// rows += new tracks of the pair; n_new_tracks[v]; totals come from the last element of the scans
+__global__ void k_tt_advance(long long k, int v, long long* __restrict__ st, const int* __restrict__ newflag,
+                             const int* __restrict__ newpos, long long* __restrict__ n_new_tracks) {
+  pdl_prologue();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long n_new = k > 0 ? (long long)newpos[k - 1] + newflag[k - 1] : 0;
+    n_new_tracks[v] = n_new;
+    st[0] += n_new;
+  }
+}
+
+__global__ void k_tt_flags_u8(long long n, const int* __restrict__ flag, unsigned char* __restrict__ out) {
+  pdl_prologue();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = flag[j] ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------

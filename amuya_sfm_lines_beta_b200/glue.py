@@ -1,4 +1,4 @@
-"""Array-native glue between the reference's ``Domain`` objects and the GPU solver (SURVEY.md 8f, rows N1, N3).
+"""Array-native glue between the reference's ``Domain`` objects and the GPU solver (SURVEY.md 8f, rows N1-N3).
 
 The reference rebuilds the BA input with Python loops after every registered view and walks 2 m ``Line``
 objects again inside ``run_bundle_adjustment`` (``src/seq_utils.py:138-208``, ``src/bundle_adjustment.py:194-250``).
@@ -68,6 +68,52 @@ def update_domain_from_arrays(domain, op_camera_params, op_points_3d, last_view=
     for i, L in enumerate(domain.lines3d):
         L.points[0].coord = op_points_3d[2 * i]                                  # :250-252
         L.points[1].coord = op_points_3d[2 * i + 1]
+
+
+def fundamental_from_cameras(K, P0, P1):
+    """``relativeCameraMotion`` (utils.py:1483-1509) + ``F_from_KRt2`` (:1039-1065) for two reference ``Camera``
+    objects: the same numpy expressions, so the same bits."""
+    R0, t0, R1, t1 = P0.R, P0.t, P1.R, P1.t
+    rR = R1 @ R0.T
+    rt = (t1 - rR @ t0).reshape((3, 1))
+    rt_x = np.array([[0, -rt[2][0], rt[1][0]], [rt[2][0], 0, -rt[0][0]], [-rt[1][0], rt[0][0], 0]])
+    F = np.linalg.inv(K).T @ rt_x @ rR @ np.linalg.inv(K)
+    return F / F[2, 2]
+
+
+def tracker_arrays_from_domain(domain, last_view):
+    """What ``Tracker.comp_tracker(domain, last_view)`` reads (tracker.py:44-55): per consecutive view pair the
+    fundamental matrix and ``domain.line_match["<v><v+1>"][1]``; the endpoints of ``domain.lines2d`` by list index."""
+    endpoints = np.array([[np.asarray(p.coord, dtype=np.float64)[:2] for p in L.points] for L in domain.lines2d])
+    F, matches = [], []
+    for v in range(last_view):
+        F.append(fundamental_from_cameras(domain.K, domain.views[v].P, domain.views[v + 1].P))
+        matches.append(np.array(domain.line_match[str(v) + str(v + 1)][1], dtype=np.int64).reshape(-1, 2))
+    return dict(endpoints=endpoints, F=np.array(F), matches=matches)
+
+
+class TrackTables:
+    """Stand-in for the reference's ``Tracker`` after ``comp_tracker``: ``ids`` / ``bin`` as float64 arrays (the
+    reference's dtype, tracker.py:39-41) and ``n_new_tracks`` as a list of ints."""
+
+    def __init__(self, ids, bi, n_new):
+        self.ids = np.asarray(ids, dtype=np.float64)
+        self.bin = np.asarray(bi, dtype=np.float64)
+        self.n_new_tracks = [int(x) for x in n_new]
+
+
+def comp_tracker(domain, last_view=2, ba=None, threshold=0.1):
+    """``Tracker().comp_tracker(domain, last_view)`` on the GPU; returns a ``TrackTables`` to assign to
+    ``domain.tracker`` (main.py:96-98)."""
+    a = tracker_arrays_from_domain(domain, last_view)
+    own = ba is None
+    ba = LineBA(0) if own else ba
+    try:
+        ids, bi, n_new = ba.track_table(a["endpoints"], a["matches"], a["F"], threshold)
+    finally:
+        if own:
+            ba.close()
+    return TrackTables(ids, bi, n_new)
 
 
 def triangulation_arrays_from_domain(domain, last_view):

@@ -109,6 +109,38 @@ class LineBA:
         check(self._lib.lba_point_wise_indices(self._h, cam_pt.ctypes.data, pt_idx.ctypes.data))
         return cam_pt, pt_idx
 
+    # -- track table (independent of set_problem) ------------------------------
+    def track_table(self, endpoints, matches_per_pair, F_per_pair, threshold=0.1, flags_in=None, want_flags=False):
+        """``Tracker.comp_tracker`` (src/tracker.py:11-96) with ``verify_duplet`` (src/utils.py:1807-1944) on the GPU.
+        ``endpoints`` (n_lines2d,2,2) f64 pixel endpoints of ``domain.lines2d[id]``; ``matches_per_pair[v]`` the (k,2)
+        int64 matches of views (v, v+1); ``F_per_pair[v]`` their 3x3 fundamental matrix.  Returns
+        ``(ids (T,V) int64, bin (T,V) int64, n_new_tracks (V-1,) int64[, flags (M,) bool])``."""
+        n_pairs = len(matches_per_pair)
+        V = n_pairs + 1
+        ms = [np.ascontiguousarray(m, dtype=np.int64).reshape(-1, 2) for m in matches_per_pair]
+        ptr = np.zeros(V, dtype=np.int64)
+        ptr[1:] = np.cumsum([len(m) for m in ms])
+        M = int(ptr[-1])
+        matches = np.concatenate(ms) if M else np.zeros((0, 2), dtype=np.int64)
+        E = np.ascontiguousarray(endpoints, dtype=np.float64)
+        F = np.ascontiguousarray(np.asarray(F_per_pair, dtype=np.float64).reshape(n_pairs, 9))
+        fin = None if flags_in is None else np.ascontiguousarray(np.asarray(flags_in).astype(np.uint8))
+        if fin is not None and fin.size != M:
+            raise ValueError(f"flags_in must have one entry per match ({M})")
+        cap = max(M, 1)
+        ids = np.empty((cap, V), dtype=np.int64)
+        bi = np.empty((cap, V), dtype=np.int64)
+        n_new = np.zeros(n_pairs, dtype=np.int64)
+        flags = np.zeros(M, dtype=np.uint8) if want_flags else None
+        n_tracks = C.c_int64()
+        check(self._lib.lba_track_table(self._h, V, int(E.shape[0]), E.ctypes.data, ptr.ctypes.data,
+                                        matches.ctypes.data if M else None, F.ctypes.data, float(threshold),
+                                        fin.ctypes.data if fin is not None else None, cap, ids.ctypes.data, bi.ctypes.data,
+                                        n_new.ctypes.data, C.byref(n_tracks), flags.ctypes.data if want_flags else None))
+        T = int(n_tracks.value)
+        out = (ids[:T].copy(), bi[:T].copy(), n_new)
+        return out + (flags.astype(bool),) if want_flags else out
+
     # -- two-view endpoint triangulation (SURVEY 8f N3; independent of set_problem) ------
     def triangulate_lines(self, P, view0, pts0, pts1, view1=None, want_homogeneous=False, out=None):
         """``cv2.triangulatePoints`` + float32 dehomogenisation for every endpoint of every track

@@ -140,6 +140,24 @@ int lba_point_wise_indices(lba_ctx* ctx, int64_t* camera_indices_pt, int64_t* pt
 /* project (:23-74): p_hat for every endpoint-observation, (2m,3) f64, row 2i+e. */
 int lba_project(lba_ctx* ctx, const double* camera_params, const double* points_3d, double* proj);
 
+/* Track table of n_views consecutive views ("next" row N2): replaces Tracker.comp_tracker (src/tracker.py:11-96)
+ * together with its verify_duplet calls (src/utils.py:1807-1944).
+ *   endpoints (n_lines2d,2,2) f64: pixel coordinates of the endpoints of domain.lines2d[id] (the reference indexes
+ *       that list by line id, utils.py:1874-1875);
+ *   match_ptr (n_views,) int64 HOST: the matches of the view pair (v, v+1) are rows [match_ptr[v], match_ptr[v+1])
+ *       of matches (M,2) int64 = domain.line_match["<v><v+1>"][1];
+ *   F (n_views-1,3,3) f64: fundamental matrix of each pair (relativeCameraMotion utils.py:1483 + F_from_KRt2 :1039);
+ *   threshold: 0.1 in the reference (tracker.py:53);  flags_in (M,) u8 or NULL: take these inlier flags instead of
+ *       running the epipolar test;
+ *   ids, bin (cap_rows,n_views) int64 out, cap_rows >= M: ids[track,view] (0 where absent) and bin[track,view]
+ *       (tracker.py:93-95; the reference holds the same integers in float64 arrays); n_new_tracks (n_views-1,) int64
+ *       HOST out; *n_tracks HOST out: rows used; flags_out (M,) u8 or NULL: inlier flag per match.
+ * Matches within 1e-12 of parallel to an epipolar line are outliers (the reference raises / divides by noise). */
+int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d, const double* endpoints,
+                    const int64_t* match_ptr, const int64_t* matches, const double* F, double threshold,
+                    const uint8_t* flags_in, int64_t cap_rows, int64_t* ids, int64_t* bin,
+                    int64_t* n_new_tracks, int64_t* n_tracks, uint8_t* flags_out);
+
 /* Two-view endpoint triangulation of n_tracks matched line segments ("next" row N3): replaces the per-line
  * loop of triangulate_model / triangulate_model2 (src/seq_utils.py:75-135, :11-72), i.e. for each endpoint
  *     X = cv2.triangulatePoints(P[view0], P[view1], x0, x1);  X = X[:3] / X[3]        (:119-121)
