@@ -17,6 +17,15 @@ import numpy as np
 from .solver import LineBA
 
 
+def observations_from_tables(ids, bin_):
+    """The observation list ``input_bundle_adj`` derives from the tracker tables (seq_utils.py:186-195): tracks seen in
+    more than one view, track-major and view-ascending.  Returns ``(camera_indices, lines_indices, line_ids)`` int64."""
+    bin_ = np.asarray(bin_)
+    n_tracks = int(np.count_nonzero(bin_.sum(axis=1) > 1))                    # :188-189
+    t_idx, v_idx = np.where(bin_[:n_tracks] == 1)                             # :190
+    return v_idx.astype(np.int64), t_idx.astype(np.int64), np.asarray(ids)[t_idx, v_idx].astype(np.int64)
+
+
 def input_arrays_from_domain(domain, last_view=2):
     """Vectorised ``input_bundle_adj(domain, "Rodrigues", last_view)`` (seq_utils.py:138-208).
 
@@ -31,12 +40,7 @@ def input_arrays_from_domain(domain, last_view=2):
     for i, v in enumerate(views):
         cams[i, :, 0] = cv2.Rodrigues(np.asarray(v.P.R))[0].ravel()          # :179
         cams[i, :, 1] = np.asarray(v.P.c, dtype=np.float64).ravel()           # :172
-    bin_ = np.asarray(domain.tracker.bin)
-    ids_ = np.asarray(domain.tracker.ids)
-    check = bin_.sum(axis=1)
-    n_tracks = int(np.count_nonzero(check > 1))                               # :188-189
-    t_idx, v_idx = np.where(bin_[:n_tracks] == 1)                             # :190  (track-major, view-ascending)
-    line_ids = ids_[t_idx, v_idx].astype(np.int64)                            # :192
+    v_idx, t_idx, line_ids = observations_from_tables(domain.tracker.ids, domain.tracker.bin)   # :188-192
     lines2d = domain.lines2d
     n = np.array([lines2d[j].n for j in line_ids], dtype=np.float64).reshape(-1, 3)
     p0 = np.array([lines2d[j].points[0].p for j in line_ids], dtype=np.float64).reshape(-1, 3)
