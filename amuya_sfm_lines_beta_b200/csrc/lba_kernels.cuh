@@ -43,10 +43,7 @@ namespace lba {
 
 constexpr int kTile = 256;             // slots per tile == threads per line-order CTA
 constexpr int kMaxLinesPerTile = 128;
-constexpr int kStages = 3;      // k_eval pipeline depth (2 CTAs/SM)
 constexpr int kLpStages = 2;    // k_line_pass pipeline depth (3 CTAs/SM)
-constexpr int kCamThreads = 128;
-constexpr int kCgThreads = 1024;
 constexpr int kVinvStride = 22;        // 21 packed entries + 1 pad -> 176 B rows (16 B aligned)
 
 struct __align__(16) TileMeta {
