@@ -98,8 +98,8 @@ main_md = summarize_full([os.path.join(go, f"prof_{rnd}.ncu-rep")], f"kernels_{r
                          f"ncu --set full, round {rnd} (one launch per kernel, config 4)")
 extra = [os.path.join(go, n) for n in ("prof_n2.ncu-rep", "prof_n3.ncu-rep") if os.path.exists(os.path.join(go, n))]
 next_md = summarize_full(extra, f"kernels_next_{rnd}",
-                         f"ncu --set full, round {rnd}: kernels of the \"next\" rows (N2 track table: scripts/bench_track_table.py, "
-                         "8 views x 250 k lines; N3 triangulation: scripts/bench_triangulate.py, 2 M tracks)") if extra else None
+                         f"ncu --set full, round {rnd}: kernels of the \"next\" rows (N2 track table: tests/measure_track_table.py, "
+                         "8 views x 250 k lines; N3 triangulation: tests/measure_triangulate.py, 2 M tracks)") if extra else None
 print(open(os.path.join(out, f"launches_{rnd}.md")).read())
 print(open(main_md).read())
 if next_md:

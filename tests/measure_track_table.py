@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Measurement for the N2 row: track-table construction on the GPU (epipolar verification of every match + table
 merge, view pair by view pair) against the sequential oracle restatement of the reference on a bounded sample.
-Prints one JSON line."""
+Prints one JSON line.
+Lives under tests/ because it times the oracle as its CPU arm (only test infrastructure may execute oracle/)."""
 import json
 import os
 import sys

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Measurement for the N3 row: batched two-view endpoint triangulation on the GPU against the reference's
-per-line cv2.triangulatePoints loop (src/seq_utils.py:113-121) on a bounded sample.  Prints one JSON line."""
+per-line cv2.triangulatePoints loop (src/seq_utils.py:113-121) on a bounded sample.  Prints one JSON line.
+Lives under tests/ because it times the oracle as its CPU arm (only test infrastructure may execute oracle/)."""
 import json
 import os
 import sys
@@ -8,8 +9,9 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
