@@ -1072,9 +1072,17 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
   return LBA_OK;
 }
 
+static int fetch_scalars(lba_ctx* c);
+
 // (2) n more PCG iterations (kernels return at once when the device-side `done` flag is set)
 static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
   for (int q = 0; q < n && sp->issued < sp->ca.max_iter; ++q, ++sp->issued) {
+    if (c->profiling) {
+      // per-class timing: look at the CG flag before every step, so that no early-exit launch (a few us each)
+      // is counted as a PCG kernel and dilutes the averages
+      CKR(fetch_scalars(c));
+      if (c->h_cgst->done) break;
+    }
     if (c->ntiles > 0) {
       c->window(c->jl.p, (size_t)c->ntiles * 6 * kTile * 8, c->l2_persist / 2);
       LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
@@ -1112,8 +1120,6 @@ static int solve_finish(lba_ctx* c, SolvePlan* sp) {
     CK(cudaMemsetAsync(&c->scal.p->dc2, 0, 16, c->stream));
   return LBA_OK;
 }
-
-static int fetch_scalars(lba_ctx* c);
 
 // the three pieces with a host check of the CG flag in between (stand-alone lba_schur_solve)
 static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
