@@ -35,7 +35,7 @@ class LbaOptions(C.Structure):
         ("lambda0", C.c_double), ("lambda_min", C.c_double), ("lambda_max", C.c_double),
         ("pcg_tol", C.c_double), ("min_ratio", C.c_double),
         ("verbose", C.c_int32), ("flags", C.c_int32), ("loss", C.c_int32), ("pad", C.c_int32),
-        ("f_scale", C.c_double),
+        ("f_scale", C.c_double), ("max_evals", C.c_int32), ("max_backtrack", C.c_int32),
     ]
 
 
@@ -45,13 +45,14 @@ LOSSES = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}  # LB
 class LbaReport(C.Structure):
     _fields_ = [
         ("iterations", C.c_int32), ("status", C.c_int32), ("n_jac", C.c_int32), ("n_res", C.c_int32),
-        ("pcg_iters_total", C.c_int32), ("chol_clamped", C.c_int32),
+        ("pcg_iters_total", C.c_int32), ("chol_clamped", C.c_int32), ("n_accepted", C.c_int32), ("pad", C.c_int32),
         ("cost_init", C.c_double), ("cost", C.c_double), ("seconds", C.c_double),
-        ("trace_len", C.c_int32),
+        ("trace_len", C.c_int32), ("trace_it", C.c_int32 * LBA_TRACE_MAX),
         ("trace_pcg", C.c_int32 * LBA_TRACE_MAX), ("trace_accepted", C.c_int32 * LBA_TRACE_MAX),
         ("trace_cost", C.c_double * LBA_TRACE_MAX), ("trace_cost_new", C.c_double * LBA_TRACE_MAX),
         ("trace_lambda", C.c_double * LBA_TRACE_MAX), ("trace_pred", C.c_double * LBA_TRACE_MAX),
         ("trace_step_norm", C.c_double * LBA_TRACE_MAX), ("trace_g_norm", C.c_double * LBA_TRACE_MAX),
+        ("trace_alpha", C.c_double * LBA_TRACE_MAX),
     ]
 
 

@@ -132,19 +132,22 @@ struct lba_ctx {
   int line_scaling_mode = 2;   // consumed by the next k_line_factor: 0 keep, 1 running max, 2 first
   DBuf<CamRec> recs, recs_new;
   DBuf<double> r, r_new, jl, jl_new, jc, jc_new, w, wk, wr;
-  DBuf<double> V, V_new, gl, gl_new, Vinv, y, Dl;
+  DBuf<double> V, V_new, gl, gl_new, Vinv, y, Dl, dl;
   DBuf<double> U, gc, Dc, Mpart, bpart, Minv, b;
   DBuf<double> cgx, cgr, cgz, cgp, tab, qpart;
   DBuf<double> cost_partial, bs_partial, cam_partial;
   DBuf<Scalars> scal;
+  DBuf<LmCtl> ctl;        // device-resident state of the running LM solve (decisions are taken on the device)
+  DBuf<LmTrace> trace;
+  LmTrace* h_trace = nullptr;   // pinned
   DBuf<CgState> cgst;
   DBuf<GridBar> gridbar;
   DBuf<double> cg_partial;
-  int cg_ctas = 1;
+  int cg_ctas = 1, cam_step_ctas = 1;
   bool use_pdl = true;     // programmatic dependent launch between kernels (LBA_PDL=0|1|2, see lba_create)
   // CTA sizes of the one-CTA-per-camera kernels: block sums (k_cam_accum / k_cam_grad) and the PCG product
   int cam_threads = 128, pcg_threads = 128, cam_threads_sel = 128;
-  DBuf<unsigned long long> gbits, gbits_new;
+  DBuf<unsigned long long> gbits, gbits_new;   // gradient inf-norm bits of the two evaluation sets
   DBuf<int> clamped;
   // pinned, device-mapped mirror of the per-iteration scalars (written by k_publish); h_* point into it
   HostMirror* h_mirror = nullptr;
@@ -154,6 +157,7 @@ struct lba_ctx {
   CgState* h_cgst = nullptr;
   unsigned long long* h_gbits = nullptr;
   int* h_clamped = nullptr;
+  LmCtl* h_ctl = nullptr;
 
   // comm
   ncclComm_t comm = nullptr;
@@ -309,6 +313,8 @@ extern "C" void lba_default_options(lba_options* o) {
   o->loss = LBA_LOSS_LINEAR;
   o->pad = 0;
   o->f_scale = 1.0;
+  o->max_evals = 0;
+  o->max_backtrack = 1;
 }
 
 extern "C" int lba_create(int device, lba_ctx** out) {
@@ -353,14 +359,20 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   memset(c->h_mirror, 0, sizeof(HostMirror));
   CK(cudaHostGetDevicePointer(&c->d_mirror, c->h_mirror, 0));
   c->h_scal = &c->h_mirror->scal; c->h_cgst = &c->h_mirror->cg;
-  c->h_gbits = &c->h_mirror->gbits; c->h_clamped = &c->h_mirror->clamped;
+  c->h_gbits = &c->h_mirror->gbits; c->h_clamped = &c->h_mirror->clamped; c->h_ctl = &c->h_mirror->ctl;
   CKR(c->scal.alloc(1));
+  CKR(c->ctl.alloc(1));
+  CKR(c->trace.alloc(1));
+  CK(cudaMemsetAsync(c->ctl.p, 0, sizeof(LmCtl), c->stream));
+  CK(cudaHostAlloc(&c->h_trace, sizeof(LmTrace), cudaHostAllocDefault));
   CKR(c->cgst.alloc(1));
   CKR(c->gridbar.alloc(1));
   CKR(c->cg_partial.alloc(2 * kCgMaxCtas));
   CK(cudaMemsetAsync(c->gridbar.p, 0, sizeof(GridBar), c->stream));
   CKR(c->gbits.alloc(1));
   CKR(c->gbits_new.alloc(1));
+  CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
+  CK(cudaMemsetAsync(c->gbits_new.p, 0, 8, c->stream));
   CKR(c->clamped.alloc(1));
   CKR(c->tickets.alloc(8));
   CK(cudaMemsetAsync(c->tickets.p, 0, 32, c->stream));
@@ -409,6 +421,7 @@ extern "C" int lba_destroy(lba_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   lba_comm_destroy(ctx);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
+  if (ctx->h_trace) cudaFreeHost(ctx->h_trace);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -532,7 +545,7 @@ static int reduce_finish(lba_ctx* c, int region, double* local, size_t n) {
   }
   c->pre(LBA_K_COMM);
   launch_kernel(c, k_peer_reduce<false>, dim3(grid), dim3(512), 0, c->peer_args, region, peer_slot_off(c, region, seq), n, seq,
-                (const double*)nullptr, local, (unsigned long long*)nullptr);
+                (const double*)nullptr, local, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -545,26 +558,27 @@ static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRed
   c->pre(LBA_K_COMM);
   if (op == ncclMax)
     launch_kernel(c, k_peer_reduce<true>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr);
+                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
   else
     launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr);
+                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
 static int allreduce_sum(lba_ctx* c, double* buf, size_t n) { return allreduce(c, buf, n, ncclDouble, ncclSum); }
-// the end-of-iteration scalars (sum) and, when `gbits` is given, the gradient inf-norm bits (max) in ONE exchange
-static int allreduce_scalars(lba_ctx* c, double* buf, size_t n, unsigned long long* gbits) {
+// the end-of-trial scalars (sum) and the gradient inf-norm bits (max) in ONE exchange.  With the peer transport
+// the kernel picks the word of the current evaluation set from the control block; the NCCL fallback reduces both.
+static int allreduce_scalars(lba_ctx* c, double* buf, size_t n, const LmCtl* ctl) {
   if (c->world <= 1) return LBA_OK;
-  if (!gbits) return allreduce_sum(c, buf, n);
   if (n > 8 || !peer_fits(c, kRgnS, 10)) {
     CKR(allreduce_sum(c, buf, n));
-    return allreduce(c, gbits, 1, ncclUint64, ncclMax);
+    CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
+    return allreduce(c, c->gbits_new.p, 1, ncclUint64, ncclMax);
   }
   const unsigned long long seq = ++c->rgn_seq[kRgnS];
   c->pre(LBA_K_COMM);
   launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                (const double*)buf, buf, gbits);
+                (const double*)buf, buf, c->gbits.p, c->gbits_new.p, ctl);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -876,13 +890,15 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->jl_new.alloc(6 * M)); CKR(ctx->jc_new.alloc(6 * (size_t)m));
   CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M)); CKR(ctx->dense_tmp.alloc((size_t)m));
   CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->V_new.alloc(NL * 21)); CKR(ctx->gl_new.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
-  CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6));
+  CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6)); CKR(ctx->dl.alloc(NL * 6 + 2));
   CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
   CKR(ctx->Mpart.alloc(NC * 39)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
   CKR(ctx->cgx.alloc(NC * 6)); CKR(ctx->cgr.alloc(NC * 6)); CKR(ctx->cgz.alloc(NC * 6)); CKR(ctx->cgp.alloc(NC * 6));
   CKR(ctx->tab.alloc(NC * 6)); CKR(ctx->qpart.alloc(NC * 6));
   CKR(ctx->cost_partial.alloc(NG)); CKR(ctx->bs_partial.alloc(NG * 4));
-  CKR(ctx->cam_partial.alloc(2 * (size_t)cdiv(std::max(nc, 1), kCamStepThreads)));
+  // k_cam_step: one thread per camera; in a retry pass its CTAs also rebuild the line side of the trial point
+  ctx->cam_step_ctas = std::max(cdiv(std::max(nc, 1), kCamStepThreads), std::min(cdiv((long long)nl * 6, kCamStepThreads * 8), 2 * ctx->n_sm));
+  CKR(ctx->cam_partial.alloc(2 * (size_t)ctx->cam_step_ctas));
   lap("state buffers");
   ctx->have_problem = true;
   if (ctx->launch_err) return LBA_ERR_CUDA;
@@ -894,13 +910,19 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
 static inline double* gc_of(lba_ctx* c) { return c->U.p + (size_t)c->nc * 21; }
 static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc * 21; }
 
-static EvalArgs eval_args(lba_ctx* c, const CamRec* recs, const double* pts, double* r) {
+// Kernel arguments name BOTH evaluation sets (index 0: the resident one, 1: the "_new" buffers); the kernels
+// pick one from the device control block, or set `which` when no LM solve is running (ctl == NULL).
+static EvalArgs eval_args(lba_ctx* c, const LmCtl* ctl, int which) {
   EvalArgs a;
   a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3; a.stg_bufs = 1;
-  a.tidx = c->tidx.p; a.cst = c->cst.p; a.recs = recs; a.pts = pts;
-  a.r = r; a.jl = c->jl.p; a.jc = c->jc.p; a.V = c->V.p; a.gl = c->gl.p;
+  a.tidx = c->tidx.p; a.cst = c->cst.p;
+  a.recs = dual<const CamRec>(c->recs.p, c->recs_new.p);
+  a.pts = dual<const double>(c->pts.p, c->pts_new.p);
+  a.r = dual(c->r.p, c->r_new.p); a.jl = dual(c->jl.p, c->jl_new.p); a.jc = dual(c->jc.p, c->jc_new.p);
+  a.V = dual(c->V.p, c->V_new.p); a.gl = dual(c->gl.p, c->gl_new.p); a.gbits = dual(c->gbits.p, c->gbits_new.p);
+  a.ctl = ctl; a.which = which;
   a.cost_partial = c->cost_partial.p;
-  a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost; a.gbits = c->gbits.p;
+  a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost;
   a.loss = c->loss; a.f_scale = c->f_scale;
   return a;
 }
@@ -928,10 +950,10 @@ static int store_state(lba_ctx* c, double* cams_api, double* pts_api) {
   return LBA_OK;
 }
 
-// residual-only pass at (recs, pts) -> r_out, scal.cost (local sum; callers all-reduce)
-static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, double* r_out) {
+// residual-only pass over evaluation set `which` (API calls: ctl == NULL) -> r of that set, scal.cost (local sum)
+static int run_residual(lba_ctx* c, const LmCtl* ctl, int which) {
   if (c->ntiles > 0) {
-    EvalArgs a = eval_args(c, recs, pts, r_out);
+    EvalArgs a = eval_args(c, ctl, which);
     a.nstages = c->eval_stages_r;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 2, true>), c->grid_eval_r, 2 * kTile, c->smem_eval_r, a);
     else LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 1, false>), c->grid_eval_r, kTile, c->smem_eval_r, a);
@@ -941,16 +963,14 @@ static int run_residual(lba_ctx* c, const CamRec* recs, const double* pts, doubl
   return LBA_OK;
 }
 
-// fused residual + Jacobian + line blocks (+ line part of the gradient norm) -> scal.cost and either
-// the resident evaluation set (r, jl, jc, V, gl, gbits) or, speculatively at the trial point, the
-// "_new" set that is swapped in when the step is accepted
-static int run_jacobian(lba_ctx* c, bool into_new) {
-  unsigned long long* gb = into_new ? c->gbits_new.p : c->gbits.p;
-  CK(cudaMemsetAsync(gb, 0, 8, c->stream));
+// fused residual + Jacobian + line blocks (+ line part of the gradient norm) of evaluation set `which` (relative
+// to the control block's current set when ctl is given) -> scal.cost and r, jl, jc, V, gl, gbits of that set.
+// The gradient-norm word of the set must be zero before: the API path clears it here, inside the LM loop
+// k_cam_step clears the trial set's word.
+static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
+  if (!ctl) CK(cudaMemsetAsync(which ? c->gbits_new.p : c->gbits.p, 0, 8, c->stream));
   if (c->ntiles > 0) {
-    EvalArgs a = into_new ? eval_args(c, c->recs_new.p, c->pts_new.p, c->r_new.p) : eval_args(c, c->recs.p, c->pts.p, c->r.p);
-    if (into_new) { a.jl = c->jl_new.p; a.jc = c->jc_new.p; a.V = c->V_new.p; a.gl = c->gl_new.p; }
-    a.gbits = gb;
+    EvalArgs a = eval_args(c, ctl, which);
     a.nstages = c->eval_stages_j;
     a.stg_bufs = c->eval_stg_bufs;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
@@ -958,7 +978,7 @@ static int run_jacobian(lba_ctx* c, bool into_new) {
   } else {
     CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
   }
-  if (!into_new) {
+  if (!ctl && which == 0) {
     c->pending_first = !c->have_scaling;
     c->line_scaling_mode = c->pending_first ? 2 : 1;
     c->have_eval = true;
@@ -970,37 +990,32 @@ static int run_jacobian(lba_ctx* c, bool into_new) {
 template <typename T>
 static inline void swap_buf(DBuf<T>& a, DBuf<T>& b) { std::swap(a.p, b.p); std::swap(a.n, b.n); }
 
-// the trial point becomes the current point: parameters, camera records and the evaluation set
-static void accept_candidate(lba_ctx* c, bool have_new_eval) {
+// after an LM solve that ended with set 1 current: make the host's names agree with the device again
+static void swap_sets(lba_ctx* c) {
   swap_buf(c->cams, c->cams_new); swap_buf(c->pts, c->pts_new);
   swap_buf(c->recs, c->recs_new); swap_buf(c->Gm, c->Gm_new);
-  if (have_new_eval) {
-    swap_buf(c->r, c->r_new); swap_buf(c->jl, c->jl_new); swap_buf(c->jc, c->jc_new);
-    swap_buf(c->V, c->V_new); swap_buf(c->gl, c->gl_new); swap_buf(c->gbits, c->gbits_new);
-    c->pending_first = false;
-    c->line_scaling_mode = 1;
-    c->have_eval = true;
-    c->have_blocks = false;
-  }
+  swap_buf(c->r, c->r_new); swap_buf(c->jl, c->jl_new); swap_buf(c->jc, c->jc_new);
+  swap_buf(c->V, c->V_new); swap_buf(c->gl, c->gl_new); swap_buf(c->gbits, c->gbits_new);
 }
 
-// camera side of the normal equations: diag(U_c) (or the full blocks) and g_c, all-reduced; camera
-// scaling; camera part of the gradient inf-norm
+// camera side of the normal equations (stand-alone API calls): diag(U_c) (or the full blocks) and g_c,
+// all-reduced; camera scaling; camera part of the gradient inf-norm
 static int run_blocks(lba_ctx* c, bool full) {
   if (c->nc > 0) {
     const size_t n27 = (size_t)c->nc * 27;
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
     if (full) {
-      // API path: the complete blocks, reduced into U | gc by a separate reduce
+      // the complete blocks, reduced into U | gc by a separate reduce
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
       c->cam_threads_sel = c->cam_threads;
-      LAUNCH_CAM2(c, LBA_K_CAM_BLOCKS, k_cam_accum, false, c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-                  (const double*)nullptr, c->r.p, (const double*)nullptr, out, out + (size_t)c->nc * 21,
-                  (double*)nullptr, c->nc, pl);
+      LAUNCH_CAM2(c, LBA_K_CAM_BLOCKS, k_cam_accum, false, c->nc, c->cam_ptr.p, c->cam_perm.p,
+                  dual<const double>(c->jc.p, c->jc_new.p), (const double*)nullptr, c->r.p,
+                  dual<const double>(nullptr, nullptr), out, out + (size_t)c->nc * 21, (double*)nullptr, c->nc, pl,
+                  (const LmCtl*)nullptr);
       CKR(reduce_finish(c, kRgnU, c->U.p, n27));
     } else {
-      // LM path: diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
+      // diag(U) and g_c only (zero-copy producer + one reduce kernel with the peer transport)
       double* out = reduce_target(c, kRgnU, c->U.p, n27);
       if (out != c->U.p) CK(cudaMemsetAsync(out, 0, n27 * 8, c->stream));   // k_cam_grad writes the diagonal only
       c->cam_threads_sel = c->cam_threads;
@@ -1018,23 +1033,31 @@ static int run_blocks(lba_ctx* c, bool full) {
 }
 
 // ---- the damped solve, in three stream-ordered pieces -------------------------------------------
+// With `ctl` (the LM loop) the kernels take the damping, the current evaluation set and whether to run at all
+// from the device control block; without it (lba_schur_solve) from the arguments.
 struct SolvePlan {
   CgArgs ca;
   LinePassArgs la;
   int issued = 0;
 };
 
-// (1) Schur elimination set-up for damping lam and the first CG state
-static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, SolvePlan* sp, bool with_grad = false) {
+// (1) Schur elimination set-up for damping lam and the first CG state.  with_grad: the camera gradient and
+// Marquardt scaling of the evaluation set ride on the preconditioner pass (one read of jc).
+static int solve_setup(lba_ctx* c, const LmCtl* ctl, double lam, double pcg_tol, int pcg_max_iter, SolvePlan* sp, bool with_grad) {
   const int nc = c->nc, nl = c->nl;
   if (nl > 0) {
-    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, kLfLines), kLfLines, nl, lam, c->V.p, c->Dl.p, c->gl.p, c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode);
+    LAUNCH(c, LBA_K_LINE_FACTOR, k_line_factor, cdiv(nl, kLfLines), kLfLines, nl, lam, dual<const double>(c->V.p, c->V_new.p),
+           c->Dl.p, dual<const double>(c->gl.p, c->gl_new.p), c->Vinv.p, c->y.p, c->clamped.p, c->line_scaling_mode, ctl);
     c->line_scaling_mode = 0;
   }
   LinePassArgs& la = sp->la;
-  la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.tidx = c->tidx.p; la.jl = c->jl.p; la.pts = c->pts.p; la.tab = c->tab.p; la.Vinv = c->Vinv.p;
-  la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p; la.gl = c->gl.p; la.r = c->r.p; la.pts_new = c->pts_new.p;
-  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &c->scal.p->rjd; la.st = c->cgst.p;
+  la.Mp = c->Mp; la.ntiles = c->ntiles; la.lmax = c->lmax; la.tidx = c->tidx.p;
+  la.jl = dual<const double>(c->jl.p, c->jl_new.p); la.pts = dual(c->pts.p, c->pts_new.p);
+  la.tab = c->tab.p; la.Vinv = c->Vinv.p;
+  la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p;
+  la.gl = dual<const double>(c->gl.p, c->gl_new.p); la.r = dual<const double>(c->r.p, c->r_new.p);
+  la.dl = c->dl.p; la.alpha = 1.0;
+  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &c->scal.p->rjd; la.st = c->cgst.p; la.ctl = ctl;
   if (c->ntiles > 0)
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
@@ -1046,24 +1069,26 @@ static int solve_setup(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter,
     memset(&pl, 0, sizeof pl);
     double* out = reduce_target(c, kRgnM, c->Mpart.p, nred);
     c->cam_threads_sel = c->cam_threads;
+    const Dual<const double> jc2 = dual<const double>(c->jc.p, c->jc_new.p);
     if (with_grad) {
-      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, true, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-                  (const double*)c->wk.p, c->wr.p, (const double*)c->r.p, out, out + (size_t)nc * 21,
-                  out + (size_t)nc * 27, nc, pl);
+      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, true, nc, c->cam_ptr.p, c->cam_perm.p, jc2,
+                  (const double*)c->wk.p, c->wr.p, dual<const double>(c->r.p, c->r_new.p), out, out + (size_t)nc * 21,
+                  out + (size_t)nc * 27, nc, pl, ctl);
     } else {
-      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, false, nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p,
-                  (const double*)c->wk.p, c->wr.p, (const double*)nullptr, out, out + (size_t)nc * 21,
-                  (double*)nullptr, nc, pl);
+      LAUNCH_CAM2(c, LBA_K_CAM_PRECOND, k_cam_accum, false, nc, c->cam_ptr.p, c->cam_perm.p, jc2,
+                  (const double*)c->wk.p, c->wr.p, dual<const double>(nullptr, nullptr), out, out + (size_t)nc * 21,
+                  (double*)nullptr, nc, pl, ctl);
     }
     CKR(reduce_finish(c, kRgnM, c->Mpart.p, nred));
     LAUNCH(c, LBA_K_CAM_PRECOND, k_cam_finish, cdiv(nc, 128), 128, nc, lam, c->Mpart.p, c->Dc.p, c->gc.p, bpart_of(c),
-           with_grad ? (const double*)(c->Mpart.p + (size_t)nc * 27) : (const double*)nullptr, c->gbits.p, c->Minv.p,
-           c->b.p, c->clamped.p, pl);
+           with_grad ? (const double*)(c->Mpart.p + (size_t)nc * 27) : (const double*)nullptr,
+           dual(c->gbits.p, c->gbits_new.p), c->Minv.p, c->b.p, c->clamped.p, pl, ctl);
     if (with_grad) c->have_scaling = true;   // the caller all-reduces gbits (max) together with its next scalars
   }
   CgArgs& ca = sp->ca;
   ca.nc = nc; ca.lam = lam; ca.tol2 = pcg_tol * pcg_tol; ca.max_iter = pcg_max_iter;
-  ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = c->Gm.p; ca.cams = c->cams.p; ca.b = c->b.p; ca.qpart = c->qpart.p;
+  ca.Dc = c->Dc.p; ca.Minv = c->Minv.p; ca.Gm = dual<const double>(c->Gm.p, c->Gm_new.p);
+  ca.cams = dual<const double>(c->cams.p, c->cams_new.p); ca.ctl = ctl; ca.b = c->b.p; ca.qpart = c->qpart.p;
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
   ca.partial = c->cg_partial.p; ca.gb = c->gridbar.p;
   memset(&ca.pl, 0, sizeof ca.pl);
@@ -1096,12 +1121,21 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
       double* out = fused_link(c, kRgnQ, n6, c->qpart.p, &pl);
       c->window(c->jc.p, (size_t)c->m * 48, c->l2_persist / 2);
       c->cam_threads_sel = c->pcg_threads;
-      LAUNCH_CAM(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), c->nc, c->cam_ptr.p, c->cam_perm.p, c->jc.p, c->w.p, out, c->cgst.p, pl);
+      LAUNCH_CAM(c, LBA_K_PCG_CAM, k_pcg_cam, std::min(c->nc, 8 * c->n_sm), c->nc, c->cam_ptr.p, c->cam_perm.p,
+                 dual<const double>(c->jc.p, c->jc_new.p), c->w.p, out, c->cgst.p, pl, sp->la.ctl);
       if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
     sp->ca.pl = pl;
     LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
   }
+  return LBA_OK;
+}
+
+// the trial point on the camera side (and, in a retry pass of the LM loop, on the line side too)
+static int launch_cam_step(lba_ctx* c, const LmCtl* ctl) {
+  LAUNCH(c, LBA_K_MISC, k_cam_step, c->cam_step_ctas, kCamStepThreads, c->nc, dual(c->cams.p, c->cams_new.p), c->cgx.p,
+         dual(c->recs.p, c->recs_new.p), dual(c->Gm.p, c->Gm_new.p), 1.0, dual(c->gbits.p, c->gbits_new.p),
+         (size_t)c->nl * 6, dual(c->pts.p, c->pts_new.p), c->dl.p, c->cam_partial.p, c->tickets.p + 2, &c->scal.p->dc2, ctl);
   return LBA_OK;
 }
 
@@ -1113,19 +1147,14 @@ static int solve_finish(lba_ctx* c, SolvePlan* sp) {
     if (c->nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
   }
-  if (c->nc > 0)
-    LAUNCH(c, LBA_K_MISC, k_cam_step, cdiv(c->nc, kCamStepThreads), kCamStepThreads, c->nc, c->cams.p, c->cgx.p, c->cams_new.p,
-           c->recs_new.p, c->Gm_new.p, c->cam_partial.p, c->tickets.p + 2, &c->scal.p->dc2);
-  else
-    CK(cudaMemsetAsync(&c->scal.p->dc2, 0, 16, c->stream));
-  return LBA_OK;
+  return launch_cam_step(c, sp->la.ctl);
 }
 
 // the three pieces with a host check of the CG flag in between (stand-alone lba_schur_solve)
 static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, int* chunk_hint, int* iters_out,
                      int* breakdown_out) {
   SolvePlan sp;
-  CKR(solve_setup(c, lam, pcg_tol, pcg_max_iter, &sp));
+  CKR(solve_setup(c, nullptr, lam, pcg_tol, pcg_max_iter, &sp, false));
   int chunk = std::max(1, std::min(*chunk_hint, pcg_max_iter));
   while (true) {
     CKR(solve_iterate(c, &sp, chunk));
@@ -1139,13 +1168,13 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
   return solve_finish(c, &sp);
 }
 
-// The host's one look per iteration at the device scalars (LM scalars, CG state, gradient-norm bits, clamp count):
+// The host's look at the device scalars (LM control block, LM scalars, CG state, gradient-norm bits, clamp count):
 // k_publish writes them into mapped pinned memory followed by a sequence number; the host spins on that word
 // and only falls back to the stream when the device reports an error.
 static int fetch_scalars(lba_ctx* c) {
   const unsigned long long seq = ++c->publish_seq;
-  LAUNCH(c, LBA_K_MISC, k_publish, 1, 32, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p,
-         (const unsigned long long*)c->gbits.p, (const int*)c->clamped.p, c->d_mirror, seq);
+  LAUNCH(c, LBA_K_MISC, k_publish, 1, 32, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p, (const LmCtl*)c->ctl.p,
+         dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), (const int*)c->clamped.p, c->d_mirror, seq);
   volatile unsigned long long* flag = &c->h_mirror->seq;
   for (unsigned spins = 0; *flag != seq; ++spins) {
     if ((spins & 0x3ff) == 0x3ff) {
@@ -1163,12 +1192,6 @@ static int fetch_scalars(lba_ctx* c) {
   std::atomic_thread_fence(std::memory_order_acquire);
   if (c->launch_err) return LBA_ERR_CUDA;
   return LBA_OK;
-}
-
-static double gnorm_host(lba_ctx* c) {
-  double g;
-  memcpy(&g, c->h_gbits, 8);
-  return g;
 }
 
 static int export_residuals(lba_ctx* c, const double* r_dev, double* out) {
@@ -1373,7 +1396,7 @@ extern "C" int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_v
 extern "C" int lba_residuals(lba_ctx* ctx, const double* cams, const double* pts, double* residuals, double* cost) {
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CKR(load_state(ctx, cams, pts));
-  CKR(run_residual(ctx, ctx->recs.p, ctx->pts.p, ctx->r.p));
+  CKR(run_residual(ctx, nullptr, 0));
   CKR(allreduce_sum(ctx, &ctx->scal.p->cost, 1));
   CKR(export_residuals(ctx, ctx->r.p, residuals));
   CKR(fetch_scalars(ctx));
@@ -1386,7 +1409,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CKR(load_state(ctx, cams, pts));
   ctx->have_scaling = false;
-  CKR(run_jacobian(ctx, false));
+  CKR(run_jacobian(ctx, nullptr, 0));
   CKR(export_residuals(ctx, ctx->r.p, residuals));
   const int m = ctx->m;
   if (m > 0 && (jcam || jline)) {
@@ -1435,12 +1458,27 @@ extern "C" int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int3
 }
 
 // ---- C ABI: the LM loop ---------------------------------------------------------------------------
+// Every decision of the loop (gain ratio, accept / reject, damping, step length, retry, termination) is taken on the
+// device by k_lm_decide; the kernels of a pass read the damping, the step length and which evaluation set is current
+// from the control block.  The host only enqueues passes: one host look per pass in this driver (it needs to know
+// whether the PCG steps it enqueued were enough).
+static int enqueue_trial_tail(lba_ctx* c, const LmCtl* ctl) {
+  // trial evaluation WITH its Jacobian into the other evaluation set (it becomes the current one when accepted)
+  CKR(run_jacobian(c, ctl, 1));
+  // cost, rjd, jd2, dl2, x2_lines are contiguous; the gradient norm of the state the solve started from rides along
+  CKR(allreduce_scalars(c, &c->scal.p->cost, 5, ctl));
+  LAUNCH(c, LBA_K_MISC, k_lm_decide, 1, 32, c->ctl.p, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p,
+         dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), c->trace.p);
+  return LBA_OK;
+}
+
 extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, const lba_options* opts_in,
                             lba_report* rep, double* residuals) {
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   lba_options o;
   if (opts_in) o = *opts_in; else lba_default_options(&o);
-  if (o.max_iter < 0 || o.pcg_max_iter < 1 || !(o.lambda0 > 0.0) || o.loss < 0 || o.loss > LBA_LOSS_ARCTAN || !(o.f_scale > 0.0))
+  if (o.max_iter < 0 || o.pcg_max_iter < 1 || !(o.lambda0 > 0.0) || o.loss < 0 || o.loss > LBA_LOSS_ARCTAN || !(o.f_scale > 0.0) ||
+      o.max_evals < 0 || o.max_backtrack < 0)
     return fail(LBA_ERR_ARG, "bad options");
   const auto t0 = std::chrono::steady_clock::now();
   lba_report local;
@@ -1452,111 +1490,80 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   c->loss = o.loss; c->f_scale = o.f_scale;
   struct LossGuard { lba_ctx* c; ~LossGuard() { c->loss = 0; c->f_scale = 1.0; } } loss_guard{c};
   CK(cudaMemsetAsync(c->clamped.p, 0, 4, c->stream));
-  CKR(run_jacobian(c, false));
-  rep->n_jac = 1;
+  // the camera scaling is a running maximum that every solve set-up refreshes (k_cam_finish): start it from zero
+  if (c->nc > 0) CK(cudaMemsetAsync(c->Dc.p, 0, (size_t)c->nc * 48, c->stream));
+  CKR(run_jacobian(c, nullptr, 0));
   CKR(allreduce_sum(c, &c->scal.p->cost, 1));
-  CKR(run_blocks(c, false));
+  LmCtl init;
+  memset(&init, 0, sizeof init);
+  init.ftol = o.ftol; init.xtol = o.xtol; init.gtol = o.gtol; init.lambda_min = o.lambda_min; init.lambda_max = o.lambda_max;
+  init.min_ratio = o.min_ratio; init.max_iter = o.max_iter; init.max_evals = o.max_evals; init.pcg_max_iter = o.pcg_max_iter;
+  init.max_backtrack = o.max_backtrack; init.lam = o.lambda0;
+  LAUNCH(c, LBA_K_MISC, k_lm_init, 1, 32, c->ctl.p, init, (const Scalars*)c->scal.p);
+  const LmCtl* ctl = c->ctl.p;
   CKR(fetch_scalars(c));
-  double cost = c->h_scal->cost;
-  rep->cost_init = cost;
-  if (!std::isfinite(cost)) return fail(LBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
-  double g_norm = gnorm_host(c);
-  double lam = o.lambda0, nu = 2.0;
-  int status = 0, it = 0, chunk_hint = 8;
-  const bool speculative = !(o.flags & 1);
-  if (o.verbose >= 2)
-    printf("   Iteration     Total nfev        Cost      Cost reduction    Step norm     Optimality   \n");
-  // One host synchronisation per LM iteration: the whole iteration (elimination, a predicted number
-  // of PCG steps, back-substitution, the trial evaluation -- speculatively with its Jacobian -- and,
-  // after an accepted step, the camera blocks of the next one) is enqueued before the host looks at
-  // any scalar.  The gradient norm of the state the solve started from arrives with the same copy;
-  // if it is already below gtol the enqueued work is discarded (same decisions as checking first).
-  bool g_pending = false;   // g_norm of the current state is still in flight
-  while (it < o.max_iter) {
-    if (!g_pending && g_norm < o.gtol) { status = 1; break; }
+  rep->cost_init = c->h_ctl->cost;
+  if (c->h_ctl->status == -5) return fail(LBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+  int chunk_hint = 8;
+  while (!c->h_ctl->done) {
+    const bool solve = c->h_ctl->need_solve != 0;
     SolvePlan sp;
-    // after an accepted step the camera gradient / scaling of the new state ride on the preconditioner pass
-    CKR(solve_setup(c, lam, o.pcg_tol, o.pcg_max_iter, &sp, g_pending));
+    if (solve) CKR(solve_setup(c, ctl, 0.0, o.pcg_tol, o.pcg_max_iter, &sp, true));
     int launch = std::max(1, std::min(chunk_hint, o.pcg_max_iter));
-    bool trial_done = false, g_reduced = false;
     while (true) {
-      CKR(solve_iterate(c, &sp, launch));
-      CKR(solve_finish(c, &sp));
-      if (speculative) CKR(run_jacobian(c, true)); else CKR(run_residual(c, c->recs_new.p, c->pts_new.p, c->r_new.p));
-      // cost, rjd, jd2, dl2, x2_lines are contiguous; the gradient norm of the state this solve started from
-      // (camera part written by its set-up) goes out in the same exchange, once
-      CKR(allreduce_scalars(c, &c->scal.p->cost, 5, (g_pending && !g_reduced) ? c->gbits.p : nullptr));
-      g_reduced = true;
+      if (solve) {
+        CKR(solve_iterate(c, &sp, launch));
+        CKR(solve_finish(c, &sp));
+      } else {
+        CKR(launch_cam_step(c, ctl));   // same direction, shorter step: both halves of the trial point
+      }
+      CKR(enqueue_trial_tail(c, ctl));
       CKR(fetch_scalars(c));
-      trial_done = c->h_cgst->done || sp.issued >= o.pcg_max_iter;
-      if (trial_done) break;
+      if (!c->h_ctl->cg_short) break;
       launch = 4;   // the prediction was short: more PCG steps, then redo the (cheap to discard) tail
     }
-    if (g_pending) {
-      g_norm = gnorm_host(c);
-      g_pending = false;
-      if (g_norm < o.gtol) { status = 1; break; }
-    }
-    const int q = c->h_cgst->k;
-    chunk_hint = q + 1;
-    rep->pcg_iters_total += q;
-    if (speculative) rep->n_jac += 1; else rep->n_res += 1;
-    const Scalars s = *c->h_scal;
-    const double cost_new = s.cost;
-    const double pred = -s.rjd - 0.5 * s.jd2;
-    const double step_norm = std::sqrt(s.dc2 + s.dl2);
-    const double x_norm = std::sqrt(s.x2_cams + s.x2_lines);
-    const double actual = cost - cost_new;
-    const bool finite = std::isfinite(cost_new);
-    const double ratio = (finite && pred > 0.0) ? actual / pred : -1.0;
-    const bool accepted = finite && ratio > o.min_ratio;
-    const bool ftol_ok = finite && (actual < o.ftol * cost) && (ratio > 0.25);
-    const bool xtol_ok = step_norm < o.xtol * (o.xtol + x_norm);
-    if (it < LBA_TRACE_MAX) {
-      rep->trace_pcg[it] = q; rep->trace_accepted[it] = accepted; rep->trace_cost[it] = cost;
-      rep->trace_cost_new[it] = cost_new; rep->trace_lambda[it] = lam; rep->trace_pred[it] = pred;
-      rep->trace_step_norm[it] = step_norm; rep->trace_g_norm[it] = g_norm;
-      rep->trace_len = it + 1;
-    }
-    if (o.verbose >= 2)
-      printf("   %6d        %6d        %.4e      %9.2e       %9.2e      %9.2e    (lam %.1e pcg %d %s)\n", it,
-             rep->n_jac + rep->n_res, accepted ? cost_new : cost, accepted ? actual : 0.0, step_norm, g_norm, lam, q,
-             accepted ? "ok" : "rej");
-    ++it;
-    if (accepted) {
-      accept_candidate(c, speculative);
-      cost = cost_new;
-      if (!speculative) { CKR(run_jacobian(c, false)); rep->n_jac += 1; }
-      g_pending = true;   // camera gradient / scaling of the new state: computed by the next solve_setup, read at its sync
-      // damping update from the gain ratio; thresholds shifted down because the residual is itself a
-      // squared distance, so good Gauss-Newton steps have ratios ~0.3-0.5 (same rule in the oracle)
-      const double fac = ratio >= 0.7 ? 1.0 / 3.0 : (ratio >= 0.4 ? 1.0 / 1.5 : (ratio >= 0.15 ? 1.0 : 2.0));
-      lam = std::min(std::max(lam * fac, o.lambda_min), o.lambda_max);
-      nu = 2.0;
-    } else {
-      lam = std::min(lam * nu, o.lambda_max);
-      nu *= 2.0;
-    }
-    if (ftol_ok && xtol_ok) status = 4;
-    else if (ftol_ok) status = 2;
-    else if (xtol_ok) status = 3;
-    if (status) break;
+    chunk_hint = c->h_ctl->q_last + 1;
   }
-  if (g_pending) { CKR(run_blocks(c, false)); CKR(fetch_scalars(c)); g_norm = gnorm_host(c); }
-  rep->iterations = it;
-  rep->status = status;
-  rep->cost = cost;
+  const LmCtl fin = *c->h_ctl;
+  if (fin.cur) swap_sets(c);
+  c->have_eval = true; c->have_blocks = false; c->have_scaling = true; c->pending_first = false; c->line_scaling_mode = 1;
+  rep->iterations = fin.it;
+  rep->status = fin.status;
+  rep->cost = fin.cost;
+  rep->n_jac = fin.evals;
+  rep->n_res = 0;
+  rep->n_accepted = fin.n_acc;
+  rep->pcg_iters_total = fin.pcg_total;
   rep->chol_clamped = *c->h_clamped;
+  CK(cudaMemcpyAsync(c->h_trace, c->trace.p, sizeof(LmTrace), cudaMemcpyDeviceToHost, c->stream));
   CKR(store_state(c, cams_api, pts_api));
   if (c->loss != 0 && residuals) {
     // with a robust loss the resident residuals are the rescaled ones; the caller gets fun itself (res.fun)
     c->loss = 0;
-    CKR(run_residual(c, c->recs.p, c->pts.p, c->r_new.p));
-    CKR(export_residuals(c, c->r_new.p, residuals));
-  } else {
-    CKR(export_residuals(c, c->r.p, residuals));
+    CKR(run_residual(c, nullptr, 0));
+    c->have_eval = false;
   }
+  CKR(export_residuals(c, c->r.p, residuals));
   CK(cudaStreamSynchronize(c->stream));
+  rep->trace_len = fin.trace_len;
+  for (int k = 0; k < fin.trace_len; ++k) {
+    const LmTrace& t = *c->h_trace;
+    rep->trace_it[k] = t.it[k]; rep->trace_pcg[k] = t.pcg[k]; rep->trace_accepted[k] = t.accepted[k];
+    rep->trace_cost[k] = t.cost[k]; rep->trace_cost_new[k] = t.cost_new[k]; rep->trace_lambda[k] = t.lam[k];
+    rep->trace_pred[k] = t.pred[k]; rep->trace_step_norm[k] = t.step_norm[k]; rep->trace_g_norm[k] = t.g_norm[k];
+    rep->trace_alpha[k] = t.alpha[k];
+  }
+  if (o.verbose >= 2) {
+    // scipy-style table (least_squares verbose=2, the reference prints it at bundle_adjustment.py:319), one row per trial
+    printf("   Iteration     Total nfev        Cost      Cost reduction    Step norm     Optimality   \n");
+    for (int k = 0; k < rep->trace_len; ++k) {
+      const bool acc = rep->trace_accepted[k] != 0;
+      printf("   %6d        %6d        %.4e      %9.2e       %9.2e      %9.2e    (lam %.1e alpha %.3f pcg %d %s)\n",
+             rep->trace_it[k], k + 2, acc ? rep->trace_cost_new[k] : rep->trace_cost[k],
+             acc ? rep->trace_cost[k] - rep->trace_cost_new[k] : 0.0, rep->trace_step_norm[k], rep->trace_g_norm[k],
+             rep->trace_lambda[k], rep->trace_alpha[k], rep->trace_pcg[k], acc ? "ok" : "rej");
+    }
+  }
   rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return c->launch_err ? LBA_ERR_CUDA : LBA_OK;
 }

@@ -36,6 +36,7 @@
 #include "lba_geometry.cuh"
 #include "lba_triangulate.cuh"
 #include "lba_tracks.cuh"
+#include "lba_policy.cuh"
 #include <stddef.h>
 #include <stdint.h>
 
@@ -69,6 +70,21 @@ static_assert(sizeof(TileIdx) % 16 == 0 && offsetof(TileIdx, cam) % 16 == 0 && o
 __host__ __device__ inline size_t tm_index(int nk, int k, size_t slot) {
   return ((slot / kTile) * nk + k) * kTile + (slot % kTile);
 }
+
+// The LM loop keeps TWO evaluation sets (parameters, camera records, residuals, Jacobian, line blocks); which one
+// is current is decided on the device (LmCtl::cur, flipped by k_lm_decide when a step is accepted), so every
+// kernel of the loop gets both pointers and picks one after reading the control block.
+template <typename T>
+struct Dual {
+  T* p[2];
+  __host__ __device__ T* sel(int i) const { return i ? p[1] : p[0]; }
+};
+template <typename T>
+__host__ inline Dual<T> dual(T* a, T* b) { Dual<T> d; d.p[0] = a; d.p[1] = b; return d; }
+// kernels of the solve part run only in passes that solve; kernels of the trial part until the loop is done
+__device__ __forceinline__ bool ctl_skip_solve(const LmCtl* ctl) { return ctl && (ctl->done || !ctl->need_solve); }
+__device__ __forceinline__ bool ctl_skip_trial(const LmCtl* ctl) { return ctl && ctl->done; }
+__device__ __forceinline__ int ctl_cur(const LmCtl* ctl) { return ctl ? ctl->cur : 0; }
 
 // ---- bulk-async (TMA) + mbarrier primitives ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -408,17 +424,20 @@ struct EvalArgs {
   int stg_bufs;            // 1 or 2 staging buffers for the per-line sums (2: one barrier per tile instead of two)
   const TileIdx* tidx;     // [ntiles]
   const double* cst;       // [ntiles][9][256]
-  const CamRec* recs;
-  const double* pts;       // [nl][6]
-  double* r;               // [Mp]
-  double* jl;              // [ntiles][6][256]
-  double* jc;              // [m][6] camera order, one 48 B record per observation
-  double* V;               // [nl][21]
-  double* gl;              // [nl][6]
+  // the two evaluation sets; the kernel works on set (ctl ? ctl->cur ^ which : which)
+  Dual<const CamRec> recs;
+  Dual<const double> pts;  // [nl][6]
+  Dual<double> r;          // [Mp]
+  Dual<double> jl;         // [ntiles][6][256]
+  Dual<double> jc;         // [m][6] camera order, one 48 B record per observation
+  Dual<double> V;          // [nl][21]
+  Dual<double> gl;         // [nl][6]
+  Dual<unsigned long long> gbits;  // inf-norm of the gradient, as ordered bits
+  const LmCtl* ctl;        // LM loop: control block (NULL for the stand-alone API calls)
+  int which;               // 0: the current set, 1: the trial set
   double* cost_partial;    // [gridDim]
   unsigned int* ticket;    // last-CTA reduction ticket
   double* cost_out;        // 0.5 * sum r^2
-  unsigned long long* gbits;  // inf-norm of the gradient, as ordered bits
   int loss;                // 0 linear, else scipy robust loss (cost 0.5 f_scale^2 sum rho((r/f_scale)^2))
   double f_scale;
 };
@@ -465,7 +484,6 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   // per-line sums; the stage of tile it-1 is then refilled right after the barrier of tile it (every
   // warp has passed the sums of tile it-1 by then).
   const bool deferred = WITH_JAC && a.stg_bufs == 2;
-  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : a.recs;
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
 
@@ -474,8 +492,18 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     fence_barrier_init();
   }
   pdl_prologue();
+  if (ctl_skip_trial(a.ctl)) return;   // uniform over the grid
+  const int set = ctl_cur(a.ctl) ^ a.which;
+  const CamRec* g_recs = a.recs.sel(set);
+  const double* g_pts = a.pts.sel(set);
+  double* g_r = a.r.sel(set);
+  double* g_jl = a.jl.sel(set);
+  double* g_jc = a.jc.sel(set);
+  double* g_V = a.V.sel(set);
+  double* g_gl = a.gl.sel(set);
+  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : g_recs;
   if (TAB_SMEM) {
-    const double2* src = reinterpret_cast<const double2*>(a.recs);
+    const double2* src = reinterpret_cast<const double2*>(g_recs);
     double2* dst = reinterpret_cast<double2*>(smem);
     for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kTile * NSUB) dst[q] = __ldg(src + q);
   }
@@ -489,7 +517,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
     mbar_expect_tx(bar, 9 * kTile * 8 + idx_bytes + nl * 48);
     bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
     bulk_g2s(st + kEvOffIdx, a.tidx + tile, idx_bytes, bar);
-    if (nl > 0) bulk_g2s(st + kEvOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
+    if (nl > 0) bulk_g2s(st + kEvOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
   };
   // the issuing thread keeps (l0, nl) of the tile it will issue next in registers, one iteration ahead
   int nx_l0 = 0, nx_nl = 0;
@@ -577,17 +605,17 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
         double G[9];
         build_G(w, B, C, G);
         // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
-        double2* dst = reinterpret_cast<double2*>(a.jc + (size_t)s_pos[t] * 6);
+        double2* dst = reinterpret_cast<double2*>(g_jc + (size_t)s_pos[t] * 6);
         dst[0] = make_double2(G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2], G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2]);
         dst[1] = make_double2(G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2], -(jl[0] + jl[3]));
         dst[2] = make_double2(-(jl[1] + jl[4]), -(jl[2] + jl[5]));
       }
     }
-    a.r[i] = r;
+    g_r[i] = r;
     cost_acc += rho_cost;
     if (WITH_JAC) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) a.jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
+      for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
       // stage (jl, r) row-major with an odd-word stride for the per-line segmented sums
 #pragma unroll
       for (int k = 0; k < 6; ++k) s_stg[t * kEvRow + k] = jl[k];
@@ -605,8 +633,8 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       for (int wi = t; wi < nlg * 4; wi += kTile) {
         const int ll = wi >> 2, part = wi & 3;
         const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        double* Vo = a.V + (size_t)(l0 + ll) * 21;
-        double* go = a.gl + (size_t)(l0 + ll) * 6;
+        double* Vo = g_V + (size_t)(l0 + ll) * 21;
+        double* go = g_gl + (size_t)(l0 + ll) * 6;
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         double g0 = 0.0, g1 = 0.0;
         if (part == 0) {
@@ -670,7 +698,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       const double other = __shfl_xor_sync(0xffffffffu, gmax, o);
       gmax = (other > gmax || other != other) ? other : gmax;
     }
-    if ((threadIdx.x & 31) == 0 && gmax != 0.0) atomicMax(a.gbits, (unsigned long long)__double_as_longlong(gmax));
+    if ((threadIdx.x & 31) == 0 && gmax != 0.0) atomicMax(a.gbits.sel(set), (unsigned long long)__double_as_longlong(gmax));
   }
   const double cs[1] = {block_sum<kTile * NSUB>(cost_acc, red)};
   last_cta_reduce<kTile * NSUB, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
@@ -763,16 +791,20 @@ __global__ void __launch_bounds__(THREADS) k_cam_grad(const int* __restrict__ ca
 template <int THREADS, bool GRAD>
 __global__ void __launch_bounds__(THREADS) k_cam_accum(const int* __restrict__ cam_ptr,
                                                             const int* __restrict__ cam_perm,
-                                                            const double* __restrict__ jc,
+                                                            const Dual<const double> jc2,
                                                             const double* __restrict__ wa,
                                                             const double* __restrict__ wb,
-                                                            const double* __restrict__ rr,
+                                                            const Dual<const double> rr2,
                                                             double* __restrict__ S, double* __restrict__ v,
                                                             double* __restrict__ dg, int nc,
-                                                            const PeerLink pl) {
+                                                            const PeerLink pl, const LmCtl* __restrict__ ctl) {
   pdl_prologue();
   constexpr int NA = GRAD ? 39 : 27;
   __shared__ double sm[THREADS / 32][NA];
+  if (ctl_skip_solve(ctl)) return;
+  const int cur = ctl_cur(ctl);
+  const double* __restrict__ jc = jc2.sel(cur);
+  const double* __restrict__ rr = rr2.sel(cur);
   const int c = blockIdx.x;
   const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
   double acc[NA];
@@ -856,11 +888,16 @@ __global__ void k_cam_post(int nc, const double* __restrict__ S, const double* _
 // 2 Dl = diag V (first Jacobian); zeros -> 1  (Marquardt scaling, the analogue of scipy's
 // compute_jac_scale, _lsq/common.py:598-610, used by x_scale='jac' at bundle_adjustment.py:319).
 constexpr int kLfLines = 128;  // lines per CTA of k_line_factor
-__global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, const double* __restrict__ V,
-                                                           double* __restrict__ Dl, const double* __restrict__ gl,
+__global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, const Dual<const double> V2,
+                                                           double* __restrict__ Dl, const Dual<const double> gl2,
                                                            double* __restrict__ Vinv, double* __restrict__ y,
-                                                           int* __restrict__ clamped, int scaling_mode) {
+                                                           int* __restrict__ clamped, int scaling_mode,
+                                                           const LmCtl* __restrict__ ctl) {
   pdl_prologue();
+  if (ctl_skip_solve(ctl)) return;
+  if (ctl) { lam = ctl->lam; scaling_mode = ctl->scaling_mode; }
+  const double* __restrict__ V = V2.sel(ctl_cur(ctl));
+  const double* __restrict__ gl = gl2.sel(ctl_cur(ctl));
   // the per-line records are AoS (21 / 6 / 22 doubles): move them through shared memory so that
   // global traffic is fully coalesced and each thread reads its own row conflict-free (odd strides)
   __shared__ double sV[kLfLines * kVinvStride];
@@ -923,10 +960,14 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
 __global__ void __launch_bounds__(128) k_cam_finish(int nc, double lam, const double* __restrict__ Mpart,
                                                      double* __restrict__ Dc, double* __restrict__ gc,
                                                      const double* __restrict__ bpart, const double* __restrict__ dg,
-                                                     unsigned long long* __restrict__ gbits,
+                                                     const Dual<unsigned long long> gbits2,
                                                      double* __restrict__ Minv,
-                                                     double* __restrict__ b, int* __restrict__ clamped, const PeerLink pl) {
+                                                     double* __restrict__ b, int* __restrict__ clamped, const PeerLink pl,
+                                                     const LmCtl* __restrict__ ctl) {
   pdl_prologue();
+  if (ctl_skip_solve(ctl)) return;
+  if (ctl) lam = ctl->lam;
+  unsigned long long* gbits = gbits2.sel(ctl_cur(ctl));
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl.seq) peer_wait(pl);   // multi-GPU: Mpart | bpart live in the symmetric slots of all ranks
   double mx = 0.0;
@@ -999,21 +1040,23 @@ __device__ __forceinline__ void make_tab_entry(const double* __restrict__ G, con
 struct LinePassArgs {
   int Mp, ntiles, lmax;
   const TileIdx* tidx;   // [ntiles]
-  const double* jl;      // [ntiles][6][256]
-  const double* pts;     // [nl][6]
+  Dual<const double> jl; // [ntiles][6][256]   (both evaluation sets; the kernel reads the current one)
+  Dual<double> pts;      // [nl][6]            (BACKSUB writes the trial point into the other set)
   const double* tab;     // [nc][6]
   const double* Vinv;    // [nl][22]
   double* w;             // MATVEC out [Mp];  SCALARS out: wk
   double* w2;            // SCALARS out: wr
   const double* y;       // SCALARS: [nl][6]
   // BACKSUB only
-  const double* gl;      // [nl][6]
-  const double* r;       // [Mp]
-  double* pts_new;       // [nl][6]
+  Dual<const double> gl; // [nl][6]
+  Dual<const double> r;  // [Mp]
+  double* dl;            // [nl][6] the full line step (kept for a retry at a shorter length)
+  double alpha;          // step length of the trial point (LM loop: taken from ctl)
   double* partial;       // [gridDim][4]: r.jd, jd.jd, |dl|^2, |pts|^2
   unsigned int* ticket;  // BACKSUB: last-CTA reduction
   double* out4;          // BACKSUB: the four sums
   const CgState* st;     // MATVEC: early exit when done
+  const LmCtl* ctl;      // LM loop: control block (NULL for the stand-alone API calls)
 };
 
 enum { kModeMatvec = 0, kModeBacksub = 1, kModeScalars = 2 };
@@ -1059,6 +1102,14 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   }
   pdl_prologue();
   if (MODE == kModeMatvec && a.st->done) return;  // uniform over the grid
+  if (MODE != kModeMatvec && ctl_skip_solve(a.ctl)) return;
+  const int cur = ctl_cur(a.ctl);
+  const double* g_jl = a.jl.sel(cur);
+  const double* g_pts = a.pts.sel(cur);
+  const double* g_gl = a.gl.sel(cur);
+  const double* g_r = a.r.sel(cur);
+  double* g_pts_new = a.pts.sel(cur ^ 1);
+  const double alpha = (MODE == kModeBacksub && a.ctl) ? a.ctl->alpha : a.alpha;
   __syncthreads();
 
   auto issue = [&](int it, int nl, int l0) {
@@ -1072,15 +1123,15 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     if (MODE == kModeBacksub) bytes += kTile * 8;
     mbar_expect_tx(bar, bytes);
     const size_t o = (size_t)tile * kTile;
-    bulk_g2s(st, a.jl + (size_t)tile * 6 * kTile, 6 * kTile * 8, bar);
+    bulk_g2s(st, g_jl + (size_t)tile * 6 * kTile, 6 * kTile * 8, bar);
     bulk_g2s(st + kLpOffIdx, a.tidx + tile, idx_bytes, bar);
     if (nl > 0) {
-      if (MODE != kModeScalars) bulk_g2s(st + kLpOffPts, a.pts + (size_t)l0 * 6, nl * 48, bar);
+      if (MODE != kModeScalars) bulk_g2s(st + kLpOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
       bulk_g2s(st + off_vinv, a.Vinv + (size_t)l0 * kVinvStride, nl * kVinvStride * 8, bar);
-      if (MODE == kModeBacksub) bulk_g2s(st + off_aux, a.gl + (size_t)l0 * 6, nl * 48, bar);
+      if (MODE == kModeBacksub) bulk_g2s(st + off_aux, g_gl + (size_t)l0 * 6, nl * 48, bar);
       if (MODE == kModeScalars) bulk_g2s(st + off_aux, a.y + (size_t)l0 * 6, nl * 48, bar);
     }
-    if (MODE == kModeBacksub) bulk_g2s(st + off_r, a.r + o, kTile * 8, bar);
+    if (MODE == kModeBacksub) bulk_g2s(st + off_r, g_r + o, kTile * 8, bar);
   };
   int nx_l0 = 0, nx_nl = 0;
   if (t == 0) {
@@ -1181,7 +1232,9 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
             if (MODE == kModeBacksub) {
               u = -u;
               const double x = s_pts[lx * 6 + sub];
-              a.pts_new[(size_t)(l0 + lx) * 6 + sub] = x + u;
+              // trial point x + alpha dl, rounded like the oracle (no FMA); dl is kept for a retry
+              g_pts_new[(size_t)(l0 + lx) * 6 + sub] = __dadd_rn(x, __dmul_rn(alpha, u));
+              a.dl[(size_t)(l0 + lx) * 6 + sub] = u;
               p2 += u * u;
               p3 += x * x;
             }
@@ -1222,12 +1275,13 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_pcg_cam(int nc, const int* __restrict__ cam_ptr,
                                                           const int* __restrict__ cam_perm,
-                                                          const double* __restrict__ jc, const double* __restrict__ w,
+                                                          const Dual<const double> jc2, const double* __restrict__ w,
                                                           double* __restrict__ qpart, const CgState* __restrict__ st,
-                                                          const PeerLink pl) {
+                                                          const PeerLink pl, const LmCtl* __restrict__ ctl) {
   pdl_prologue();
   __shared__ double sm[THREADS / 32][6];
   if (st->done) return;
+  const double* __restrict__ jc = jc2.sel(ctl_cur(ctl));
   for (int c = blockIdx.x; c < nc; c += gridDim.x) {
     const int j0 = cam_ptr[c], j1 = cam_ptr[c + 1];
     double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -1266,8 +1320,9 @@ struct CgArgs {
   int max_iter;
   const double* Dc;     // [nc][6]
   const double* Minv;   // [nc][21]
-  const double* Gm;     // [nc][9]
-  const double* cams;   // [nc][6]
+  Dual<const double> Gm;     // [nc][9]   (both evaluation sets)
+  Dual<const double> cams;   // [nc][6]
+  const LmCtl* ctl;     // LM loop: current set and damping come from the control block
   const double* b;      // [nc][6]
   const double* qpart;  // [nc][6] (all-reduced partial S p without the damping term)
   double* x; double* r; double* z; double* p; double* tab;
@@ -1353,6 +1408,9 @@ __device__ __forceinline__ void group_table(const double* __restrict__ G, const 
 __global__ void __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
   pdl_prologue();
   __shared__ double red[kCgBlock / 32];
+  if (ctl_skip_solve(a.ctl)) return;
+  const double* Gm = a.Gm.sel(ctl_cur(a.ctl));
+  const double* cams = a.cams.sel(ctl_cur(a.ctl));
   const unsigned long long base = a.gb->base;
   const int gt = blockIdx.x * kCgBlock + threadIdx.x;
   const int k = gt & 7;
@@ -1368,7 +1426,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_begin(const CgArgs a) {
       a.x[e] = 0.0; a.r[e] = rk; a.z[e] = zk; a.p[e] = zk;
       acc += rk * zk;
     }
-    group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, zk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
+    group_table(Gm + (size_t)(act ? c : 0) * 9, cams + (size_t)(act ? c : 0) * 6, zk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
   }
   const double rz = grid_sum(acc, red, a.partial, a.gb, base + gridDim.x);
   if (gt == 0) {
@@ -1386,6 +1444,10 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
   pdl_prologue();
   __shared__ double red[kCgBlock / 32];
   if (a.st->done) return;   // uniform over the whole grid (written by the previous launch)
+  const double* Gm = a.Gm.sel(ctl_cur(a.ctl));
+  const double* cams = a.cams.sel(ctl_cur(a.ctl));
+  const double lam = a.ctl ? a.ctl->lam : a.lam;
+  const int max_iter = a.ctl ? a.ctl->pcg_max_iter : a.max_iter;
   const double rz = a.st->rz, rz0 = a.st->rz0;
   const int k_new = a.st->k + 1;
   const unsigned long long base = a.gb->base;
@@ -1408,7 +1470,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
       const size_t e = (size_t)c * 6 + k;
       const double pp = a.p[e];
       const double qsum = fused ? peer_sum(a.pl, e) : a.qpart[e];
-      const double q = qsum + a.lam * a.Dc[e] * pp;
+      const double q = qsum + lam * a.Dc[e] * pp;
       a.z[e] = q;  // z is free until the preconditioner is applied below; reuse it to keep q
       acc += pp * q;
     }
@@ -1434,7 +1496,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
     }
   }
   const double rz_new = grid_sum(acc, red, a.partial + kCgMaxCtas, a.gb, base + 2ULL * gridDim.x);
-  const bool stop = !ok || rz_new <= a.tol2 * rz0 || k_new >= a.max_iter;
+  const bool stop = !ok || rz_new <= a.tol2 * rz0 || k_new >= max_iter;
   const double beta = stop ? 0.0 : rz_new / rz;
   for (int c0 = 0; c0 < a.nc; c0 += groups) {
     const int c = c0 + (gt >> 3);
@@ -1445,7 +1507,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
       if (stop) vk = a.x[e];
       else { vk = a.z[e] + beta * a.p[e]; a.p[e] = vk; }
     }
-    group_table(a.Gm + (size_t)(act ? c : 0) * 9, a.cams + (size_t)(act ? c : 0) * 6, vk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
+    group_table(Gm + (size_t)(act ? c : 0) * 9, cams + (size_t)(act ? c : 0) * 6, vk, k, act, a.tab + (size_t)(act ? c : 0) * 6);
   }
   // every CTA has read st and gb->base before the second barrier, so thread 0 may publish the new state
   if (gt == 0) {
@@ -1471,39 +1533,91 @@ struct Scalars {            // device-resident LM scalars, copied to the host on
   int clamped, pad;
 };
 
-// What the host reads once per LM iteration, in pinned host memory the device writes directly: one tiny
-// kernel posts the values and then a sequence number the host spins on (no copy-engine round trips).
+// What the host reads of a running solve, in pinned host memory the device writes directly: one tiny kernel
+// posts the values and then a sequence number the host spins on (no copy-engine round trips).
 struct HostMirror {
   Scalars scal;
   CgState cg;
+  LmCtl ctl;
   unsigned long long gbits;
   int clamped, pad;
   unsigned long long seq;
 };
-__global__ void k_publish(const Scalars* __restrict__ s, const CgState* __restrict__ cg,
-                          const unsigned long long* __restrict__ gbits, const int* __restrict__ clamped,
+__global__ void k_publish(const Scalars* __restrict__ s, const CgState* __restrict__ cg, const LmCtl* __restrict__ ctl,
+                          const Dual<const unsigned long long> gbits, const int* __restrict__ clamped,
                           HostMirror* __restrict__ h, unsigned long long seq) {
   pdl_prologue();
   if (threadIdx.x == 0) {
     h->scal = *s;
     h->cg = *cg;
-    h->gbits = *gbits;
+    h->ctl = *ctl;
+    h->gbits = *gbits.sel(ctl->cur);
     h->clamped = *clamped;
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&h->seq) = seq;
   }
 }
 
-// cams_new = cams + dc, its camera records and SO(3) Jacobians, and the step / parameter norms
-// (grid-wide sums by the last CTA, fixed order).
+// Start of an LM solve: options and the initial state of the control block (the initial evaluation is in set 0
+// and its cost, all-reduced, in scal->cost).
+__global__ void k_lm_init(LmCtl* __restrict__ L, const LmCtl opts, const Scalars* __restrict__ s) {
+  pdl_prologue();
+  if (threadIdx.x != 0) return;
+  LmCtl c = opts;
+  c.cost = s->cost;
+  c.cur = 0; c.need_solve = 1; c.done = 0; c.status = 0; c.it = 0; c.evals = 1; c.streak = 0; c.bt = 0;
+  c.n_acc = 0; c.pcg_total = 0; c.cg_short = 0; c.trace_len = 0; c.scaling_mode = 2; c.q_last = 0; c.pass = 0;
+  c.nu = 2.0; c.sigma = 1.0; c.alpha = 1.0; c.g_norm = 0.0;
+  if (!pol_finite(c.cost)) { c.done = 1; c.status = -5; }   // "Residuals are not finite in the initial point."
+  if (c.max_iter <= 0) c.done = 1;
+  *L = c;
+}
+
+// The decision after a trial evaluation (lba_policy.cuh): one thread.
+__global__ void k_lm_decide(LmCtl* __restrict__ L, const Scalars* __restrict__ s, const CgState* __restrict__ cg,
+                            const Dual<const unsigned long long> gbits, LmTrace* __restrict__ tr) {
+  pdl_prologue();
+  if (threadIdx.x != 0) return;
+  LmCtl c = *L;
+  LmTrial t;
+  t.cost_new = s->cost; t.rjd = s->rjd; t.jd2 = s->jd2;
+  t.d2 = __dadd_rn(s->dc2, s->dl2);
+  t.x2 = __dadd_rn(s->x2_cams, s->x2_lines);
+  t.g_norm = __longlong_as_double((long long)*gbits.sel(c.cur));
+  t.pcg_iters = cg->k; t.pcg_done = cg->done;
+  lm_decide(c, t, tr);
+  *L = c;
+}
+
+// Trial point on the camera side: cams_new = cams + alpha dc, its camera records and SO(3) Jacobians, the step /
+// parameter norms (grid-wide sums by the last CTA, fixed order), and the reset of the trial set's gradient-norm
+// word.  In a RETRY pass (same direction, shorter alpha) the CTAs also rebuild the line side of the trial point
+// from the kept step: pts_new = pts + alpha dl.
 constexpr int kCamStepThreads = 128;
-__global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const double* __restrict__ cams,
-                                                               const double* __restrict__ dc, double* __restrict__ cams_new,
-                                                               CamRec* __restrict__ recs_new, double* __restrict__ Gm_new,
+__global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const Dual<double> cams2, const double* __restrict__ dc,
+                                                               const Dual<CamRec> recs2, const Dual<double> Gm2,
+                                                               double alpha, const Dual<unsigned long long> gbits2,
+                                                               size_t n_line_params, const Dual<double> pts2,
+                                                               const double* __restrict__ dl,
                                                                double* __restrict__ partial, unsigned int* ticket,
-                                                               double* __restrict__ out2 /* dc2, x2_cams */) {
+                                                               double* __restrict__ out2 /* dc2, x2_cams */,
+                                                               const LmCtl* __restrict__ ctl) {
   pdl_prologue();
   __shared__ double red[kCamStepThreads / 32];
+  if (ctl_skip_trial(ctl)) return;
+  const int cur = ctl_cur(ctl);
+  if (ctl) alpha = ctl->alpha;
+  const double* __restrict__ cams = cams2.sel(cur);
+  double* __restrict__ cams_new = cams2.sel(cur ^ 1);
+  CamRec* __restrict__ recs_new = recs2.sel(cur ^ 1);
+  double* __restrict__ Gm_new = Gm2.sel(cur ^ 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gbits2.sel(cur ^ 1) = 0ULL;
+  if (ctl && !ctl->need_solve) {
+    const double* __restrict__ pts = pts2.sel(cur);
+    double* __restrict__ pts_new = pts2.sel(cur ^ 1);
+    for (size_t e = (size_t)blockIdx.x * kCamStepThreads + threadIdx.x; e < n_line_params; e += (size_t)gridDim.x * kCamStepThreads)
+      pts_new[e] = __dadd_rn(pts[e], __dmul_rn(alpha, dl[e]));
+  }
   double d2 = 0.0, x2 = 0.0;
   const int c = blockIdx.x * kCamStepThreads + threadIdx.x;
   if (c < nc) {
@@ -1511,7 +1625,7 @@ __global__ void __launch_bounds__(kCamStepThreads) k_cam_step(int nc, const doub
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const double x = cams[c * 6 + k], d = dc[c * 6 + k];
-      const double xn = x + d;
+      const double xn = __dadd_rn(x, __dmul_rn(alpha, d));
       cams_new[c * 6 + k] = xn;
       if (k < 3) rec.w[k] = xn; else rec.c[k - 3] = xn;
       d2 += d * d;
@@ -1581,8 +1695,11 @@ template <bool MAX_U64>
 __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int region, size_t slot_off, size_t n,
                                                       unsigned long long seq, const double* __restrict__ src,
                                                       double* __restrict__ dst,
-                                                      unsigned long long* __restrict__ maxp = nullptr) {
+                                                      unsigned long long* maxp = nullptr,
+                                                      unsigned long long* maxp1 = nullptr,
+                                                      const LmCtl* __restrict__ ctl = nullptr) {
   pdl_prologue();
+  if (maxp && ctl && ctl->cur) maxp = maxp1;   // LM loop: the gradient-norm word of the current evaluation set
   const int slot = (int)(seq & 1ULL);
   const int t = threadIdx.x;
   constexpr int kMaxAt = 8;   // maxp (single-CTA mode, n <= 8): one more word, max-reduced as u64, rides at this index

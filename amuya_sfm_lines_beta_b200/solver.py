@@ -57,6 +57,7 @@ class LMResult:
     n_res: int
     pcg_iters_total: int
     chol_clamped: int
+    n_accepted: int
     cost_init: float
     cost: float
     seconds: float
@@ -243,11 +244,11 @@ class LineBA:
         check(self._lib.lba_lm_solve(self._h, pc, pp, C.byref(o), C.byref(rep),
                                      r.ctypes.data if r is not None else None))
         n = rep.trace_len
-        trace = [dict(it=i, cost=rep.trace_cost[i], cost_new=rep.trace_cost_new[i], lam=rep.trace_lambda[i],
+        trace = [dict(it=rep.trace_it[i], alpha=rep.trace_alpha[i], cost=rep.trace_cost[i], cost_new=rep.trace_cost_new[i], lam=rep.trace_lambda[i],
                       pcg=rep.trace_pcg[i], pred=rep.trace_pred[i], accepted=bool(rep.trace_accepted[i]),
                       step_norm=rep.trace_step_norm[i], g_norm=rep.trace_g_norm[i]) for i in range(n)]
         return LMResult(cams, pts, r, rep.iterations, rep.status, STATUS_TEXT.get(rep.status, "?"), rep.n_jac,
-                        rep.n_res, rep.pcg_iters_total, rep.chol_clamped, rep.cost_init, rep.cost, rep.seconds, trace)
+                        rep.n_res, rep.pcg_iters_total, rep.chol_clamped, rep.n_accepted, rep.cost_init, rep.cost, rep.seconds, trace)
 
     # -- multi-GPU --------------------------------------------------------------------------
     def init_comm(self, rank=None, world=None, group=None, peer_bytes=64 << 20):

@@ -48,7 +48,8 @@ typedef struct lba_ctx lba_ctx;
  * least_squares(..., ftol=1e-4, method='trf', x_scale='jac') with scipy's default
  * xtol = gtol = 1e-8 (bundle_adjustment.py:319). */
 typedef struct lba_options {
-  int32_t max_iter;       /* LM iterations (one solve + one trial evaluation each) */
+  int32_t max_iter;       /* LM iterations: damped solves, each followed by one trial evaluation (two when the
+                             first is rejected and retried at a shorter length) */
   int32_t pcg_max_iter;   /* PCG iterations per solve */
   double ftol;            /* stop when dF < ftol*F and ratio > 0.25 (scipy check_termination) */
   double xtol;            /* stop when |step| < xtol*(xtol+|x|) */
@@ -59,10 +60,12 @@ typedef struct lba_options {
   double pcg_tol;         /* eta: stop PCG when |r|_{M^-1} <= eta |r0|_{M^-1} */
   double min_ratio;       /* accept a step when actual/predicted > min_ratio */
   int32_t verbose;        /* 2: print scipy-style iteration table to stdout */
-  int32_t flags;          /* bit 0: evaluate the trial point without its Jacobian (non-speculative) */
+  int32_t flags;          /* reserved (0) */
   int32_t loss;           /* LBA_LOSS_*: scipy least_squares `loss` (forwarded as loss_f at bundle_adjustment.py:319) */
   int32_t pad;
   double f_scale;         /* scipy `f_scale` (soft margin between inliers and outliers); 1.0 like the reference */
+  int32_t max_evals;      /* > 0: stop after this many evaluations, the initial one included (scipy's max_nfev) */
+  int32_t max_backtrack;  /* retries along a rejected step at the measured length before the damping is raised (1) */
 } lba_options;
 
 /* scipy.optimize.least_squares robust losses, rho(z) with z = (r/f_scale)^2 (scipy/optimize/_lsq/least_squares.py) */
@@ -76,15 +79,18 @@ typedef struct lba_options {
 typedef struct lba_report {
   int32_t iterations;
   int32_t status;         /* 0 max_iter, 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol */
-  int32_t n_jac;          /* residual+Jacobian evaluations */
-  int32_t n_res;          /* residual-only (trial) evaluations */
+  int32_t n_jac;          /* residual+Jacobian evaluations (every trial point is evaluated with its Jacobian) */
+  int32_t n_res;          /* residual-only evaluations (0) */
   int32_t pcg_iters_total;
   int32_t chol_clamped;   /* number of 6x6 pivots clamped (0 on healthy problems) */
+  int32_t n_accepted;     /* accepted trial steps */
+  int32_t pad;
   double cost_init;       /* 0.5 * sum r^2 at the input */
   double cost;            /* at the output */
   double seconds;         /* wall time inside lba_lm_solve */
-  /* per-iteration trace (first LBA_TRACE_MAX iterations) */
+  /* trace: one entry per trial evaluation (first LBA_TRACE_MAX), written by the device decision kernel */
   int32_t trace_len;
+  int32_t trace_it[LBA_TRACE_MAX];       /* iteration (damped solve) the trial belongs to */
   int32_t trace_pcg[LBA_TRACE_MAX];
   int32_t trace_accepted[LBA_TRACE_MAX];
   double trace_cost[LBA_TRACE_MAX];      /* cost before the step */
@@ -93,6 +99,7 @@ typedef struct lba_report {
   double trace_pred[LBA_TRACE_MAX];
   double trace_step_norm[LBA_TRACE_MAX];
   double trace_g_norm[LBA_TRACE_MAX];
+  double trace_alpha[LBA_TRACE_MAX];     /* step length of the trial */
 } lba_report;
 
 /* Kernel classes for lba_get_profile */

@@ -321,7 +321,7 @@ def scale_for_robust_loss(r, jc, jl, loss, f_scale=1.0):
 
 @dataclass
 class LMOptions:
-    max_iter: int = 50
+    max_iter: int = 50       # damped solves (each followed by one trial evaluation, two when the first is rejected)
     ftol: float = 1e-4       # reference call site bundle_adjustment.py:319
     xtol: float = 1e-8       # scipy default
     gtol: float = 1e-8       # scipy default
@@ -333,33 +333,75 @@ class LMOptions:
     min_ratio: float = 1e-4
     loss: str = "linear"    # scipy least_squares `loss` (bundle_adjustment.py:319 forwards loss_f)
     f_scale: float = 1.0
+    max_evals: int = 0       # > 0: stop after this many residual(+Jacobian) evaluations (scipy's max_nfev)
+    max_backtrack: int = 1   # step-length retries along a rejected step before the damping is raised
 
 
-def damping_factor(ratio):
-    """Damping update after an ACCEPTED step, from the gain ratio rho = actual / predicted reduction.
-    The residual of this problem is itself a squared distance, so even good Gauss-Newton steps have
-    rho ~ 0.3-0.5; the classic thresholds are therefore shifted down a little:
-    rho >= 0.7 -> lambda/3, 0.4 <= rho < 0.7 -> lambda/1.5, 0.15 <= rho < 0.4 -> unchanged,
-    rho < 0.15 -> 2 lambda.  (Rejected steps: lambda *= nu, nu *= 2.)"""
-    if ratio >= 0.7:
-        return 1.0 / 3.0
-    if ratio >= 0.4:
-        return 1.0 / 1.5
-    if ratio >= 0.15:
-        return 1.0
-    return 2.0
+# Step policy (the same constants are compiled into the device decision kernel, csrc/lba_kernels.cuh k_lm_decide).
+# The residual of this problem is itself a sum of squares r_i = sum_k e_ik^2, so the Gauss-Newton model J^T J of
+# 1/2 sum r_i^2 misses the term sum_i r_i grad^2 r_i, which is positive semi-definite and at least HALF of J^T J in
+# every direction (Cauchy-Schwarz on grad r_i = 2 sum_k e_ik grad e_ik): near a solution the cost curves >= 1.5x
+# more than the model says and the best length along a Gauss-Newton direction is <= 2/3 of the step (SURVEY.md F3:
+# gain ratios of 0.3-0.5 for perfectly good steps).  The policy therefore measures that length instead of guessing:
+#   * every trial gives the curvature of the cost along the step (parabola through F(x), the slope r.J d and
+#     F(x + alpha d)) and with it the best length a_opt along that direction;
+#   * the NEXT step is tried at sigma = 1.15 a_opt (clamped to [0.1, 1]) -- the overshoot factor changes slowly
+#     from one iteration to the next -- so that rejected trials become rare;
+#   * the damping follows a_opt as well: a_opt >= 0.6 with a gain ratio >= 0.5 is what a good model looks like here,
+#     consecutive good steps divide lambda by 2, 4, 8 (the analogue of a trust radius that doubles); otherwise
+#     lambda grows by a_opt^-2 (at most 10x), which bends the next direction towards the scaled gradient;
+#   * a rejected trial is first retried at the measured length along the SAME direction (one evaluation, no solve;
+#     scipy's trust-region loop likewise re-solves its 2-D subproblem without a new Gauss-Newton step,
+#     scipy/optimize/_lsq/trf.py:509-533) before the damping is raised.
+RATIO_GOOD, LENGTH_GOOD = 0.5, 0.6
+STREAK_MAX = 3
+SIGMA_GAIN, SIGMA_MIN = 1.15, 0.1
+LENGTH_CAP = 4.0
+GROWTH_MAX = 10.0
+ALPHA_LO, ALPHA_HI = 0.1, 0.5
+
+
+def measured_length(alpha, cost, cost_new, rjd):
+    """Best step length along the direction, from the parabola through phi(0) = cost, phi'(0) = r.J delta and
+    phi(alpha) = cost_new; None when the parabola is not convex or the trial cost is not finite."""
+    if not math.isfinite(cost_new):
+        return None
+    c2 = (cost_new - cost - rjd * alpha) / (alpha * alpha)
+    if not (c2 > 0.0):
+        return None
+    return -rjd / (2.0 * c2)
+
+
+def damping_update(ratio, a_opt, streak):
+    """After an accepted step: (factor on lambda, new streak, first trial length of the next step)."""
+    a = LENGTH_CAP if a_opt is None else min(a_opt, LENGTH_CAP)
+    if ratio >= RATIO_GOOD and a >= LENGTH_GOOD:
+        streak = streak + 1
+        fac = 0.5 ** min(streak, STREAK_MAX)
+    else:
+        streak = 0
+        fac = min(1.0 / (a * a), GROWTH_MAX) if a < 1.0 else 1.0
+    sigma = min(1.0, max(SIGMA_MIN, SIGMA_GAIN * a))
+    return fac, streak, sigma
+
+
+def backtrack_alpha(alpha, a_opt):
+    """Next length after a rejected trial at `alpha`: the measured one, clamped to [0.1, 0.5] alpha."""
+    a = ALPHA_HI * alpha if a_opt is None else a_opt
+    return min(max(a, ALPHA_LO * alpha), ALPHA_HI * alpha)
 
 
 @dataclass
 class LMReport:
-    iterations: int = 0
-    status: int = 0          # 0 max_iter, 1 gtol, 2 ftol, 3 xtol, 4 both
+    iterations: int = 0      # damped solves
+    status: int = 0          # 0 max_iter / max_evals, 1 gtol, 2 ftol, 3 xtol, 4 both
     cost_init: float = 0.0
     cost: float = 0.0
     n_jac: int = 0
     n_res: int = 0
     pcg_iters_total: int = 0
-    trace: list = field(default_factory=list)   # per iteration dict
+    n_accepted: int = 0
+    trace: list = field(default_factory=list)   # one dict per trial evaluation
 
 
 class SchurSystem:
@@ -442,7 +484,8 @@ class SchurSystem:
 def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None = None,
              verbose=False):
     """Levenberg-Marquardt with Marquardt scaling, Schur elimination of the line
-    blocks and block-Jacobi PCG on the reduced camera system.
+    blocks, block-Jacobi PCG on the reduced camera system and a step-length retry on
+    rejected steps.
 
     Replaces the scipy call at bundle_adjustment.py:319.  Termination mirrors
     scipy ``check_termination`` (scipy/optimize/_lsq/common.py:705): ftol when
@@ -471,9 +514,15 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
     Dl = update_scaling(None, V[:, idx, idx])
     lam = opts.lambda0
     nu = 2.0
+    streak = 0
+    sigma = 1.0
     status = 0
     it = 0
-    while it < opts.max_iter:
+    nev = 1
+    done = False
+    while not done and it < opts.max_iter:
+        if opts.max_evals and nev >= opts.max_evals:
+            break
         g_norm = max(np.abs(gc).max() if nc else 0.0, np.abs(gl).max() if nl else 0.0)
         if g_norm < opts.gtol:
             status = 1
@@ -482,49 +531,75 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
         dc, q = sys_.pcg(opts.pcg_tol, opts.pcg_max_iter)
         dl, jd = sys_.back_substitute(dc)
         rep.pcg_iters_total += q
-        pred = -float(np.dot(r, jd)) - 0.5 * float(np.dot(jd, jd))
-        om_new = omega + dc[:, 0:3]
-        ce_new = centre + dc[:, 3:6]
-        pts_new = pts + dl
-        r_new = residuals_jacobian(om_new, ce_new, pts_new, ci, li, n, m0, m1)[0]
-        rep.n_res += 1
-        cost_new = robust_cost(r_new, opts.loss, opts.f_scale)
-        step_norm = math.sqrt(float(np.sum(dc * dc) + np.sum(dl * dl)))
-        x_norm = math.sqrt(float(np.sum(omega * omega) + np.sum(centre * centre) + np.sum(pts * pts)))
-        actual = cost - cost_new
-        finite = math.isfinite(cost_new)
-        ratio = actual / pred if (finite and pred > 0.0) else -1.0
-        accepted = finite and ratio > opts.min_ratio
-        ftol_ok = finite and (actual < opts.ftol * cost) and (ratio > 0.25)
-        xtol_ok = step_norm < opts.xtol * (opts.xtol + x_norm)
-        rep.trace.append(dict(it=it, cost=cost, cost_new=cost_new, lam=lam, pcg=q, pred=pred,
-                              ratio=ratio, accepted=accepted, step_norm=step_norm, g_norm=g_norm))
-        if verbose:
-            print(f"{it:4d} cost {cost:.6e} -> {cost_new:.6e} lam {lam:.2e} pcg {q:3d} "
-                  f"ratio {ratio:+.3f} step {step_norm:.2e} |g| {g_norm:.2e}")
         it += 1
-        if accepted:
-            omega, centre, pts = om_new, ce_new, pts_new
-            cost = cost_new
-            r_true, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
-            r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
-            rep.n_jac += 1
-            U, gc, V, gl = normal_equations(r, jc, jl, ci, li, nc, nl)
-            Dc = update_scaling(Dc, U[:, idx, idx])
-            Dl = update_scaling(Dl, V[:, idx, idx])
-            lam = min(max(lam * damping_factor(ratio), opts.lambda_min), opts.lambda_max)
-            nu = 2.0
-        else:
-            lam = min(lam * nu, opts.lambda_max)
-            nu *= 2.0
-        if ftol_ok and xtol_ok:
-            status = 4
-        elif ftol_ok:
-            status = 2
-        elif xtol_ok:
-            status = 3
-        if status:
-            break
+        rjd = float(np.dot(r, jd))
+        jd2 = float(np.dot(jd, jd))
+        d2 = float(np.sum(dc * dc) + np.sum(dl * dl))
+        x2 = float(np.sum(omega * omega) + np.sum(centre * centre) + np.sum(pts * pts))
+        x_norm = math.sqrt(x2)
+        alpha = sigma
+        bt = 0
+        while True:
+            if opts.max_evals and nev >= opts.max_evals:
+                done = True
+                break
+            pred = -alpha * rjd - 0.5 * alpha * alpha * jd2
+            om_new = omega + alpha * dc[:, 0:3]
+            ce_new = centre + alpha * dc[:, 3:6]
+            pts_new = pts + alpha * dl
+            r_new = residuals_jacobian(om_new, ce_new, pts_new, ci, li, n, m0, m1)[0]
+            rep.n_res += 1
+            nev += 1
+            cost_new = robust_cost(r_new, opts.loss, opts.f_scale)
+            step_norm = alpha * math.sqrt(d2)
+            actual = cost - cost_new
+            finite = math.isfinite(cost_new)
+            ratio = actual / pred if (finite and pred > 0.0) else -1.0
+            accepted = finite and ratio > opts.min_ratio
+            a_opt = measured_length(alpha, cost, cost_new, rjd)
+            ftol_ok = finite and (actual < opts.ftol * cost) and (ratio > 0.25)
+            xtol_ok = step_norm < opts.xtol * (opts.xtol + x_norm)
+            rep.trace.append(dict(it=it - 1, cost=cost, cost_new=cost_new, lam=lam, pcg=q, pred=pred, alpha=alpha,
+                                  ratio=ratio, accepted=accepted, step_norm=step_norm, g_norm=g_norm, a_opt=a_opt,
+                                  rjd=rjd, jd2=jd2, d2=d2, x2=x2))
+            if verbose:
+                print(f"{it - 1:4d} cost {cost:.6e} -> {cost_new:.6e} lam {lam:.2e} alpha {alpha:.3f} pcg {q:3d} "
+                      f"ratio {ratio:+.3f} step {step_norm:.2e} |g| {g_norm:.2e}")
+            retry = False
+            if accepted:
+                rep.n_accepted += 1
+                omega, centre, pts = om_new, ce_new, pts_new
+                r_true, jc, jl = residuals_jacobian(omega, centre, pts, ci, li, n, m0, m1)
+                r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
+                rep.n_jac += 1
+                U, gc, V, gl = normal_equations(r, jc, jl, ci, li, nc, nl)
+                Dc = update_scaling(Dc, U[:, idx, idx])
+                Dl = update_scaling(Dl, V[:, idx, idx])
+                fac, streak, sigma = damping_update(ratio, a_opt, streak)
+                lam = min(max(lam * fac, opts.lambda_min), opts.lambda_max)
+                nu = 2.0
+            elif bt < opts.max_backtrack:
+                bt += 1
+                alpha_next = backtrack_alpha(alpha, a_opt)
+                retry = True
+            else:
+                lam = min(lam * GROWTH_MAX * nu, opts.lambda_max)
+                nu *= 2.0
+                streak = 0
+            if accepted:
+                cost = cost_new
+            if ftol_ok and xtol_ok:
+                status = 4
+            elif ftol_ok:
+                status = 2
+            elif xtol_ok:
+                status = 3
+            if status:
+                done = True
+                break
+            if not retry:
+                break
+            alpha = alpha_next
     rep.iterations = it
     rep.status = status
     rep.cost = cost

@@ -30,8 +30,11 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().lba_version() >= 100
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors of lba_options / lba_report have the layout a C compiler gives include/lba.h."""
     _ensure_built()
+    import shutil
+    import subprocess
     from amuya_sfm_lines_beta_b200 import _lib
     lib = _lib.load()
     o = _lib.LbaOptions()
@@ -39,9 +42,27 @@ def test_struct_layouts_match_header():
     assert (o.max_iter, o.pcg_max_iter) == (50, 200)
     assert (o.ftol, o.xtol, o.gtol) == (1e-4, 1e-8, 1e-8)   # reference call site :319 + scipy defaults
     assert o.lambda0 == 1e-2 and o.lambda_min == 1e-6 and o.pcg_tol == 1e-2 and o.min_ratio == 1e-4
-    assert ctypes.sizeof(_lib.LbaOptions) == 2 * 4 + 8 * 8 + 4 * 4 + 8
-    assert (o.loss, o.flags, o.f_scale) == (0, 0, 1.0)
-    assert ctypes.sizeof(_lib.LbaReport) == 6 * 4 + 3 * 8 + 8 + 2 * 4 * 512 + 6 * 8 * 512
+    assert (o.loss, o.flags, o.f_scale, o.max_evals, o.max_backtrack) == (0, 0, 1.0, 0, 1)
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc is not available")
+    fields_o = [f[0] for f in _lib.LbaOptions._fields_]
+    fields_r = [f[0] for f in _lib.LbaReport._fields_]
+    src = "#include <stdio.h>\n#include <stddef.h>\n#include \"lba.h\"\nint main(void){\n"
+    src += 'printf("%zu %zu\\n", sizeof(lba_options), sizeof(lba_report));\n'
+    for f in fields_o:
+        src += f'printf("o {f} %zu\\n", offsetof(lba_options, {f}));\n'
+    for f in fields_r:
+        src += f'printf("r {f} %zu\\n", offsetof(lba_report, {f}));\n'
+    src += "return 0;}\n"
+    (tmp_path / "lay.c").write_text(src)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "lay"), str(tmp_path / "lay.c")], check=True)
+    out = subprocess.run([str(tmp_path / "lay")], capture_output=True, text=True, check=True).stdout.splitlines()
+    so, sr = (int(x) for x in out[0].split())
+    assert ctypes.sizeof(_lib.LbaOptions) == so and ctypes.sizeof(_lib.LbaReport) == sr
+    for line in out[1:]:
+        which, name, off = line.split()
+        cls = _lib.LbaOptions if which == "o" else _lib.LbaReport
+        assert getattr(cls, name).offset == int(off), line
 
 
 def test_no_gpu_fails_loudly():
@@ -56,13 +77,34 @@ def test_no_gpu_fails_loudly():
 
 
 def test_product_never_imports_the_oracle():
+    """The product package neither imports oracle/ nor touches /root/reference: the path may appear in comments and
+    docstrings (citations) only -- never in code or in a string the code uses."""
+    import ast
     pkg = os.path.join(ROOT, "amuya_sfm_lines_beta_b200")
+    checked = 0
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                src = open(path).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
-                assert "/root/reference" not in src.replace("/root/reference/src/bundle_adjustment.py", "") or f.endswith((".cu", ".cuh", ".py", ".h"))
+                tree = ast.parse(src)
+                doc_nodes = set()
+                for node in ast.walk(tree):
+                    if isinstance(node, (ast.Module, ast.ClassDef, ast.FunctionDef, ast.AsyncFunctionDef)) and node.body and \
+                            isinstance(node.body[0], ast.Expr) and isinstance(node.body[0].value, ast.Constant):
+                        doc_nodes.add(id(node.body[0].value))
+                for node in ast.walk(tree):
+                    if isinstance(node, ast.Constant) and isinstance(node.value, str) and id(node) not in doc_nodes:
+                        assert "/root/reference" not in node.value and "oracle" not in node.value.split("/"), (f, node.value[:80])
+                checked += 1
+            elif f.endswith((".cu", ".cuh", ".h")):
+                src = open(path).read()
+                code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+                code = re.sub(r"//[^\n]*", "", code)
+                assert "/root/reference" not in code and "oracle" not in code, f
+                checked += 1
+    assert checked >= 8
 
 
 class _P:  # minimal stand-ins for the reference's Point/Line/Line3D attribute bags (src/point.py, src/line.py)

@@ -158,3 +158,77 @@ def test_spd6_inverse_matches_numpy(geo):
     Z = np.zeros((1, 21)); c1 = np.empty(1, dtype=np.int32)
     geo.geo_spd6(C.c_long(1), ptr(Z), ptr(c1))
     assert c1[0] > 0 and np.all(np.isfinite(Z))
+
+
+# ---------------------------------------------------------------- the LM step policy (csrc/lba_policy.cuh)
+POLICY_SRC = r"""
+#include <string.h>
+#include "lba_policy.cuh"
+using namespace lba;
+extern "C" {
+// replays a sequence of trials through lm_decide; st_out rows: lam, sigma, alpha(next), cur, need_solve, done, status, it, evals, n_acc
+int policy_replay(int n, const double* cost_new, const double* rjd, const double* jd2, const double* d2, const double* x2,
+                  const double* g_norm, const int* pcg, double cost0, double lam0, int max_iter, int max_evals,
+                  int max_backtrack, double ftol, double xtol, double gtol, double* st_out) {
+  LmCtl L; memset(&L, 0, sizeof L);
+  L.ftol = ftol; L.xtol = xtol; L.gtol = gtol; L.lambda_min = 1e-6; L.lambda_max = 1e12; L.min_ratio = 1e-4;
+  L.max_iter = max_iter; L.max_evals = max_evals; L.pcg_max_iter = 200; L.max_backtrack = max_backtrack;
+  L.lam = lam0; L.nu = 2.0; L.sigma = 1.0; L.alpha = 1.0; L.cost = cost0; L.need_solve = 1; L.evals = 1; L.scaling_mode = 2;
+  int k = 0;
+  for (; k < n && !L.done; ++k) {
+    LmTrial t; t.cost_new = cost_new[k]; t.rjd = rjd[k]; t.jd2 = jd2[k]; t.d2 = d2[k]; t.x2 = x2[k]; t.g_norm = g_norm[k];
+    t.pcg_iters = pcg[k]; t.pcg_done = 1;
+    lm_decide(L, t, nullptr);
+    double* o = st_out + 10 * k;
+    o[0] = L.lam; o[1] = L.sigma; o[2] = L.alpha; o[3] = L.cur; o[4] = L.need_solve; o[5] = L.done; o[6] = L.status;
+    o[7] = L.it; o[8] = L.evals; o[9] = L.n_acc;
+  }
+  return k;
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def policy(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ is not available")
+    d = tmp_path_factory.mktemp("policy_host")
+    (d / "policy.cpp").write_text(POLICY_SRC)
+    so = d / "libpolicy_host.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "amuya_sfm_lines_beta_b200", "csrc"),
+                    "-o", str(so), str(d / "policy.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    lib.policy_replay.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("scene,kw", [("manual3", dict(max_iter=40, max_evals=22)), ("toy1_lv9", dict(max_iter=12)),
+                                      ("synth", dict(max_iter=60, ftol=1e-4))])
+def test_step_policy_header_follows_the_oracle(policy, scene, kw):
+    """The decision kernel's function, compiled for the host and fed the oracle's own per-trial scalars, takes the
+    oracle's decisions: same accepts / retries / termination and the same damping and step lengths (bit-equal)."""
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene, scene_from_npz
+    s = make_synthetic_scene(12, 200, 5, seed=1) if scene == "synth" else scene_from_npz(os.path.join(GOLD, scene + ".npz"))
+    kw = dict(dict(ftol=0.0, xtol=0.0, gtol=0.0), **kw)
+    rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(**kw))[3]
+    tr = rep.trace
+    n = len(tr)
+    arr = lambda key: np.ascontiguousarray([t[key] for t in tr], dtype=np.float64)   # noqa: E731
+    pcg = np.ascontiguousarray([t["pcg"] for t in tr], dtype=np.int32)
+    out = np.zeros((n, 10))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))   # noqa: E731
+    k = policy.policy_replay(n, dp(arr("cost_new")), dp(arr("rjd")), dp(arr("jd2")), dp(arr("d2")), dp(arr("x2")), dp(arr("g_norm")),
+                             pcg.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(rep.cost_init), C.c_double(1e-2),
+                             kw["max_iter"], kw.get("max_evals", 0), 1, C.c_double(kw["ftol"]), C.c_double(kw["xtol"]),
+                             C.c_double(kw["gtol"]), dp(out))
+    assert k == n
+    # state after trial j is what the oracle used for trial j+1
+    for j in range(n - 1):
+        assert out[j, 0] == tr[j + 1]["lam"], (j, out[j, 0], tr[j + 1]["lam"])
+        assert out[j, 2] == tr[j + 1]["alpha"], (j, out[j, 2], tr[j + 1]["alpha"])
+        assert int(out[j, 4]) == (1 if tr[j + 1]["it"] != tr[j]["it"] else 0)
+        assert int(out[j, 5]) == 0
+    assert int(out[n - 1, 9]) == rep.n_accepted and int(out[n - 1, 7]) == rep.iterations
+    assert int(out[n - 1, 5]) == 1 and int(out[n - 1, 6]) == rep.status
+    assert int(out[n - 1, 3]) == rep.n_accepted % 2

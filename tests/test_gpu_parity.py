@@ -238,6 +238,9 @@ def test_p4_lm_trajectory_matches_oracle(LineBA, orc, scene, iters):
           f"(floor {fin['cost']:.2e})")
     assert acc_d == [t["accepted"] for t in rep.trace]
     assert pcg_d == [t["pcg"] for t in rep.trace]
+    assert [t["it"] for t in res.trace] == [t["it"] for t in rep.trace]          # same retries
+    assert np.allclose([t["alpha"] for t in res.trace], [t["alpha"] for t in rep.trace], rtol=max(1e-6, FLOOR_MULT * floor.max()))
+    assert res.n_accepted == rep.n_accepted
     assert np.all(np.abs(cost_d - cost_o) <= np.maximum(RTOL_TRAJ, FLOOR_MULT * floor) * np.abs(cost_o))
     assert abs(res.cost - rep.cost) <= max(RTOL_FINAL, FLOOR_MULT * fin["cost"]) * rep.cost
     assert np.max(np.abs(res.camera_params - cams_o)) <= max(RTOL_FINAL, FLOOR_MULT * fin["cams"]) * np.max(np.abs(cams_o))
@@ -302,21 +305,29 @@ def test_p5_dropin_beats_reference_run(LineBA, capsys):
 
 
 def test_p5_final_cost_vs_reference_on_every_fixture(LineBA, capsys):
-    """Default options on every fixture: the CUDA solver ends below the final cost of the reference's scipy
-    call as shipped; the cost of scipy with the analytic Jacobian at 15 Jacobian evaluations is printed
-    beside it (tests/golden/p5_costs.json)."""
+    """SURVEY 8(c) P5 on every fixture, at the SAME number of evaluations as the reference's scipy call was given
+    (max_nfev = 15: the initial point + 14 trial points; every one of ours is a residual+Jacobian evaluation):
+    the CUDA solver ends at or below BOTH the reference as shipped (finite differences with the shipped sparsity
+    pattern, ftol=1e-4) and scipy with the analytic Jacobian in the right columns (tests/golden/p5_costs.json).
+    The default run (ftol=1e-4 as the reference call site) is printed beside it with its accept rate."""
     import json
-    p5 = json.load(open(os.path.join(GOLDEN, "p5_costs.json")))["fixtures"]
+    p5j = json.load(open(os.path.join(GOLDEN, "p5_costs.json")))
+    budget = p5j["njev_budget"]
     lines = []
-    for name, ref in p5.items():
+    for name, ref in p5j["fixtures"].items():
         s = synth(12, 200, 5, seed=1) if name.startswith("synth") else load(name)[0]
         ba = make_ctx(LineBA, s)
-        res = ba.lm_solve(s.camera_params, s.points_3d)
+        res = ba.lm_solve(s.camera_params, s.points_3d, max_iter=50, max_evals=budget)
+        dflt = ba.lm_solve(s.camera_params, s.points_3d)
         ba.close()
-        lines.append(f"[P5] {name:16s} init {res.cost_init:.3e}  ours {res.cost:.3e} ({res.iterations} it)  "
-                     f"reference as shipped {ref['as_shipped_cost']:.3e}  scipy+analytic J @15 {ref['analytic_cost']:.3e}")
+        lines.append(f"[P5] {name:16s} init {res.cost_init:.3e}  ours @{res.n_jac} evals {res.cost:.3e} (accepted "
+                     f"{res.n_accepted}/{len(res.trace)} trials)  reference as shipped {ref['as_shipped_cost']:.3e}  "
+                     f"scipy+analytic J @{budget} {ref['analytic_cost']:.3e} | default run: {dflt.iterations} it, "
+                     f"{dflt.n_jac} evals, status {dflt.status}, cost {dflt.cost:.3e}, accepted {dflt.n_accepted}/{len(dflt.trace)}")
         assert abs(res.cost_init - ref["cost_init"]) <= 1e-9 * ref["cost_init"]
-        assert res.cost < ref["as_shipped_cost"], lines[-1]
+        assert res.n_jac <= budget
+        assert res.cost <= min(ref["as_shipped_cost"], ref["analytic_cost"]), lines[-1]
+        assert dflt.cost <= ref["as_shipped_cost"], lines[-1]
     with capsys.disabled():
         print("\n" + "\n".join(lines))
 
@@ -478,16 +489,47 @@ def test_many_cameras_take_the_global_gather_variant(LineBA, orc):
     ba.close()
 
 
-def test_non_speculative_path_matches(LineBA):
-    """flags bit 0 disables the speculative trial Jacobian: same trajectory either way."""
-    s = synth(12, 200, 5, seed=1)
+@pytest.mark.parametrize("scene", ["manual3", "toy1_lv2", "synth_noisy"])
+def test_retry_and_evaluation_budget_match_oracle(LineBA, orc, scene):
+    """Scenes whose first Gauss-Newton steps overshoot: the rejected trial is retried at the measured length along
+    the same direction (no new solve) and `max_evals` stops the loop like scipy's max_nfev.  Same trials, same
+    lengths, same costs as the oracle."""
+    s = synth(12, 200, 5, seed=1) if scene == "synth_noisy" else load(scene)[0]
+    kw = dict(max_iter=40, max_evals=22, ftol=0.0, xtol=0.0, gtol=0.0)
     ba = make_ctx(LineBA, s)
-    a = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0)
-    b = ba.lm_solve(s.camera_params, s.points_3d, max_iter=8, ftol=0.0, flags=1)
-    assert [t["accepted"] for t in a.trace] == [t["accepted"] for t in b.trace]
-    assert np.allclose([t["cost_new"] for t in a.trace], [t["cost_new"] for t in b.trace], rtol=1e-12)
-    assert abs(a.cost - b.cost) <= 1e-12 * a.cost
+    res = ba.lm_solve(s.camera_params, s.points_3d, **kw)
+    rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(**kw))[3]
+    assert res.n_jac == 22 == 1 + len(res.trace)
+    assert [t["it"] for t in res.trace] == [t["it"] for t in rep.trace]
+    assert [t["accepted"] for t in res.trace] == [t["accepted"] for t in rep.trace]
+    if scene != "toy1_lv2":
+        assert len(res.trace) > res.iterations          # at least one retry happened
+    assert np.allclose([t["alpha"] for t in res.trace], [t["alpha"] for t in rep.trace], rtol=1e-6)
+    cost_d = np.array([t["cost_new"] for t in res.trace]); cost_o = np.array([t["cost_new"] for t in rep.trace])
+    assert np.all(np.abs(cost_d - cost_o) <= 1e-6 * cost_o)
+    assert abs(res.cost - rep.cost) <= RTOL_FINAL * rep.cost
     ba.close()
+
+
+def test_config4_trajectory_matches_recorded_oracle(LineBA):
+    """BASELINE config [3] at full size (1k cameras / 200k lines / 2M observations): the device trajectory against
+    the oracle's, recorded by tests/golden/make_config4_trajectory.py (the numpy oracle needs minutes for it)."""
+    import json
+    fx = json.load(open(os.path.join(GOLDEN, "config4_trajectory.json")))
+    s = synth(1000, 200_000, 10, seed=0, variant="A")
+    ba = make_ctx(LineBA, s)
+    res = ba.lm_solve(s.camera_params, s.points_3d, **fx["options"])
+    ba.close()
+    assert abs(res.cost_init - fx["cost_init"]) <= 1e-12 * fx["cost_init"]
+    assert [t["it"] for t in res.trace] == fx["it"]
+    assert [bool(t["accepted"]) for t in res.trace] == fx["accepted"]
+    assert [t["pcg"] for t in res.trace] == fx["pcg"]
+    cost_d = np.array([t["cost_new"] for t in res.trace]); cost_o = np.array(fx["cost_new"])
+    print(f"\n[config 4] per-trial rel diff vs recorded oracle: {np.max(np.abs(cost_d - cost_o) / cost_o):.2e}")
+    assert np.all(np.abs(cost_d - cost_o) <= RTOL_TRAJ * cost_o)
+    assert abs(res.cost - fx["cost"]) <= RTOL_FINAL * fx["cost"]
+    assert abs(np.linalg.norm(res.camera_params) - fx["cams_norm"]) <= RTOL_FINAL * fx["cams_norm"]
+    assert abs(np.linalg.norm(res.points_3d) - fx["pts_norm"]) <= RTOL_FINAL * fx["pts_norm"]
 
 
 # ---------------------------------------------------------------- full size (config 4) properties
