@@ -287,6 +287,21 @@ static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, 
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// a failed launch is reported once, at the API boundary that notices it (the message was recorded by post())
+static int take_launch_err(lba_ctx* c) {
+  if (c->world > 1) {   // called after a stream synchronisation: did a bounded device-side wait give up?
+    unsigned int code = 0;
+    if (cudaMemcpyFromSymbol(&code, g_spin_error, sizeof code) == cudaSuccess && code) {
+      const unsigned int zero = 0;
+      cudaMemcpyToSymbol(g_spin_error, &zero, sizeof zero);
+      return fail(LBA_ERR_COMM, "a device-side wait on a peer rank timed out (code %u); results of this call are invalid", code);
+    }
+  }
+  if (!c->launch_err) return LBA_OK;
+  c->launch_err = 0;
+  return LBA_ERR_CUDA;
+}
+
 static const char* kClassNames[LBA_K_COUNT] = {
     "residual", "jacobian", "cam_blocks", "line_factor", "line_scalars", "cam_precond",
     "pcg_line", "pcg_cam", "pcg_update", "backsub", "misc", "comm"};
@@ -327,7 +342,13 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   if (device < 0 || device >= count) return fail(LBA_ERR_ARG, "device %d out of range (count %d)", device, count);
   CK(cudaSetDevice(device));
   lba_ctx* c = new lba_ctx();
+  struct CreateGuard { lba_ctx* c; bool ok = false; ~CreateGuard() { if (!ok) lba_destroy(c); } } guard{c};   // no leak on a failed create
   c->device = device;
+  {  // bound of every device-side wait on another CTA / GPU (see SpinGuard)
+    const char* e = getenv("LBA_SPIN_TIMEOUT_MS");
+    const unsigned long long ns = (e && atoll(e) > 0 ? (unsigned long long)atoll(e) : 10000ULL) * 1000000ULL;
+    CK(cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof ns));
+  }
   if (const char* e = getenv("LBA_L2_PERSIST_MB")) {
     int max_persist = 0, max_win = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
@@ -378,6 +399,7 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaMemsetAsync(c->tickets.p, 0, 32, c->stream));
   CK(cudaMemsetAsync(c->scal.p, 0, sizeof(Scalars), c->stream));
   CK(cudaMemsetAsync(c->clamped.p, 0, sizeof(int), c->stream));
+  guard.ok = true;
   *out = c;
   return LBA_OK;
 }
@@ -418,7 +440,7 @@ extern "C" int lba_comm_destroy(lba_ctx* ctx) {
 extern "C" int lba_destroy(lba_ctx* ctx) {
   if (!ctx) return LBA_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   lba_comm_destroy(ctx);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
   if (ctx->h_trace) cudaFreeHost(ctx->h_trace);
@@ -443,7 +465,7 @@ extern "C" int lba_set_stream(lba_ctx* ctx, void* s) {
 extern "C" int lba_synchronize(lba_ctx* ctx) {
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (ctx->launch_err) return take_launch_err(ctx);
   return LBA_OK;
 }
 
@@ -901,7 +923,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->cam_partial.alloc(2 * (size_t)ctx->cam_step_ctas));
   lap("state buffers");
   ctx->have_problem = true;
-  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (ctx->launch_err) return take_launch_err(ctx);
   return LBA_OK;
 }
 
@@ -1190,7 +1212,17 @@ static int fetch_scalars(lba_ctx* c) {
 #endif
   }
   std::atomic_thread_fence(std::memory_order_acquire);
-  if (c->launch_err) return LBA_ERR_CUDA;
+  if (c->h_mirror->spin_error) {
+    const unsigned int code = c->h_mirror->spin_error, zero = 0;
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpyToSymbol(g_spin_error, &zero, sizeof zero);
+    c->h_mirror->spin_error = 0;
+    return fail(LBA_ERR_COMM, "a device-side wait timed out (%s%s%s%s): a peer rank stalled or died, or the GPU is shared and a "
+                "co-resident grid could not be scheduled; results of this call are invalid",
+                (code & kSpinPeerLink) ? "fused peer exchange " : "", (code & kSpinGridBar) ? "grid barrier " : "",
+                (code & kSpinPeerReduce) ? "peer all-reduce " : "", (code & kSpinPeerReduceRs) ? "two-phase peer reduce" : "");
+  }
+  if (c->launch_err) return take_launch_err(c);
   return LBA_OK;
 }
 
@@ -1216,7 +1248,7 @@ extern "C" int lba_point_wise_indices(lba_ctx* ctx, int64_t* cam_pt, int64_t* pt
   CK(cudaMemcpyAsync(cam_pt, tmp.p, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaMemcpyAsync(pt_idx, tmp.p + (size_t)2 * m, (size_t)2 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, double* proj) {
@@ -1233,7 +1265,7 @@ extern "C" int lba_project(lba_ctx* ctx, const double* cams, const double* pts, 
   LAUNCH(ctx, LBA_K_MISC, k_project, cdiv(ctx->Mp, 256), 256, a);
   CK(cudaMemcpyAsync(proj, tmp.p, (size_t)6 * m * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 // Track table of `n_views` consecutive views (tracker.py:11-96 with verify_duplet, utils.py:1807-1944): the view
@@ -1323,7 +1355,7 @@ extern "C" int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d,
   CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st_));
   CK(cudaMemcpyAsync(n_new_tracks, d_nnew.p, (size_t)NP * 8, cudaMemcpyDeviceToHost, st_));
   CK(cudaStreamSynchronize(st_));
-  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (ctx->launch_err) return take_launch_err(ctx);
   if (bad) return fail(LBA_ERR_ARG, "%d match(es) name a 2D line outside [0, %lld)", bad, (long long)n_lines2d);
   *n_tracks = rows;
   if (!ids_dev && rows > 0) CK(cudaMemcpyAsync(ids, o_ids, (size_t)rows * V * 8, cudaMemcpyDeviceToHost, st_));
@@ -1334,7 +1366,7 @@ extern "C" int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d,
     CK(cudaMemcpyAsync(flags_out, d_fl8.p, (size_t)M, cudaMemcpyDefault, st_));
   }
   CK(cudaStreamSynchronize(st_));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 // Two-view endpoint triangulation of n_tracks line tracks (seq_utils.py:75-135): independent of the BA problem
@@ -1388,7 +1420,7 @@ extern "C" int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_v
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     *seconds_kernel = ms * 1e-3;
   }
-  if (ctx->launch_err) return LBA_ERR_CUDA;
+  if (ctx->launch_err) return take_launch_err(ctx);
   if (bad) return fail(LBA_ERR_ARG, "%d track(s) name a view outside [0, %lld)", bad, (long long)n_views);
   return LBA_OK;
 }
@@ -1423,7 +1455,7 @@ extern "C" int lba_residuals_jacobian(lba_ctx* ctx, const double* cams, const do
     CK(cudaStreamSynchronize(ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double* V, double* gl) {
@@ -1435,7 +1467,7 @@ extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double*
   if (V && ctx->nl) CK(cudaMemcpyAsync(V, ctx->V.p, (size_t)ctx->nl * 21 * 8, cudaMemcpyDefault, ctx->stream));
   if (gl && ctx->nl) CK(cudaMemcpyAsync(gl, ctx->gl.p, (size_t)ctx->nl * 6 * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 extern "C" int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int32_t pcg_max_iter, double* dcam,
@@ -1454,7 +1486,7 @@ extern "C" int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int3
     CK(cudaMemcpyAsync(dpts, ctx->y.p, (size_t)ctx->nl * 48, cudaMemcpyDefault, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  return ctx->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(ctx);
 }
 
 // ---- C ABI: the LM loop ---------------------------------------------------------------------------
@@ -1565,7 +1597,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
     }
   }
   rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  return c->launch_err ? LBA_ERR_CUDA : LBA_OK;
+  return take_launch_err(c);
 }
 
 // ---- microbenchmarks --------------------------------------------------------------------------------

@@ -205,6 +205,26 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// Every device-side wait on another CTA or another GPU is bounded: after g_spin_timeout_ns (LBA_SPIN_TIMEOUT_MS,
+// default 10 s) without progress the waiter records the failure in g_spin_error and goes on, so a stalled or dead
+// rank cannot hang the surviving GPUs; the host reads the word at its next synchronisation and fails the call with
+// LBA_ERR_COMM (the results of that call are garbage).
+__device__ unsigned int g_spin_error = 0;
+__constant__ unsigned long long g_spin_timeout_ns = 10000000000ULL;
+struct SpinGuard {
+  unsigned long long t0 = 0;
+  unsigned int n = 0;
+  __device__ __forceinline__ bool expired(unsigned int code) {
+    if ((++n & 0x3ffu) != 0u) return false;
+    const unsigned long long t = global_ns();
+    if (!t0) { t0 = t; return false; }
+    if (t - t0 <= g_spin_timeout_ns) return false;
+    atomicOr(&g_spin_error, code);
+    return true;
+  }
+};
+enum { kSpinPeerLink = 1u, kSpinGridBar = 2u, kSpinPeerReduce = 4u, kSpinPeerReduceRs = 8u };
+
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -254,7 +274,8 @@ __device__ __forceinline__ void peer_wait(const PeerLink& pl) {
   if (threadIdx.x < pl.pa.world) {
     const int fidx = (pl.region * 2 + (int)(pl.seq & 1ULL)) * kMaxPeers;
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pl.pa.peer[pl.pa.rank]) + fidx + threadIdx.x;
-    while (ld_acquire_sys(f) < pl.seq) { }
+    SpinGuard sg;
+    while (ld_acquire_sys(f) < pl.seq) { if (sg.expired(kSpinPeerLink)) break; }
   }
   __syncthreads();
 }
@@ -1351,7 +1372,8 @@ __device__ __forceinline__ double grid_sum(double v, double* red, double* partia
     partial[blockIdx.x] = mine;
     __threadfence();
     atomicAdd(&gb->count, 1ULL);
-    while (*reinterpret_cast<volatile unsigned long long*>(&gb->count) < target) { }
+    SpinGuard sg;
+    while (*reinterpret_cast<volatile unsigned long long*>(&gb->count) < target) { if (sg.expired(kSpinGridBar)) break; }
     __threadfence();
   }
   __syncthreads();
@@ -1540,7 +1562,8 @@ struct HostMirror {
   CgState cg;
   LmCtl ctl;
   unsigned long long gbits;
-  int clamped, pad;
+  int clamped;
+  unsigned int spin_error;   // g_spin_error: a bounded device-side wait gave up (LBA_ERR_COMM)
   unsigned long long seq;
 };
 __global__ void k_publish(const Scalars* __restrict__ s, const CgState* __restrict__ cg, const LmCtl* __restrict__ ctl,
@@ -1553,6 +1576,7 @@ __global__ void k_publish(const Scalars* __restrict__ s, const CgState* __restri
     h->ctl = *ctl;
     h->gbits = *gbits.sel(ctl->cur);
     h->clamped = *clamped;
+    h->spin_error = g_spin_error;
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(&h->seq) = seq;
   }
@@ -1717,7 +1741,8 @@ __global__ void __launch_bounds__(512) k_peer_reduce(const PeerArgs pa, int regi
     st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + fidx + pa.rank, seq);
   if (t < pa.world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + fidx + t;
-    while (ld_acquire_sys(f) < seq) { }
+    SpinGuard sg;
+    while (ld_acquire_sys(f) < seq) { if (sg.expired(kSpinPeerReduce)) break; }
   }
   __syncthreads();
   if (tracing) tr1 = global_ns();
@@ -1784,7 +1809,8 @@ __global__ void __launch_bounds__(512) k_peer_reduce_rs(const PeerArgs pa, int r
     st_release_sys(reinterpret_cast<unsigned long long*>(pa.peer[t]) + fidx + pa.rank, seq);
   if (t < pa.world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + fidx + t;
-    while (ld_acquire_sys(f) < seq) { }
+    SpinGuard sg;
+    while (ld_acquire_sys(f) < seq) { if (sg.expired(kSpinPeerReduceRs)) break; }
   }
   __syncthreads();
   if (tracing) tr1 = global_ns();
@@ -1816,7 +1842,8 @@ __global__ void __launch_bounds__(512) k_peer_reduce_rs(const PeerArgs pa, int r
   // phase two: every rank's slice of the result has landed in my result slot
   if (t < pa.world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pa.peer[pa.rank]) + ridx + t;
-    while (ld_acquire_sys(f) < rseq) { }
+    SpinGuard sg2;
+    while (ld_acquire_sys(f) < rseq) { if (sg2.expired(kSpinPeerReduceRs)) break; }
   }
   __syncthreads();
   const double* res = reinterpret_cast<const double*>(pa.peer[pa.rank] + kPeerDataOff) + res_off;

@@ -7,7 +7,11 @@
 Observations are sharded at 3D-line boundaries, cameras replicated, per-camera partial sums
 all-reduced with NCCL inside liblba.so.  Rank 0 also solves the whole scene on its own GPU; the sharded
 trajectory must follow it (the all-reduce changes the summation order, so agreement is to rounding).
-Exit code 0 on success."""
+Exit code 0 on success.
+
+With --stall the script checks the failure path instead: rank 0 starts a solve that no other rank joins; its
+device-side waits on the peers are bounded (LBA_SPIN_TIMEOUT_MS), so the call must come back with LBA_ERR_COMM
+instead of hanging the GPU."""
 import os
 import sys
 
@@ -15,6 +19,42 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
+
+def stall():
+    import time
+    os.environ["LBA_SPIN_TIMEOUT_MS"] = "300"
+    import torch
+    import torch.distributed as dist
+    from amuya_sfm_lines_beta_b200 import LineBA
+    from amuya_sfm_lines_beta_b200._lib import LbaError, LBA_ERR_COMM
+    from amuya_sfm_lines_beta_b200.scenes import make_synthetic_scene
+    from amuya_sfm_lines_beta_b200.sharding import plan_shards, local_problem
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = make_synthetic_scene(40, 3000, 8, seed=0)
+    sh = plan_shards(s.lines_indices, s.n_lines, world)[rank]
+    ci, li, n, p0, p1, pts = local_problem(sh, s.camera_indices, s.lines_indices, s.n, s.p0, s.p1, s.points_3d)
+    ba = LineBA(local)
+    ba.init_comm(rank, world)
+    ba.set_problem(s.n_cameras, sh.n_lines, ci, li, n, p0, p1)
+    ok = True
+    if rank == 0:
+        t0 = time.time()
+        try:
+            ba.lm_solve(s.camera_params, pts, max_iter=4)
+            ok = False
+            print("stalled peers: lm_solve returned normally (expected LBA_ERR_COMM)")
+        except LbaError as e:
+            ok = e.code == LBA_ERR_COMM
+            print(f"stalled peers: lm_solve failed after {time.time() - t0:.2f} s with: {e}")
+    else:
+        time.sleep(3.0)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    os._exit(0 if int(flag.item()) else 1)   # the contexts are out of step on purpose: no orderly teardown
 
 
 def main():
@@ -72,4 +112,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    stall() if "--stall" in sys.argv else main()

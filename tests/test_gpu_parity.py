@@ -254,10 +254,12 @@ def test_p4_lm_trajectory_matches_oracle(LineBA, orc, scene, iters):
 
 @pytest.mark.parametrize("scene", ["synth_small", "synth_mid", "toy1_lv9"])
 def test_p4_strict_on_well_conditioned_scenes(LineBA, orc, scene):
-    """No floor allowance: 1e-9 per iteration, 1e-6 final, on scenes with many cameras per gauge."""
+    """No floor allowance: 1e-9 per iteration, 1e-6 final, on scenes with many cameras per gauge.  (toy1_lv9 is
+    noise-free: from the sixth iteration on its damping has fallen below 1e-4 and the seven gauge directions, which
+    only the damping holds, set a rounding floor above 1e-9 -- the floor-aware test above covers those iterations.)"""
     s = {"synth_small": lambda: synth(12, 200, 5, seed=1), "synth_mid": lambda: synth(50, 2000, 10, seed=0),
          "toy1_lv9": lambda: load("toy1_lv9")[0]}[scene]()
-    kw = dict(max_iter=8, ftol=0.0, xtol=0.0, gtol=0.0)
+    kw = dict(max_iter=5 if scene == "toy1_lv9" else 8, ftol=0.0, xtol=0.0, gtol=0.0)
     ba = make_ctx(LineBA, s)
     res = ba.lm_solve(s.camera_params, s.points_3d, **kw)
     cams_o, pts_o, r_o, rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions(**kw))
@@ -581,3 +583,18 @@ def test_multi_gpu_sharded_solve_matches_single_gpu(transport):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", script],
                          capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_multi_gpu_stalled_peer_is_an_error_not_a_hang():
+    """A rank whose peers never join the exchange gets LBA_ERR_COMM from the bounded device-side waits."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_multigpu_parity.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", script, "--stall"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "LBA_ERR_COMM" in out.stdout or "error -6" in out.stdout, out.stdout[-2000:]
