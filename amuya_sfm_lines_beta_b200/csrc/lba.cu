@@ -136,7 +136,7 @@ struct lba_ctx {
   DBuf<double> U, gc, Dc, Mpart, bpart, Minv, b;
   DBuf<double> cgx, cgr, cgz, cgp, tab, qpart;
   DBuf<double> cost_partial, bs_partial, cam_partial;
-  DBuf<Scalars> scal;
+  DBuf<Scalars> scal, scal_loc;   // reduced over ranks (read by k_lm_decide and the host) / this rank's sums
   DBuf<LmCtl> ctl;        // device-resident state of the running LM solve (decisions are taken on the device)
   DBuf<LmTrace> trace;
   LmTrace* h_trace = nullptr;   // pinned
@@ -382,6 +382,8 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   c->h_scal = &c->h_mirror->scal; c->h_cgst = &c->h_mirror->cg;
   c->h_gbits = &c->h_mirror->gbits; c->h_clamped = &c->h_mirror->clamped; c->h_ctl = &c->h_mirror->ctl;
   CKR(c->scal.alloc(1));
+  CKR(c->scal_loc.alloc(1));
+  CK(cudaMemsetAsync(c->scal_loc.p, 0, sizeof(Scalars), c->stream));
   CKR(c->ctl.alloc(1));
   CKR(c->trace.alloc(1));
   CK(cudaMemsetAsync(c->ctl.p, 0, sizeof(LmCtl), c->stream));
@@ -513,9 +515,9 @@ extern "C" int lba_comm_init(lba_ctx* ctx, const void* id128, int32_t rank, int3
   return LBA_OK;
 }
 
-static int nccl_allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+static int nccl_allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op, const void* src = nullptr) {
   c->pre(LBA_K_COMM);
-  ncclResult_t r = g_nccl.AllReduce(buf, buf, n, dt, op, c->comm, c->stream);
+  ncclResult_t r = g_nccl.AllReduce(src ? src : buf, buf, n, dt, op, c->comm, c->stream);
   c->post(LBA_K_COMM);
   --c->launches;  // a library collective is not one of our kernels
   if (r != ncclSuccess) return fail(LBA_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -572,35 +574,45 @@ static int reduce_finish(lba_ctx* c, int region, double* local, size_t n) {
   return LBA_OK;
 }
 
-// Small in-place all-reduce of a few scalars that live in ordinary device memory (copy variant).
-static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op) {
+// Small all-reduce of a few scalars that live in ordinary device memory (copy variant): buf <- reduce(src), in
+// place when src is NULL.
+static int allreduce(lba_ctx* c, void* buf, size_t n, ncclDataType_t dt, ncclRedOp_t op, const void* src = nullptr) {
   if (c->world <= 1 || n == 0) return LBA_OK;
-  if (!peer_fits(c, kRgnS, n)) return nccl_allreduce(c, buf, n, dt, op);
+  if (!peer_fits(c, kRgnS, n)) return nccl_allreduce(c, buf, n, dt, op, src);
+  if (!src) src = buf;
   const unsigned long long seq = ++c->rgn_seq[kRgnS];
   c->pre(LBA_K_COMM);
   if (op == ncclMax)
     launch_kernel(c, k_peer_reduce<true>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
+                  (const double*)src, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
   else
     launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                  (const double*)buf, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
+                  (const double*)src, (double*)buf, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (const LmCtl*)nullptr);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
-static int allreduce_sum(lba_ctx* c, double* buf, size_t n) { return allreduce(c, buf, n, ncclDouble, ncclSum); }
-// the end-of-trial scalars (sum) and the gradient inf-norm bits (max) in ONE exchange.  With the peer transport
-// the kernel picks the word of the current evaluation set from the control block; the NCCL fallback reduces both.
-static int allreduce_scalars(lba_ctx* c, double* buf, size_t n, const LmCtl* ctl) {
+// The per-pass sums are produced into a LOCAL scalar block (scal_loc) and reduced into the one the decision kernel
+// and the host read (scal), so that a pass which re-uses sums of an earlier pass (a retry does not repeat the
+// back-substitution) never reduces an already reduced value again.  Single rank: the kernels write scal directly.
+static inline Scalars* scal_local(lba_ctx* c) { return c->world > 1 ? c->scal_loc.p : c->scal.p; }
+// scal.cost .. (n doubles) <- sum over ranks of the local block
+static int reduce_scalars(lba_ctx* c, size_t n) {
+  return allreduce(c, &c->scal.p->cost, n, ncclDouble, ncclSum, &scal_local(c)->cost);
+}
+// the end-of-trial scalars (sum, local block -> scal) and the gradient inf-norm bits (max) in ONE exchange.  With the
+// peer transport the kernel picks the word of the current evaluation set from the control block; the NCCL fallback
+// reduces both.
+static int allreduce_scalars(lba_ctx* c, size_t n, const LmCtl* ctl) {
   if (c->world <= 1) return LBA_OK;
   if (n > 8 || !peer_fits(c, kRgnS, 10)) {
-    CKR(allreduce_sum(c, buf, n));
+    CKR(reduce_scalars(c, n));
     CKR(allreduce(c, c->gbits.p, 1, ncclUint64, ncclMax));
     return allreduce(c, c->gbits_new.p, 1, ncclUint64, ncclMax);
   }
   const unsigned long long seq = ++c->rgn_seq[kRgnS];
   c->pre(LBA_K_COMM);
   launch_kernel(c, k_peer_reduce<false>, dim3(1), dim3(512), 0, c->peer_args, (int)kRgnS, peer_slot_off(c, kRgnS, seq), n, seq,
-                (const double*)buf, buf, c->gbits.p, c->gbits_new.p, ctl);
+                (const double*)&scal_local(c)->cost, &c->scal.p->cost, c->gbits.p, c->gbits_new.p, ctl);
   c->post(LBA_K_COMM);
   return LBA_OK;
 }
@@ -944,7 +956,7 @@ static EvalArgs eval_args(lba_ctx* c, const LmCtl* ctl, int which) {
   a.V = dual(c->V.p, c->V_new.p); a.gl = dual(c->gl.p, c->gl_new.p); a.gbits = dual(c->gbits.p, c->gbits_new.p);
   a.ctl = ctl; a.which = which;
   a.cost_partial = c->cost_partial.p;
-  a.ticket = c->tickets.p; a.cost_out = &c->scal.p->cost;
+  a.ticket = c->tickets.p; a.cost_out = &scal_local(c)->cost;
   a.loss = c->loss; a.f_scale = c->f_scale;
   return a;
 }
@@ -980,7 +992,7 @@ static int run_residual(lba_ctx* c, const LmCtl* ctl, int which) {
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 2, true>), c->grid_eval_r, 2 * kTile, c->smem_eval_r, a);
     else LAUNCH_DYN(c, LBA_K_RESIDUAL, (k_eval<false, 1, false>), c->grid_eval_r, kTile, c->smem_eval_r, a);
   } else {
-    CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
+    CK(cudaMemsetAsync(&scal_local(c)->cost, 0, 8, c->stream));
   }
   return LBA_OK;
 }
@@ -998,7 +1010,7 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
   } else {
-    CK(cudaMemsetAsync(&c->scal.p->cost, 0, 8, c->stream));
+    CK(cudaMemsetAsync(&scal_local(c)->cost, 0, 8, c->stream));
   }
   if (!ctl && which == 0) {
     c->pending_first = !c->have_scaling;
@@ -1079,7 +1091,7 @@ static int solve_setup(lba_ctx* c, const LmCtl* ctl, double lam, double pcg_tol,
   la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p;
   la.gl = dual<const double>(c->gl.p, c->gl_new.p); la.r = dual<const double>(c->r.p, c->r_new.p);
   la.dl = c->dl.p; la.alpha = 1.0;
-  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &c->scal.p->rjd; la.st = c->cgst.p; la.ctl = ctl;
+  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &scal_local(c)->rjd; la.st = c->cgst.p; la.ctl = ctl;
   if (c->ntiles > 0)
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
@@ -1167,7 +1179,7 @@ static int solve_finish(lba_ctx* c, SolvePlan* sp) {
     LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->grid_lp[1], kTile, c->smem_lp[1], sp->la);
   } else {
     if (c->nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemsetAsync(&c->scal.p->rjd, 0, 32, c->stream));
+    CK(cudaMemsetAsync(&scal_local(c)->rjd, 0, 32, c->stream));
   }
   return launch_cam_step(c, sp->la.ctl);
 }
@@ -1429,7 +1441,7 @@ extern "C" int lba_residuals(lba_ctx* ctx, const double* cams, const double* pts
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
   CKR(load_state(ctx, cams, pts));
   CKR(run_residual(ctx, nullptr, 0));
-  CKR(allreduce_sum(ctx, &ctx->scal.p->cost, 1));
+  CKR(reduce_scalars(ctx, 1));
   CKR(export_residuals(ctx, ctx->r.p, residuals));
   CKR(fetch_scalars(ctx));
   if (cost) *cost = ctx->h_scal->cost;
@@ -1498,7 +1510,7 @@ static int enqueue_trial_tail(lba_ctx* c, const LmCtl* ctl) {
   // trial evaluation WITH its Jacobian into the other evaluation set (it becomes the current one when accepted)
   CKR(run_jacobian(c, ctl, 1));
   // cost, rjd, jd2, dl2, x2_lines are contiguous; the gradient norm of the state the solve started from rides along
-  CKR(allreduce_scalars(c, &c->scal.p->cost, 5, ctl));
+  CKR(allreduce_scalars(c, 5, ctl));
   LAUNCH(c, LBA_K_MISC, k_lm_decide, 1, 32, c->ctl.p, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p,
          dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), c->trace.p);
   return LBA_OK;
@@ -1525,7 +1537,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   // the camera scaling is a running maximum that every solve set-up refreshes (k_cam_finish): start it from zero
   if (c->nc > 0) CK(cudaMemsetAsync(c->Dc.p, 0, (size_t)c->nc * 48, c->stream));
   CKR(run_jacobian(c, nullptr, 0));
-  CKR(allreduce_sum(c, &c->scal.p->cost, 1));
+  CKR(reduce_scalars(c, 1));
   LmCtl init;
   memset(&init, 0, sizeof init);
   init.ftol = o.ftol; init.xtol = o.xtol; init.gtol = o.gtol; init.lambda_min = o.lambda_min; init.lambda_max = o.lambda_max;

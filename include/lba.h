@@ -159,7 +159,9 @@ int lba_project(lba_ctx* ctx, const double* camera_params, const double* points_
  *   ids, bin (cap_rows,n_views) int64 out, cap_rows >= M: ids[track,view] (0 where absent) and bin[track,view]
  *       (tracker.py:93-95; the reference holds the same integers in float64 arrays); n_new_tracks (n_views-1,) int64
  *       HOST out; *n_tracks HOST out: rows used; flags_out (M,) u8 or NULL: inlier flag per match.
- * Matches within 1e-12 of parallel to an epipolar line are outliers (the reference raises / divides by noise). */
+ * The epipolar arithmetic is rounded operation by operation like the reference's numpy code, so the flags equal the
+ * reference's also where it divides by rounding noise (segments parallel to an epipolar line within a few ulps); only an
+ * exactly zero determinant, on which the reference raises, is an outlier by rule. */
 int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d, const double* endpoints,
                     const int64_t* match_ptr, const int64_t* matches, const double* F, double threshold,
                     const uint8_t* flags_in, int64_t cap_rows, int64_t* ids, int64_t* bin,

@@ -16,17 +16,21 @@ Restates, array-native, what the reference does with Python objects:
 
 Two reference behaviours are kept on purpose: absent entries of ``ids`` are 0 and take part in the membership test
 ``l in Tr_ij[:, v]`` (tracker.py:60), so a match whose first line has id 0 extends every track that has no line in
-view v; and a line that sits in column v of several tracks extends all of them (:68-70).  One is not reproducible:
-for exactly parallel lines ``intersection`` returns ``False`` and the reference raises (utils.py:1890), and within
-rounding of parallel it divides by noise (its decision then depends on the summation order inside ``np.dot``);
-here a match whose segment is parallel to an epipolar line to within ``PARALLEL_TOL`` is an outlier.
+view v; and a line that sits in column v of several tracks extends all of them (:68-70).  For exactly parallel lines
+``intersection`` returns ``False`` and the reference raises (utils.py:1890): such a match is an outlier here.  Within
+rounding of parallel the reference divides by noise and its decision is set by the rounding of every operation,
+including the summation order inside ``np.dot``; ``duplet_inlier`` reproduces those roundings (pinned by the
+recorded flags of 2240 reference matches, 88 of them near-parallel).
 
 Pinned against the reference's own ``Tracker`` on the toy domains (tests/golden/trk_*.npz,
 make_tracker_golden.py) and against a re-run of the reference's ``verify_duplet`` on perturbed copies of them.
 """
+import math
+from fractions import Fraction
+
 import numpy as np
 
-PARALLEL_TOL = 1e-12   # |sin| of the angle between the segment and the epipolar line below which a match is dropped
+PARALLEL_TOL = 0.0   # opt-in: |sin| of the angle between the segment and the epipolar line below which a match is dropped
 
 
 def fundamental_from_cameras(K, R0, t0, R1, t1):
@@ -41,35 +45,48 @@ def fundamental_from_cameras(K, R0, t0, R1, t1):
     return F / F[2, 2]
 
 
-def duplet_inlier(F, a0, a1, b0, b1, threshold):
+def _fma(a, b, c):
+    """Correctly rounded a*b + c (Python 3.12 has no math.fma): exact rational arithmetic, rounded once."""
+    return float(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def _norm2(dx, dy):
+    """np.linalg.norm of a 2-vector: sqrt(x.dot(x)), products and sum rounded one at a time."""
+    return math.sqrt(dx * dx + dy * dy)
+
+
+def duplet_inlier(F, a0, a1, b0, b1, threshold, parallel_tol=PARALLEL_TOL):
     """One match: a0, a1 endpoints (x, y) of the segment in view v, b0, b1 of the segment in view v+1.
-    utils.py:1877-1911 in scalar arithmetic."""
+    utils.py:1877-1911 in scalar arithmetic, every operation rounded as numpy rounds it in the reference: the rows of
+    np.dot(F, [x, y, 1]) (:1886) as the BLAS kernel evaluates them, fma(F_k0, x, F_k1 * y) + F_k2 (pinned by the
+    recorded reference flags, which are pure rounding on the near-parallel matches), the rest plain scalar ops."""
     F = np.asarray(F, dtype=np.float64)
+    a0 = [float(v) for v in a0]; a1 = [float(v) for v in a1]; b0 = [float(v) for v in b0]; b1 = [float(v) for v in b1]
     # line through b0, b1 (:1250)
     A = b0[1] - b1[1]
     B = b1[0] - b0[0]
     Cc = b0[0] * b1[1] - b1[0] * b0[1]
     inter = []
     for a in (a0, a1):
-        l0 = F[0, 0] * a[0] + F[0, 1] * a[1] + F[0, 2]          # np.dot(F, [x, y, 1]) (:1886)
-        l1 = F[1, 0] * a[0] + F[1, 1] * a[1] + F[1, 2]
-        l2 = F[2, 0] * a[0] + F[2, 1] * a[1] + F[2, 2]
+        l0 = _fma(F[0, 0], a[0], float(F[0, 1]) * a[1]) + float(F[0, 2])
+        l1 = _fma(F[1, 0], a[0], float(F[1, 1]) * a[1]) + float(F[1, 2])
+        l2 = _fma(F[2, 0], a[0], float(F[2, 1]) * a[1]) + float(F[2, 2])
         D = A * l1 - B * l0                                      # intersection (:1279)
         Dx = -Cc * l1 + B * l2
         Dy = -A * l2 + Cc * l0
-        # parallel lines: the reference raises on D == 0 and divides by rounding noise next to it; both are
-        # declared outliers here (same guard in csrc/lba_tracks.cuh)
-        if abs(D) <= PARALLEL_TOL * np.hypot(A, B) * np.hypot(l0, l1):
+        if D == 0.0:                 # the reference raises here (intersection returns False, :1890): outlier by rule
             return False
+        if parallel_tol > 0.0 and not abs(D) > parallel_tol * _norm2(A, B) * _norm2(l0, l1):
+            return False             # opt-in: drop matches within parallel_tol of parallel
         inter.append((Dx / D, Dy / D))
     (x0, y0), (x1, y1) = inter
-    len_line = np.hypot(x1 - x0, y1 - y0)
-    len_corr = np.hypot(b1[0] - b0[0], b1[1] - b0[1])
+    len_line = _norm2(x1 - x0, y1 - y0)
+    len_corr = _norm2(b1[0] - b0[0], b1[1] - b0[1])
     thr = threshold * min(len_line, len_corr)
-    d11 = np.hypot(b0[0] - x0, b0[1] - y0)
-    d22 = np.hypot(b1[0] - x1, b1[1] - y1)
-    d12 = np.hypot(b0[0] - x1, b0[1] - y1)
-    d21 = np.hypot(b1[0] - x0, b1[1] - y0)
+    d11 = _norm2(b0[0] - x0, b0[1] - y0)
+    d22 = _norm2(b1[0] - x1, b1[1] - y1)
+    d12 = _norm2(b0[0] - x1, b0[1] - y1)
+    d21 = _norm2(b1[0] - x0, b1[1] - y0)
     if d11 < thr or d22 < thr:
         if (d11 <= d22 and d22 < d21) or (d22 < d11 and d11 < d12):
             return True

@@ -2,11 +2,10 @@
 data-parallel formulation against the sequential one (including the reference's quirks), the device arithmetic of
 the epipolar test checked on the host, and (``-m gpu``) the CUDA path through the C ABI.
 
-Parity bar: integer tables (ids, bin, n_new_tracks) bit-exact.  Inlier flags equal to the reference's for every
-match that is not numerically degenerate: a segment parallel to its epipolar line within rounding makes the
-reference divide by noise (its flag then depends on the summation order inside np.dot); those matches are outliers
-here by rule (PARALLEL_TOL) and are excluded from the flag comparison; with the reference's flags fed in, the
-tables equal the reference's exactly."""
+Parity bar: everything bit-exact with the flags computed HERE (nothing of the reference fed in): inlier flags, ids, bin
+and n_new_tracks equal the reference's own Tracker on all three toy domains -- including the 88 matches whose
+segment is parallel to an epipolar line within 1e-9, where the reference divides by rounding noise and its flag is
+set by the rounding of every operation (the epipolar arithmetic reproduces those roundings, see csrc/lba_tracks.cuh)."""
 import ctypes as C
 import os
 import shutil
@@ -88,13 +87,15 @@ def test_oracle_flags_and_tables_match_reference(name):
     q = load(name)
     ids, bi, n_new, fl = K.comp_tracker(q["endpoints"], q["pairs"], q["F"])
     fl = np.concatenate(fl)
-    ok = ~degenerate(q)
-    assert ok.mean() > 0.9                                       # (toy 1 has ~7 % of its edges on epipolar lines)
-    assert np.array_equal(fl[ok], q["flags"][ok])
-    assert not np.any(fl[degenerate(q, 1e-13)])                  # parallel within rounding: outliers by rule
-    if np.array_equal(fl, q["flags"]):
-        assert np.array_equal(ids, q["ids"].astype(np.int64)) and np.array_equal(bi, q["bin"].astype(np.int64))
-        assert np.array_equal(n_new, q["n_new_tracks"])
+    assert np.array_equal(fl, q["flags"])                        # every match, the near-parallel ones included
+    if name == "trk_toy1_lv5":
+        assert degenerate(q).sum() >= 40 and q["flags"][degenerate(q)].sum() >= 1   # the fixture does exercise them
+    assert np.array_equal(ids, q["ids"].astype(np.int64)) and np.array_equal(bi, q["bin"].astype(np.int64))
+    assert np.array_equal(n_new, q["n_new_tracks"])
+    # the opt-in tolerance drops the matches that are parallel within rounding
+    assert not any(K.duplet_inlier(q["F"][v], *q["endpoints"][l0], *q["endpoints"][l1], 0.1, parallel_tol=1e-12)
+                   for v, m in enumerate(q["pairs"]) for j, (l0, l1) in enumerate(m)
+                   if degenerate(q, 1e-13)[q["match_ptr"][v] + j])
     # with the reference's own flags the tables are the reference's, exactly
     pf = [q["flags"][q["match_ptr"][v]:q["match_ptr"][v + 1]] for v in range(len(q["pairs"]))]
     ids2, bi2, n2 = tables_from_flags(q["pairs"], pf, q["R"].shape[0], K.comp_tracker)
@@ -164,7 +165,7 @@ def host_duplets(tmp_path_factory):
     d = tmp_path_factory.mktemp("trk_host")
     (d / "host.cpp").write_text(HOST_SRC)
     so = d / "libtrk_host.so"
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "amuya_sfm_lines_beta_b200", "csrc"),
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "amuya_sfm_lines_beta_b200", "csrc"),
                     "-o", str(so), str(d / "host.cpp")], check=True)
     lib = C.CDLL(str(so))
 
@@ -182,8 +183,7 @@ def host_duplets(tmp_path_factory):
 def test_device_epipolar_test_on_host_matches_reference(host_duplets, name):
     q = load(name)
     fl = np.concatenate([host_duplets(q["F"][v], q["endpoints"], m) for v, m in enumerate(q["pairs"])])
-    ok = ~degenerate(q)
-    assert np.array_equal(fl[ok], q["flags"][ok]) and not np.any(fl[degenerate(q, 1e-13)])
+    assert np.array_equal(fl, q["flags"])                        # the reference's flag for every match
     assert np.array_equal(fl, np.concatenate(K.comp_tracker(q["endpoints"], q["pairs"], q["F"])[3]))
 
 
@@ -219,9 +219,11 @@ def test_gpu_track_table_matches_oracle_and_reference(gpu_ba, name):
     o_ids, o_bin, o_new, o_fl = K.comp_tracker(q["endpoints"], q["pairs"], q["F"])
     assert np.array_equal(fl, np.concatenate(o_fl))
     assert np.array_equal(ids, o_ids) and np.array_equal(bi, o_bin) and np.array_equal(n_new, o_new)
-    ok = ~degenerate(q)
-    assert np.array_equal(fl[ok], q["flags"][ok])
-    # the reference's flags in -> the reference's tables out, bit-exact
+    # own flags, own tables == the reference's Tracker, every match and every entry
+    assert np.array_equal(fl, q["flags"])
+    assert np.array_equal(ids, q["ids"].astype(np.int64)) and np.array_equal(bi, q["bin"].astype(np.int64))
+    assert np.array_equal(n_new, q["n_new_tracks"])
+    # (and with the reference's flags fed in, too)
     ids2, bi2, n2 = gpu_ba.track_table(q["endpoints"], q["pairs"], q["F"], flags_in=q["flags"])
     assert np.array_equal(ids2, q["ids"].astype(np.int64)) and np.array_equal(bi2, q["bin"].astype(np.int64))
     assert np.array_equal(n2, q["n_new_tracks"])
