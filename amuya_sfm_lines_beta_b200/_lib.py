@@ -20,7 +20,7 @@ LBA_ERR_CUDA, LBA_ERR_ARG, LBA_ERR_STATE, LBA_ERR_UNSUPPORTED, LBA_ERR_NONFINITE
 
 EXPORTS = [
     "lba_last_error", "lba_version", "lba_default_options", "lba_create", "lba_destroy", "lba_set_stream",
-    "lba_synchronize", "lba_set_problem", "lba_point_wise_indices", "lba_project", "lba_residuals",
+    "lba_synchronize", "lba_wait_stream", "lba_set_problem", "lba_point_wise_indices", "lba_project", "lba_residuals",
     "lba_residuals_jacobian", "lba_normal_equations", "lba_schur_solve", "lba_lm_solve",
     "lba_comm_unique_id", "lba_comm_init", "lba_comm_destroy", "lba_comm_peer_local", "lba_comm_peer_attach", "lba_launch_count", "lba_set_profiling",
     "lba_get_profile", "lba_kernel_class_name", "lba_measure_fp64_peak", "lba_measure_copy_bandwidth",
@@ -85,6 +85,7 @@ def load():
     lib.lba_destroy.argtypes = [vp]
     lib.lba_set_stream.argtypes = [vp, vp]
     lib.lba_synchronize.argtypes = [vp]
+    lib.lba_wait_stream.argtypes = [vp, vp]
     lib.lba_set_problem.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp]
     lib.lba_point_wise_indices.argtypes = [vp, vp, vp]
     lib.lba_project.argtypes = [vp, vp, vp, vp]

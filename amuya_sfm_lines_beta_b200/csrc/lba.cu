@@ -104,7 +104,7 @@ struct lba_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_order = nullptr;
   int n_sm = 148;
 
   // problem
@@ -374,6 +374,7 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   c->own_stream = true;
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
   CK(cudaHostAlloc(&c->h_mirror, sizeof(HostMirror), cudaHostAllocMapped));
@@ -450,6 +451,7 @@ extern "C" int lba_destroy(lba_ctx* ctx) {
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return LBA_OK;
@@ -461,6 +463,18 @@ extern "C" int lba_set_stream(lba_ctx* ctx, void* s) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)s;
   ctx->own_stream = false;
+  return LBA_OK;
+}
+
+// Order the context's stream behind work already enqueued on another stream of the same device (e.g. the PyTorch
+// stream that produced a tensor about to be passed in): event record on `s`, wait on the context's stream.
+extern "C" int lba_wait_stream(lba_ctx* ctx, void* s) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if ((cudaStream_t)s == ctx->stream) return LBA_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev_order, (cudaStream_t)s));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_order, 0));
+  if (ctx->copy_stream) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
   return LBA_OK;
 }
 

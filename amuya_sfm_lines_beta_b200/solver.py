@@ -28,16 +28,23 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def _as_ptr(x, np_dtype, torch_dtype_name, shape_size=None):
-    """Return (address, keepalive) for a C-contiguous numpy array or torch tensor."""
+def _as_ptr(x, np_dtype, torch_dtype_name, shape_size=None, ctx=None):
+    """Return (address, keepalive) for a C-contiguous numpy array or torch tensor.  A CUDA tensor must live on the
+    context's device; the context's stream is ordered behind the torch stream that (may have) produced it, so a
+    tensor written by still-running torch kernels -- or the converted temporary made here -- is complete before
+    liblba reads it."""
     if x is None:
         return None, None
     if _is_torch(x):
         import torch
         want = getattr(torch, torch_dtype_name)
+        if x.is_cuda and ctx is not None and x.device.index != ctx.device:
+            raise ValueError(f"tensor lives on cuda:{x.device.index}, the context on cuda:{ctx.device}")
         t = x if (x.dtype == want and x.is_contiguous()) else x.to(want).contiguous()
         if shape_size is not None and t.numel() != shape_size:
             raise ValueError(f"expected {shape_size} elements, got {t.numel()}")
+        if t.is_cuda and ctx is not None:
+            check(ctx._lib.lba_wait_stream(ctx._h, torch.cuda.current_stream(t.device).cuda_stream))
         return t.data_ptr(), t
     a = np.ascontiguousarray(x, dtype=np_dtype)
     if shape_size is not None and a.size != shape_size:
@@ -90,18 +97,18 @@ class LineBA:
     # -- problem ------------------------------------------------------------------
     def set_problem(self, n_cameras, n_lines, camera_indices, lines_indices, n, p0, p1):
         m = int(camera_indices.shape[0])
-        pc, k0 = _as_ptr(camera_indices, np.int64, "int64", m)
-        pl, k1 = _as_ptr(lines_indices, np.int64, "int64", m)
-        pn, k2 = _as_ptr(n, np.float64, "float64", 3 * m)
-        pa, k3 = _as_ptr(p0, np.float64, "float64", 3 * m)
-        pb, k4 = _as_ptr(p1, np.float64, "float64", 3 * m)
+        pc, k0 = _as_ptr(camera_indices, np.int64, "int64", m, ctx=self)
+        pl, k1 = _as_ptr(lines_indices, np.int64, "int64", m, ctx=self)
+        pn, k2 = _as_ptr(n, np.float64, "float64", 3 * m, ctx=self)
+        pa, k3 = _as_ptr(p0, np.float64, "float64", 3 * m, ctx=self)
+        pb, k4 = _as_ptr(p1, np.float64, "float64", 3 * m, ctx=self)
         check(self._lib.lba_set_problem(self._h, m, int(n_cameras), int(n_lines), pc, pl, pn, pa, pb))
         self.m, self.n_cameras, self.n_lines = m, int(n_cameras), int(n_lines)
         return self
 
     def _params(self, camera_params, points_3d):
-        pc, kc = _as_ptr(camera_params, np.float64, "float64", 6 * self.n_cameras)
-        pp, kp = _as_ptr(points_3d, np.float64, "float64", 6 * self.n_lines)
+        pc, kc = _as_ptr(camera_params, np.float64, "float64", 6 * self.n_cameras, ctx=self)
+        pp, kp = _as_ptr(points_3d, np.float64, "float64", 6 * self.n_lines, ctx=self)
         return pc, pp, (kc, kp)
 
     def point_wise_indices(self):
@@ -152,11 +159,11 @@ class LineBA:
         kernel is left in ``self.last_triangulate_seconds``."""
         n = int(view0.shape[0])
         n_views = int(P.shape[0])
-        pP, k0 = _as_ptr(P, np.float64, "float64", 12 * n_views)
-        pv0, k1 = _as_ptr(view0, np.int64, "int64", n)
-        pv1, k2 = _as_ptr(view1, np.int64, "int64", n)
-        pa, k3 = _as_ptr(pts0, np.float32, "float32", 4 * n)
-        pb, k4 = _as_ptr(pts1, np.float32, "float32", 4 * n)
+        pP, k0 = _as_ptr(P, np.float64, "float64", 12 * n_views, ctx=self)
+        pv0, k1 = _as_ptr(view0, np.int64, "int64", n, ctx=self)
+        pv1, k2 = _as_ptr(view1, np.int64, "int64", n, ctx=self)
+        pa, k3 = _as_ptr(pts0, np.float32, "float32", 4 * n, ctx=self)
+        pb, k4 = _as_ptr(pts1, np.float32, "float32", 4 * n, ctx=self)
         if out is None:
             X = np.empty((n, 2, 3), dtype=np.float32)
             pX = X.ctypes.data
@@ -235,8 +242,8 @@ class LineBA:
             pc, pp = cams.ctypes.data, pts.ctypes.data
         else:
             cams, pts = out
-            pc, _k0 = _as_ptr(cams, np.float64, "float64", 6 * self.n_cameras)
-            pp, _k1 = _as_ptr(pts, np.float64, "float64", 6 * self.n_lines)
+            pc, _k0 = _as_ptr(cams, np.float64, "float64", 6 * self.n_cameras, ctx=self)
+            pp, _k1 = _as_ptr(pts, np.float64, "float64", 6 * self.n_lines, ctx=self)
             if (_k0 is not cams) or (_k1 is not pts):
                 raise ValueError("out buffers must be contiguous float64")
         r = np.empty(self.m, dtype=np.float64) if want_residuals else None

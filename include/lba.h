@@ -129,6 +129,10 @@ int lba_destroy(lba_ctx* ctx);
 /* Use an existing CUDA stream (cudaStream_t passed as void*); default is a private stream. */
 int lba_set_stream(lba_ctx* ctx, void* cuda_stream);
 int lba_synchronize(lba_ctx* ctx);
+/* Device pointers handed to this library are read on the context's stream.  If they were produced by work still
+ * in flight on ANOTHER stream (e.g. the caller's PyTorch stream), call this first: the context's streams then wait
+ * for everything enqueued on `cuda_stream` so far.  Calls that return host data synchronise before returning. */
+int lba_wait_stream(lba_ctx* ctx, void* cuda_stream);
 
 /* Describe the observations (everything `fun` reads that is not a parameter).
  * Replaces point_wise_input (bundle_adjustment.py:194-250) and the per-call reads of

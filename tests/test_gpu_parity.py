@@ -598,3 +598,24 @@ def test_multi_gpu_stalled_peer_is_an_error_not_a_hang():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "LBA_ERR_COMM" in out.stdout or "error -6" in out.stdout, out.stdout[-2000:]
+
+
+def test_cuda_tensor_inputs_are_ordered_behind_the_torch_stream(LineBA, orc):
+    """Inputs that are CUDA tensors still being written by kernels on a torch side stream: the context's stream
+    waits for that stream (lba_wait_stream) before reading them, so the results equal the host-array path."""
+    import torch
+    s = synth(20, 4000, 8, seed=5)
+    ba = make_ctx(LineBA, s)
+    r_ref, cost_ref = ba.residuals(s.camera_params, s.points_3d)
+    side = torch.cuda.Stream()
+    big = torch.randn(6144, 6144, device="cuda")
+    hc = torch.from_numpy(s.camera_params).pin_memory(); hp = torch.from_numpy(s.points_3d).pin_memory()
+    for _ in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                big = big @ big * 1e-3                     # keeps the side stream busy for milliseconds
+            cams = hc.to("cuda", non_blocking=True) * 1.0    # written behind that work, on the side stream
+            pts = hp.to("cuda", non_blocking=True) * 1.0
+            r, cost = ba.residuals(cams, pts)
+        assert cost == cost_ref and np.array_equal(r, r_ref)
+    ba.close()
