@@ -25,6 +25,7 @@ EXPORTS = [
     "lba_comm_unique_id", "lba_comm_init", "lba_comm_destroy", "lba_comm_peer_local", "lba_comm_peer_attach", "lba_launch_count", "lba_set_profiling",
     "lba_get_profile", "lba_kernel_class_name", "lba_measure_fp64_peak", "lba_measure_copy_bandwidth",
     "lba_triangulate_lines", "lba_track_table",
+    "lba_lines2d_set", "lba_observations_from_tables", "lba_set_problem_lines2d", "lba_triangulate_tracks",
 ]
 
 
@@ -109,6 +110,10 @@ def load():
     lib.lba_measure_copy_bandwidth.argtypes = [vp, i64, C.POINTER(dbl)]
     lib.lba_triangulate_lines.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(dbl)]
     lib.lba_track_table.argtypes = [vp, i32, i64, vp, vp, vp, vp, dbl, vp, i64, vp, vp, vp, C.POINTER(i64), vp]
+    lib.lba_lines2d_set.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.lba_observations_from_tables.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.lba_set_problem_lines2d.argtypes = [vp, i64, i64, i64, vp, vp, vp]
+    lib.lba_triangulate_tracks.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("lba_version",):

@@ -177,6 +177,10 @@ struct lba_ctx {
   size_t peer_rs_min = 16384;
   DBuf<unsigned long long> peer_trace;   // LBA_PEER_TRACE: device-side wait/total times of the exchanges
 
+  // N1: per-2D-line tables resident across the incremental loop (lba_lines2d_set)
+  long long n_lines2d = 0;
+  DBuf<double> l2d_n, l2d_p0, l2d_p1, l2d_end, l2d_stage;
+
   // second stream + event: the 72 B/observation constants cross PCIe while the index arrays are processed
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_done = nullptr;
@@ -1302,6 +1306,7 @@ extern "C" int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d,
                                const uint8_t* flags_in, int64_t cap_rows, int64_t* ids, int64_t* bin,
                                int64_t* n_new_tracks, int64_t* n_tracks, uint8_t* flags_out) {
   if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (!endpoints && ctx->l2d_end.p) { endpoints = ctx->l2d_end.p; n_lines2d = ctx->n_lines2d; }   // resident table (lba_lines2d_set)
   if (n_views < 2 || n_lines2d < 1) return fail(LBA_ERR_ARG, "need at least two views and one 2D line");
   if (!endpoints || !match_ptr || !F || !ids || !bin || !n_new_tracks || !n_tracks) return fail(LBA_ERR_ARG, "NULL array");
   if (is_device_ptr(match_ptr) || is_device_ptr(n_new_tracks) || is_device_ptr(n_tracks))
@@ -1449,6 +1454,150 @@ extern "C" int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_v
   if (ctx->launch_err) return take_launch_err(ctx);
   if (bad) return fail(LBA_ERR_ARG, "%d track(s) name a view outside [0, %lld)", bad, (long long)n_views);
   return LBA_OK;
+}
+
+// ---- C ABI: BA input resident on the device across the incremental loop ---------------------------
+extern "C" int lba_lines2d_set(lba_ctx* ctx, int64_t n_lines2d, const double* n, const double* p0, const double* p1,
+                               const double* endpoints) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_lines2d < 0 || n_lines2d > 0x7fffffffLL / 4) return fail(LBA_ERR_ARG, "bad number of 2D lines");
+  if (n_lines2d > 0 && (!n || !p0 || !p1)) return fail(LBA_ERR_ARG, "NULL array");
+  CK(cudaSetDevice(ctx->device));
+  const size_t N = (size_t)n_lines2d;
+  CKR(ctx->l2d_n.alloc(3 * N)); CKR(ctx->l2d_p0.alloc(3 * N)); CKR(ctx->l2d_p1.alloc(3 * N));
+  if (N) {
+    CK(cudaMemcpyAsync(ctx->l2d_n.p, n, 24 * N, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->l2d_p0.p, p0, 24 * N, cudaMemcpyDefault, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->l2d_p1.p, p1, 24 * N, cudaMemcpyDefault, ctx->stream));
+    if (endpoints) {
+      CKR(ctx->l2d_end.alloc(4 * N));
+      CK(cudaMemcpyAsync(ctx->l2d_end.p, endpoints, 32 * N, cudaMemcpyDefault, ctx->stream));
+    }
+  }
+  if (!endpoints) ctx->l2d_end.release();
+  CK(cudaStreamSynchronize(ctx->stream));   // the caller's arrays are no longer read
+  ctx->n_lines2d = n_lines2d;
+  return take_launch_err(ctx);
+}
+
+extern "C" int lba_observations_from_tables(lba_ctx* ctx, int64_t n_rows, int32_t n_views, const int64_t* ids,
+                                            const int64_t* bin, int64_t cap, int64_t* cam_idx, int64_t* line_idx,
+                                            int64_t* line2d_id, int64_t* m_out, int64_t* n_tracks_out) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_rows < 0 || n_views < 1 || (long long)n_rows * n_views > 0x7fffffffLL) return fail(LBA_ERR_ARG, "bad table size");
+  if (!m_out || !n_tracks_out) return fail(LBA_ERR_ARG, "NULL output");
+  *m_out = 0; *n_tracks_out = 0;
+  if (n_rows == 0) return LBA_OK;
+  if (!ids || !bin || !cam_idx || !line_idx || !line2d_id) return fail(LBA_ERR_ARG, "NULL array");
+  const long long TV = (long long)n_rows * n_views;
+  if (cap < TV) return fail(LBA_ERR_ARG, "cap (%lld) must be at least rows x views (%lld)", (long long)cap, TV);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st_ = ctx->stream;
+  DBuf<long long> s_ids, s_bin, o_cam, o_line, o_id, d_m; DBuf<int> d_nt, d_flag, d_pos; DBuf<unsigned char> d_tmp;
+  const long long *d_ids = reinterpret_cast<const long long*>(ids), *d_bin = reinterpret_cast<const long long*>(bin);
+  if (!is_device_ptr(ids)) { CKR(s_ids.alloc(TV)); CK(cudaMemcpyAsync(s_ids.p, ids, TV * 8, cudaMemcpyHostToDevice, st_)); d_ids = s_ids.p; }
+  if (!is_device_ptr(bin)) { CKR(s_bin.alloc(TV)); CK(cudaMemcpyAsync(s_bin.p, bin, TV * 8, cudaMemcpyHostToDevice, st_)); d_bin = s_bin.p; }
+  long long* outs[3] = {reinterpret_cast<long long*>(cam_idx), reinterpret_cast<long long*>(line_idx), reinterpret_cast<long long*>(line2d_id)};
+  DBuf<long long>* stage[3] = {&o_cam, &o_line, &o_id};
+  long long* dev_out[3];
+  for (int k = 0; k < 3; ++k) {
+    if (is_device_ptr(outs[k])) dev_out[k] = outs[k];
+    else { CKR(stage[k]->alloc(TV)); dev_out[k] = stage[k]->p; }
+  }
+  CKR(d_nt.alloc(1)); CKR(d_m.alloc(1)); CKR(d_flag.alloc(TV)); CKR(d_pos.alloc(TV));
+  CK(cudaMemsetAsync(d_nt.p, 0, 4, st_));
+  LAUNCH(ctx, LBA_K_MISC, k_obs_count, cdiv(n_rows, 256), 256, (long long)n_rows, (int)n_views, d_bin, d_nt.p);
+  LAUNCH(ctx, LBA_K_MISC, k_obs_flags, cdiv(TV, 256), 256, (long long)n_rows, (int)n_views, d_bin, (const int*)d_nt.p, d_flag.p);
+  size_t tmp_bytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag.p, d_pos.p, (int)TV, st_));
+  CKR(d_tmp.alloc(tmp_bytes));
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_flag.p, d_pos.p, (int)TV, st_));
+  LAUNCH(ctx, LBA_K_MISC, k_obs_scatter, cdiv(TV, 256), 256, (long long)n_rows, (int)n_views, d_ids, (const int*)d_flag.p,
+         (const int*)d_pos.p, dev_out[0], dev_out[1], dev_out[2], d_m.p);
+  long long m = 0; int nt = 0;
+  CK(cudaMemcpyAsync(&m, d_m.p, 8, cudaMemcpyDeviceToHost, st_));
+  CK(cudaMemcpyAsync(&nt, d_nt.p, 4, cudaMemcpyDeviceToHost, st_));
+  CK(cudaStreamSynchronize(st_));
+  for (int k = 0; k < 3; ++k)
+    if (dev_out[k] != outs[k] && m > 0) CK(cudaMemcpyAsync(outs[k], dev_out[k], (size_t)m * 8, cudaMemcpyDeviceToHost, st_));
+  CK(cudaStreamSynchronize(st_));
+  *m_out = m; *n_tracks_out = nt;
+  return take_launch_err(ctx);
+}
+
+extern "C" int lba_set_problem_lines2d(lba_ctx* ctx, int64_t m, int64_t nc, int64_t nl, const int64_t* cam_idx,
+                                       const int64_t* line_idx, const int64_t* line2d_id) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (m < 0 || m > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "bad observation count");
+  if (m > 0 && (!cam_idx || !line_idx || !line2d_id)) return fail(LBA_ERR_ARG, "NULL array");
+  if (m > 0 && ctx->n_lines2d == 0) return fail(LBA_ERR_STATE, "lba_lines2d_set has not been called");
+  CK(cudaSetDevice(ctx->device));
+  const size_t M = (size_t)m;
+  CKR(ctx->l2d_stage.alloc(9 * M + 2));
+  double *gn = ctx->l2d_stage.p, *gp0 = gn + 3 * M, *gp1 = gp0 + 3 * M;
+  if (m > 0) {
+    DBuf<long long> s_id; DBuf<int> d_bad;
+    const long long* d_id = reinterpret_cast<const long long*>(line2d_id);
+    if (!is_device_ptr(line2d_id)) { CKR(s_id.alloc(M)); CK(cudaMemcpyAsync(s_id.p, line2d_id, M * 8, cudaMemcpyHostToDevice, ctx->stream)); d_id = s_id.p; }
+    CKR(d_bad.alloc(1));
+    CK(cudaMemsetAsync(d_bad.p, 0, 4, ctx->stream));
+    LAUNCH(ctx, LBA_K_MISC, k_gather_lines2d, cdiv(3 * (long long)m, 256), 256, (long long)m, ctx->n_lines2d, d_id,
+           (const double*)ctx->l2d_n.p, (const double*)ctx->l2d_p0.p, (const double*)ctx->l2d_p1.p, gn, gp0, gp1, d_bad.p);
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(LBA_ERR_ARG, "%d observation(s) name a 2D line outside [0, %lld)", bad, ctx->n_lines2d);
+  }
+  return lba_set_problem(ctx, m, nc, nl, cam_idx, line_idx, gn, gp0, gp1);
+}
+
+extern "C" int lba_triangulate_tracks(lba_ctx* ctx, int32_t n_views, const double* P, const int64_t* ids,
+                                      const int64_t* n_new_tracks, float* X, double* points_3d, int64_t* n_tracks_out) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_views < 2 || !P || !n_new_tracks || !n_tracks_out) return fail(LBA_ERR_ARG, "bad argument");
+  if (is_device_ptr(n_new_tracks)) return fail(LBA_ERR_ARG, "n_new_tracks is a host array");
+  if (!ctx->l2d_end.p || ctx->n_lines2d == 0) return fail(LBA_ERR_STATE, "lba_lines2d_set was not given the endpoints");
+  long long n = 0;
+  for (int v = 0; v < n_views - 1; ++v) { if (n_new_tracks[v] < 0) return fail(LBA_ERR_ARG, "negative track count"); n += n_new_tracks[v]; }
+  *n_tracks_out = n;
+  if (n == 0) return LBA_OK;
+  if (!ids || (!X && !points_3d)) return fail(LBA_ERR_ARG, "NULL array");
+  if (!is_device_ptr(ids)) return fail(LBA_ERR_ARG, "ids must be the device table written by lba_track_table");
+  CK(cudaSetDevice(ctx->device));
+  DBuf<long long> d_v0; DBuf<float> d_p0, d_p1, d_X; DBuf<int> d_bad;
+  CKR(d_v0.alloc(n)); CKR(d_p0.alloc(4 * n)); CKR(d_p1.alloc(4 * n)); CKR(d_bad.alloc(1));
+  CK(cudaMemsetAsync(d_bad.p, 0, 4, ctx->stream));
+  long long row = 0;
+  for (int v = 0; v < n_views - 1; ++v) {
+    const long long k = n_new_tracks[v];
+    if (k > 0)
+      LAUNCH(ctx, LBA_K_MISC, k_tri_gather, cdiv(k, 256), 256, k, row, row, (int)n_views, v, ctx->n_lines2d,
+             reinterpret_cast<const long long*>(ids), (const double*)ctx->l2d_end.p, d_v0.p, reinterpret_cast<float2*>(d_p0.p),
+             reinterpret_cast<float2*>(d_p1.p), d_bad.p);
+    row += k;
+  }
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) return fail(LBA_ERR_ARG, "%d track(s) name a 2D line outside [0, %lld)", bad, ctx->n_lines2d);
+  float* Xd = X;
+  if (!X || !is_device_ptr(X)) { CKR(d_X.alloc(6 * n)); Xd = d_X.p; }
+  CKR(lba_triangulate_lines(ctx, n, n_views, P, reinterpret_cast<const int64_t*>(d_v0.p), nullptr, d_p0.p, d_p1.p, Xd, nullptr, nullptr));
+  if (X && Xd != X) CK(cudaMemcpyAsync(X, Xd, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (points_3d) {
+    // the BA starts from these float32 coordinates widened to double (bundle_adjustment.py:231-233, :311)
+    if (is_device_ptr(points_3d)) {
+      LAUNCH(ctx, LBA_K_MISC, k_f32_to_f64, cdiv(6 * n, 256), 256, 6 * n, (const float*)Xd, points_3d);
+    } else {
+      DBuf<double> d64;
+      CKR(d64.alloc(6 * n));
+      LAUNCH(ctx, LBA_K_MISC, k_f32_to_f64, cdiv(6 * n, 256), 256, 6 * n, (const float*)Xd, d64.p);
+      CK(cudaMemcpyAsync(points_3d, d64.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return take_launch_err(ctx);
 }
 
 extern "C" int lba_residuals(lba_ctx* ctx, const double* cams, const double* pts, double* residuals, double* cost) {

@@ -1981,6 +1981,77 @@ __global__ void __launch_bounds__(256) k_triangulate(long long n2, int n_views, 
 }
 
 // ---------------------------------------------------------------------------------
+// N1: BA input kept on the device across the incremental loop (seq_utils.py:138-208, main.py:111-133).
+// The per-2D-line constants (n, p0, p1 of domain.spherical_representation, domain.py:338-351) and pixel endpoints are
+// uploaded ONCE; after every added view the observation list is rebuilt on the device from the track tables and the
+// observation constants are gathered from the resident table by 2D line id.
+// ---------------------------------------------------------------------------------
+// rows of `bin` (T x V int64) seen in more than one view (seq_utils.py:188-189)
+__global__ void k_obs_count(long long T, int V, const long long* __restrict__ bin, int* __restrict__ n_tracks) {
+  pdl_prologue();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  long long s = 0;
+  for (int v = 0; v < V; ++v) s += bin[t * V + v];
+  if (s > 1) atomicAdd(n_tracks, 1);
+}
+// the reference takes the FIRST n_tracks rows (bin[:len(cond1)], :190), row-major (track, view) order
+__global__ void k_obs_flags(long long T, int V, const long long* __restrict__ bin, const int* __restrict__ n_tracks,
+                            int* __restrict__ flag) {
+  pdl_prologue();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= T * V) return;
+  flag[e] = (e / V < *n_tracks && bin[e] == 1) ? 1 : 0;
+}
+__global__ void k_obs_scatter(long long T, int V, const long long* __restrict__ ids, const int* __restrict__ flag,
+                              const int* __restrict__ pos, long long* __restrict__ cam_idx, long long* __restrict__ line_idx,
+                              long long* __restrict__ line2d, long long* __restrict__ m_out) {
+  pdl_prologue();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= T * V) return;
+  if (flag[e]) {
+    const int p = pos[e];
+    cam_idx[p] = e % V; line_idx[p] = e / V; line2d[p] = ids[e];
+  }
+  if (e == T * V - 1) *m_out = (long long)pos[e] + flag[e];
+}
+// observation constants of observation i = row line2d[i] of the resident per-2D-line table
+__global__ void k_gather_lines2d(long long m, long long n_lines2d, const long long* __restrict__ line2d,
+                                 const double* __restrict__ tn, const double* __restrict__ tp0, const double* __restrict__ tp1,
+                                 double* __restrict__ n, double* __restrict__ p0, double* __restrict__ p1, int* __restrict__ bad) {
+  pdl_prologue();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * m) return;
+  const long long i = e / 3, k = e % 3, id = line2d[i];
+  if (id < 0 || id >= n_lines2d) { if (k == 0) atomicAdd(bad, 1); n[e] = p0[e] = p1[e] = 0.0; return; }
+  n[e] = tn[id * 3 + k]; p0[e] = tp0[id * 3 + k]; p1[e] = tp1[id * 3 + k];
+}
+// triangulation input of the NEW tracks of view pair (i, i+1), rows [row0, row0 + k) of ids: float32 endpoints of the
+// two 2D lines (np.array(..., dtype=np.float32), seq_utils.py:114-117) and the pair's first view
+__global__ void k_tri_gather(long long k, long long row0, long long out0, int V, int pair, long long n_lines2d,
+                             const long long* __restrict__ ids, const double* __restrict__ endpoints,
+                             long long* __restrict__ view0, float2* __restrict__ pts0, float2* __restrict__ pts1,
+                             int* __restrict__ bad) {
+  pdl_prologue();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const long long l0 = ids[(row0 + j) * V + pair], l1 = ids[(row0 + j) * V + pair + 1];
+  const long long o = out0 + j;
+  view0[o] = pair;
+  const bool ok = l0 >= 0 && l0 < n_lines2d && l1 >= 0 && l1 < n_lines2d;
+  if (!ok) atomicAdd(bad, 1);
+  for (int e = 0; e < 2; ++e) {
+    pts0[o * 2 + e] = ok ? make_float2((float)endpoints[(l0 * 2 + e) * 2], (float)endpoints[(l0 * 2 + e) * 2 + 1]) : make_float2(0.f, 0.f);
+    pts1[o * 2 + e] = ok ? make_float2((float)endpoints[(l1 * 2 + e) * 2], (float)endpoints[(l1 * 2 + e) * 2 + 1]) : make_float2(0.f, 0.f);
+  }
+}
+__global__ void k_f32_to_f64(long long n, const float* __restrict__ src, double* __restrict__ dst) {
+  pdl_prologue();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) dst[e] = (double)src[e];
+}
+
+// ---------------------------------------------------------------------------------
 // microbenchmarks for the roofline denominators
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {

@@ -168,14 +168,38 @@ def triangulate_model(domain, last_view, ba=None, point3d_cls=None, line3d_cls=N
     return X
 
 
+def lines2d_arrays_from_domain(domain, start=0):
+    """Flatten ``domain.lines2d[start:]`` once: ``n``, ``p0``, ``p1`` (k,3) f64 (``Line.n`` / ``Line.points[e].p``,
+    domain.py:338-351) and the pixel endpoints (k,2,2) f64."""
+    L = domain.lines2d[start:]
+    n = np.array([l.n for l in L], dtype=np.float64).reshape(-1, 3)
+    p0 = np.array([l.points[0].p for l in L], dtype=np.float64).reshape(-1, 3)
+    p1 = np.array([l.points[1].p for l in L], dtype=np.float64).reshape(-1, 3)
+    E = np.array([[np.asarray(p.coord, dtype=np.float64)[:2] for p in l.points] for l in L], dtype=np.float64).reshape(-1, 2, 2)
+    return n, p0, p1, E
+
+
 class IncrementalBA:
-    """One GPU context for the whole incremental reconstruction (src/main.py:111-133 re-runs BA after every
-    added view on a growing problem)."""
+    """One GPU context for the whole incremental reconstruction (src/main.py:111-133 re-runs tracker, triangulation
+    and BA after every added view on a growing problem).
+
+    ``solve`` is the array-native drop-in for ``input_bundle_adj`` + ``run_bundle_adjustment`` +
+    ``update_structure_motion`` on whatever ``domain.tracker`` / ``domain.lines3d`` currently hold.
+
+    ``step`` is the device-resident version of main.py:118-133 (everything after the PnL registration of the new
+    view): the ``Line`` objects are flattened and uploaded ONCE (``lines2d_arrays_from_domain``; only a grown tail
+    is flattened again), and per added view the track table, the triangulated endpoints, the observation list and
+    the observation constants are produced and consumed on the device -- what crosses PCIe per view is the match
+    lists of the new pair, the fundamental matrices and camera rows in, and the optimised cameras, 3D endpoints and
+    the track table out (the reference's PnL stage reads them from the ``Domain`` objects)."""
 
     def __init__(self, device=0):
         self.ba = LineBA(device)
         self.last = None
+        self._l2d = None          # host copies of the flattened 2D-line arrays (n, p0, p1, endpoints)
+        self._matches = {}        # view pair -> (k,2) int64, flattened once
 
+    # -- array-native BA on the domain's current tracker / lines3d ------------------------------------------------
     def solve(self, domain, last_view, loss_f="linear", write_back=True, **options):
         a = input_arrays_from_domain(domain, last_view)
         nc = a["camera_params"].shape[0]
@@ -185,6 +209,59 @@ class IncrementalBA:
         if write_back:
             update_domain_from_arrays(domain, res.camera_params, res.points_3d, last_view)
         self.last = res
+        return res.camera_params, res.points_3d, res.residuals
+
+    # -- device-resident incremental step ----------------------------------------------------------------------------
+    def _sync_lines2d(self, domain):
+        have = 0 if self._l2d is None else self._l2d[0].shape[0]
+        if have == len(domain.lines2d):
+            return
+        tail = lines2d_arrays_from_domain(domain, have)
+        self._l2d = tail if self._l2d is None else tuple(np.concatenate((x, y)) for x, y in zip(self._l2d, tail))
+        self.ba.set_lines2d(*self._l2d)
+
+    def step(self, domain, last_view, loss_f="linear", threshold=0.1, write_back=True, point3d_cls=None, line3d_cls=None,
+             **options):
+        """Tracker -> triangulation -> BA -> update for views 0..last_view (main.py:118-133), device-resident."""
+        import cv2
+        self._sync_lines2d(domain)
+        views = domain.views[:last_view + 1]
+        F, matches = [], []
+        for v in range(last_view):
+            F.append(fundamental_from_cameras(domain.K, views[v].P, views[v + 1].P))
+            key = str(v) + str(v + 1)
+            if key not in self._matches:
+                self._matches[key] = np.array(domain.line_match[key][1], dtype=np.int64).reshape(-1, 2)
+            matches.append(self._matches[key])
+        ids, bi, n_new = self.ba.track_table_device(matches, np.array(F), threshold)              # tracker.py:11-96
+        P = np.array([np.asarray(v.P.P, dtype=np.float64) for v in views])
+        X, pts = self.ba.triangulate_tracks(P, ids, n_new)                                       # seq_utils.py:75-135
+        cam_idx, line_idx, l2d, n_tracks = self.ba.observations_from_tables(ids, bi)             # seq_utils.py:186-195
+        cams = np.empty((len(views), 3, 2), dtype=np.float64)
+        for i, v in enumerate(views):
+            cams[i, :, 0] = cv2.Rodrigues(np.asarray(v.P.R))[0].ravel()                          # seq_utils.py:179
+            cams[i, :, 1] = np.asarray(v.P.c, dtype=np.float64).ravel()
+        cams = cams.reshape(len(views), 6)
+        nl = int(X.shape[0])
+        self.ba.set_problem_lines2d(len(views), nl, cam_idx, line_idx, l2d)
+        res = self.ba.lm_solve(None, None, out=(cams, pts), loss=loss_f, **options)              # bundle_adjustment.py:254
+        res.camera_params = cams
+        res.points_3d = pts.cpu().numpy()
+        if write_back:
+            if point3d_cls is None:
+                from point import Point3D as point3d_cls
+            if line3d_cls is None:
+                from line import Line3D as line3d_cls
+            domain.tracker = TrackTables(ids.cpu().numpy(), bi.cpu().numpy(), n_new)             # main.py:121-123
+            Xh = X.cpu().numpy()
+            domain.lines3d, domain.points3d = [], []
+            for t in range(nl):                                                                   # seq_utils.py:122-131
+                p_ini = point3d_cls(2 * t, Xh[t, 0]); p_fin = point3d_cls(2 * t + 1, Xh[t, 1])
+                domain.points3d += [p_ini, p_fin]
+                domain.lines3d.append(line3d_cls(t, [p_ini, p_fin]))
+            update_domain_from_arrays(domain, res.camera_params, res.points_3d, last_view)      # seq_utils.py:211-252
+        self.last = res
+        self.last_tables = (ids, bi, n_new)
         return res.camera_params, res.points_3d, res.residuals
 
     def close(self):

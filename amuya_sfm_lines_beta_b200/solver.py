@@ -149,6 +149,98 @@ class LineBA:
         out = (ids[:T].copy(), bi[:T].copy(), n_new)
         return out + (flags.astype(bool),) if want_flags else out
 
+    # -- BA input resident on the device across the incremental loop ------------
+    def set_lines2d(self, n, p0, p1, endpoints=None):
+        """Upload ONCE the per-2D-line constants ``Line.n`` / ``Line.points[e].p`` (domain.py:338-351) and, optionally,
+        the pixel endpoints of every ``domain.lines2d[id]``; later calls name 2D lines by id."""
+        k = int(np.asarray(n).shape[0]) if not _is_torch(n) else int(n.shape[0])
+        pn, k0 = _as_ptr(n, np.float64, "float64", 3 * k, ctx=self)
+        pa, k1 = _as_ptr(p0, np.float64, "float64", 3 * k, ctx=self)
+        pb, k2 = _as_ptr(p1, np.float64, "float64", 3 * k, ctx=self)
+        pe, k3 = _as_ptr(endpoints, np.float64, "float64", 4 * k, ctx=self)
+        check(self._lib.lba_lines2d_set(self._h, k, pn, pa, pb, pe))
+        self.n_lines2d = k
+        return self
+
+    def track_table_device(self, matches_per_pair, F_per_pair, threshold=0.1):
+        """``track_table`` on the resident endpoint table with the tables LEFT on the device: returns
+        ``(ids, bin)`` torch CUDA int64 tensors of shape (T, V) (views of the capacity buffers) and ``n_new_tracks``."""
+        import torch
+        n_pairs = len(matches_per_pair)
+        V = n_pairs + 1
+        ms = [np.ascontiguousarray(m, dtype=np.int64).reshape(-1, 2) for m in matches_per_pair]
+        ptr = np.zeros(V, dtype=np.int64)
+        ptr[1:] = np.cumsum([len(m) for m in ms])
+        M = int(ptr[-1])
+        matches = np.concatenate(ms) if M else np.zeros((0, 2), dtype=np.int64)
+        F = np.ascontiguousarray(np.asarray(F_per_pair, dtype=np.float64).reshape(n_pairs, 9))
+        cap = max(M, 1)
+        dev = torch.device("cuda", self.device)
+        ids = torch.empty((cap, V), dtype=torch.int64, device=dev)
+        bi = torch.empty((cap, V), dtype=torch.int64, device=dev)
+        check(self._lib.lba_wait_stream(self._h, torch.cuda.current_stream(dev).cuda_stream))
+        n_new = np.zeros(n_pairs, dtype=np.int64)
+        n_tracks = C.c_int64()
+        check(self._lib.lba_track_table(self._h, V, 0, None, ptr.ctypes.data, matches.ctypes.data if M else None,
+                                        F.ctypes.data, float(threshold), None, cap, ids.data_ptr(), bi.data_ptr(),
+                                        n_new.ctypes.data, C.byref(n_tracks), None))
+        T = int(n_tracks.value)
+        return ids[:T], bi[:T], n_new
+
+    def observations_from_tables(self, ids, bi):
+        """The observation list of ``input_bundle_adj`` (seq_utils.py:186-195) from the track tables.  Device tables
+        (torch CUDA int64) give device results ``(camera_indices, lines_indices, line2d_ids)``; host tables host results.
+        Also returns ``n_tracks`` (rows seen in more than one view)."""
+        on_dev = _is_torch(ids) and ids.is_cuda
+        T, V = int(ids.shape[0]), int(ids.shape[1])
+        m, nt = C.c_int64(), C.c_int64()
+        cap = max(T * V, 1)
+        if on_dev:
+            import torch
+            pi, k0 = _as_ptr(ids, np.int64, "int64", T * V, ctx=self)
+            pb, k1 = _as_ptr(bi, np.int64, "int64", T * V, ctx=self)
+            out = [torch.empty(cap, dtype=torch.int64, device=ids.device) for _ in range(3)]
+            check(self._lib.lba_wait_stream(self._h, torch.cuda.current_stream(ids.device).cuda_stream))
+            ptrs = [o.data_ptr() for o in out]
+        else:
+            a = np.ascontiguousarray(ids, dtype=np.int64); b = np.ascontiguousarray(bi, dtype=np.int64)
+            pi, pb = a.ctypes.data, b.ctypes.data
+            out = [np.empty(cap, dtype=np.int64) for _ in range(3)]
+            ptrs = [o.ctypes.data for o in out]
+        check(self._lib.lba_observations_from_tables(self._h, T, V, pi, pb, cap, ptrs[0], ptrs[1], ptrs[2],
+                                                     C.byref(m), C.byref(nt)))
+        k = int(m.value)
+        return out[0][:k], out[1][:k], out[2][:k], int(nt.value)
+
+    def set_problem_lines2d(self, n_cameras, n_lines, camera_indices, lines_indices, line2d_ids):
+        """``set_problem`` with n, p0, p1 gathered on the device from the table given to ``set_lines2d``."""
+        m = int(camera_indices.shape[0])
+        pc, k0 = _as_ptr(camera_indices, np.int64, "int64", m, ctx=self)
+        pl, k1 = _as_ptr(lines_indices, np.int64, "int64", m, ctx=self)
+        pi, k2 = _as_ptr(line2d_ids, np.int64, "int64", m, ctx=self)
+        check(self._lib.lba_set_problem_lines2d(self._h, m, int(n_cameras), int(n_lines), pc, pl, pi))
+        self.m, self.n_cameras, self.n_lines = m, int(n_cameras), int(n_lines)
+        return self
+
+    def triangulate_tracks(self, P, ids, n_new_tracks, want_points64=True):
+        """``triangulate_model`` (seq_utils.py:105-131) from the DEVICE track table ``ids`` and the resident endpoint
+        table.  Returns ``(X (n,2,3) float32, points_3d (2n,3) float64)`` as torch CUDA tensors (points_3d: the float32
+        coordinates widened to double, the BA's starting point)."""
+        import torch
+        V = int(P.shape[0])
+        pP, k0 = _as_ptr(P, np.float64, "float64", 12 * V, ctx=self)
+        nn = np.ascontiguousarray(n_new_tracks, dtype=np.int64)
+        n = int(nn.sum())
+        dev = ids.device
+        X = torch.empty((n, 2, 3), dtype=torch.float32, device=dev)
+        pts = torch.empty((2 * n, 3), dtype=torch.float64, device=dev) if want_points64 else None
+        check(self._lib.lba_wait_stream(self._h, torch.cuda.current_stream(dev).cuda_stream))
+        nt = C.c_int64()
+        base = ids._base if ids._base is not None else ids      # the full capacity buffer: rows are V apart
+        check(self._lib.lba_triangulate_tracks(self._h, V, pP, base.data_ptr(), nn.ctypes.data, X.data_ptr() if n else None,
+                                               pts.data_ptr() if (pts is not None and n) else None, C.byref(nt)))
+        return X, pts
+
     # -- two-view endpoint triangulation (SURVEY 8f N3; independent of set_problem) ------
     def triangulate_lines(self, P, view0, pts0, pts1, view1=None, want_homogeneous=False, out=None):
         """``cv2.triangulatePoints`` + float32 dehomogenisation for every endpoint of every track

@@ -154,7 +154,7 @@ int lba_project(lba_ctx* ctx, const double* camera_params, const double* points_
 /* Track table of n_views consecutive views ("next" row N2): replaces Tracker.comp_tracker (src/tracker.py:11-96)
  * together with its verify_duplet calls (src/utils.py:1807-1944).
  *   endpoints (n_lines2d,2,2) f64: pixel coordinates of the endpoints of domain.lines2d[id] (the reference indexes
- *       that list by line id, utils.py:1874-1875);
+ *       that list by line id, utils.py:1874-1875); NULL: the table made resident by lba_lines2d_set;
  *   match_ptr (n_views,) int64 HOST: the matches of the view pair (v, v+1) are rows [match_ptr[v], match_ptr[v+1])
  *       of matches (M,2) int64 = domain.line_match["<v><v+1>"][1];
  *   F (n_views-1,3,3) f64: fundamental matrix of each pair (relativeCameraMotion utils.py:1483 + F_from_KRt2 :1039);
@@ -182,6 +182,35 @@ int lba_track_table(lba_ctx* ctx, int32_t n_views, int64_t n_lines2d, const doub
 int lba_triangulate_lines(lba_ctx* ctx, int64_t n_tracks, int64_t n_views, const double* P,
                           const int64_t* view0, const int64_t* view1, const float* pts0, const float* pts1,
                           float* X, float* Xh, double* seconds_kernel);
+
+/* ---- "next" row N1: the BA input kept on the device across the incremental loop -------------------------------
+ * The reference rebuilds the BA input from Python objects after every registered view (src/main.py:111-133:
+ * Tracker.comp_tracker -> triangulate_model -> input_bundle_adj -> run_bundle_adjustment) and re-reads Line.n /
+ * Line.points[e].p of every observation.  Here the per-2D-line constants are uploaded once and everything between
+ * the track tables and the solve stays on the device.
+ *
+ * lba_lines2d_set: n, p0, p1 (n_lines2d,3) f64 = Line.n, Line.points[e].p of domain.lines2d[id] (domain.py:338-351);
+ *   endpoints (n_lines2d,2,2) f64 pixel coordinates or NULL (needed by lba_triangulate_tracks).  Host or device. */
+int lba_lines2d_set(lba_ctx* ctx, int64_t n_lines2d, const double* n, const double* p0, const double* p1,
+                    const double* endpoints);
+/* The observation list input_bundle_adj derives from the track tables (src/seq_utils.py:186-195): with
+ * n_tracks = #rows of bin seen in more than one view, the entries bin[t,v] == 1 of the FIRST n_tracks rows in
+ * row-major order give camera_indices = v, lines_indices = t and the 2D line ids[t,v].  ids, bin (n_rows,n_views)
+ * int64 as written by lba_track_table (host or device); outputs (cap >= n_rows*n_views) int64, host or device;
+ * *m_out, *n_tracks_out HOST. */
+int lba_observations_from_tables(lba_ctx* ctx, int64_t n_rows, int32_t n_views, const int64_t* ids, const int64_t* bin,
+                                 int64_t cap, int64_t* camera_indices, int64_t* lines_indices, int64_t* line2d_ids,
+                                 int64_t* m_out, int64_t* n_tracks_out);
+/* lba_set_problem with the observation constants gathered on the device from the resident per-2D-line table:
+ * n[i], p0[i], p1[i] = row line2d_ids[i].  Index arrays host or device. */
+int lba_set_problem_lines2d(lba_ctx* ctx, int64_t m, int64_t n_cameras, int64_t n_lines, const int64_t* camera_indices,
+                            const int64_t* lines_indices, const int64_t* line2d_ids);
+/* triangulate_model (src/seq_utils.py:105-131) straight from the DEVICE track table: the new tracks of view pair
+ * (v, v+1) are the next n_new_tracks[v] rows of ids (HOST counts, as returned by lba_track_table); their float32
+ * endpoints come from the resident endpoint table.  X (n,2,3) f32 and/or points_3d (2n,3) f64 (the float32
+ * coordinates widened: the BA's starting point, bundle_adjustment.py:231-233), host or device; *n_tracks_out HOST. */
+int lba_triangulate_tracks(lba_ctx* ctx, int32_t n_views, const double* P, const int64_t* ids,
+                           const int64_t* n_new_tracks, float* X, double* points_3d, int64_t* n_tracks_out);
 
 /* fun (:78-139): residuals (m,) in the caller's observation order; cost = 0.5*sum r^2
  * (either output may be NULL). */

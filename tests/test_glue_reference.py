@@ -58,3 +58,22 @@ def test_update_domain_equals_reference_update_structure_motion(ref_env):
         assert np.array_equal(va.P.P, vb.P.P) and np.array_equal(va.P.R, vb.P.R) and np.array_equal(va.P.c, vb.P.c)
     for La, Lb in zip(dom_a.lines3d, dom_b.lines3d):
         assert np.array_equal(La.points[0].coord, Lb.points[0].coord) and np.array_equal(La.points[1].coord, Lb.points[1].coord)
+
+
+def test_lines2d_tables_gathered_by_id_equal_reference_observation_constants(ref_env):
+    """The once-per-domain flattening used by the device-resident incremental step (IncrementalBA.step): rows of the
+    per-2D-line tables, gathered by the 2D line id of every observation, are the reference's per-observation arrays."""
+    from amuya_sfm_lines_beta_b200.glue import input_arrays_from_domain, lines2d_arrays_from_domain
+    mg, ref = ref_env
+    dom = mg.build_toy_domain(ref, "toy_example1", "toy_example1_3Dvision.json", 6)
+    inp = mg.ba_input_from_domain(ref, dom, 5)
+    flat = mg.flatten_input(inp)
+    n, p0, p1, E = lines2d_arrays_from_domain(dom)
+    head = lines2d_arrays_from_domain(dom, 0)[0][:10]
+    tail = lines2d_arrays_from_domain(dom, 10)[0]
+    assert np.array_equal(np.concatenate((head, tail)), n)          # a grown tail can be flattened on its own
+    a = input_arrays_from_domain(dom, 5)
+    ids = a["line_ids"]
+    assert np.array_equal(n[ids], flat["n"]) and np.array_equal(p0[ids], flat["p0"]) and np.array_equal(p1[ids], flat["p1"])
+    assert E.shape == (len(dom.lines2d), 2, 2)
+    assert np.array_equal(E[3], np.array([np.asarray(p.coord, dtype=np.float64)[:2] for p in dom.lines2d[3].points]))
