@@ -1150,6 +1150,8 @@ static int solve_setup(lba_ctx* c, const LmCtl* ctl, double lam, double pcg_tol,
 }
 
 static int fetch_scalars(lba_ctx* c);
+static int publish_scalars(lba_ctx* c);
+static int wait_scalars(lba_ctx* c);
 
 // (2) n more PCG iterations (kernels return at once when the device-side `done` flag is set)
 static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
@@ -1223,10 +1225,15 @@ static int run_solve(lba_ctx* c, double lam, double pcg_tol, int pcg_max_iter, i
 // The host's look at the device scalars (LM control block, LM scalars, CG state, gradient-norm bits, clamp count):
 // k_publish writes them into mapped pinned memory followed by a sequence number; the host spins on that word
 // and only falls back to the stream when the device reports an error.
-static int fetch_scalars(lba_ctx* c) {
+static int publish_scalars(lba_ctx* c) {
   const unsigned long long seq = ++c->publish_seq;
   LAUNCH(c, LBA_K_MISC, k_publish, 1, 32, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p, (const LmCtl*)c->ctl.p,
          dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), (const int*)c->clamped.p, c->d_mirror, seq);
+  return LBA_OK;
+}
+// wait for the newest publication (kernels enqueued behind it keep the GPU busy meanwhile)
+static int wait_scalars(lba_ctx* c) {
+  const unsigned long long seq = c->publish_seq;
   volatile unsigned long long* flag = &c->h_mirror->seq;
   for (unsigned spins = 0; *flag != seq; ++spins) {
     if ((spins & 0x3ff) == 0x3ff) {
@@ -1254,6 +1261,11 @@ static int fetch_scalars(lba_ctx* c) {
   }
   if (c->launch_err) return take_launch_err(c);
   return LBA_OK;
+}
+
+static int fetch_scalars(lba_ctx* c) {
+  CKR(publish_scalars(c));
+  return wait_scalars(c);
 }
 
 static int export_residuals(lba_ctx* c, const double* r_dev, double* out) {
@@ -1712,10 +1724,19 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
   rep->cost_init = c->h_ctl->cost;
   if (c->h_ctl->status == -5) return fail(LBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
   int chunk_hint = 8;
+  // The host looks at the device once per pass (it has to know whether the PCG steps it enqueued were enough and how
+  // many the next solve will probably need), but the GPU does not wait for that look: the set-up kernels of the NEXT
+  // pass -- elimination, Schur weights, preconditioner, first CG state, ~25 % of an iteration -- are enqueued BEHIND
+  // the decision kernel before the host reads its result.  They take everything from the control block, and skip
+  // themselves when the decision turns out to be "done", "retry the same direction" or "more PCG steps first".
+  const bool ahead = !c->profiling && !getenv("LBA_NO_ENQUEUE_AHEAD");
+  bool setup_enqueued = false;
+  SolvePlan sp;
   while (!c->h_ctl->done) {
     const bool solve = c->h_ctl->need_solve != 0;
-    SolvePlan sp;
-    if (solve) CKR(solve_setup(c, ctl, 0.0, o.pcg_tol, o.pcg_max_iter, &sp, true));
+    if (solve && !setup_enqueued) CKR(solve_setup(c, ctl, 0.0, o.pcg_tol, o.pcg_max_iter, &sp, true));
+    setup_enqueued = false;
+    sp.issued = 0;
     int launch = std::max(1, std::min(chunk_hint, o.pcg_max_iter));
     while (true) {
       if (solve) {
@@ -1725,8 +1746,14 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
         CKR(launch_cam_step(c, ctl));   // same direction, shorter step: both halves of the trial point
       }
       CKR(enqueue_trial_tail(c, ctl));
-      CKR(fetch_scalars(c));
-      if (!c->h_ctl->cg_short) break;
+      CKR(publish_scalars(c));
+      if (ahead) {
+        const int issued = sp.issued;
+        CKR(solve_setup(c, ctl, 0.0, o.pcg_tol, o.pcg_max_iter, &sp, true));
+        sp.issued = issued;
+      }
+      CKR(wait_scalars(c));
+      if (!c->h_ctl->cg_short) { setup_enqueued = ahead; break; }
       launch = 4;   // the prediction was short: more PCG steps, then redo the (cheap to discard) tail
     }
     chunk_hint = c->h_ctl->q_last + 1;

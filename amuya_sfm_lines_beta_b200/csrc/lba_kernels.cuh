@@ -82,7 +82,9 @@ struct Dual {
 template <typename T>
 __host__ inline Dual<T> dual(T* a, T* b) { Dual<T> d; d.p[0] = a; d.p[1] = b; return d; }
 // kernels of the solve part run only in passes that solve; kernels of the trial part until the loop is done
-__device__ __forceinline__ bool ctl_skip_solve(const LmCtl* ctl) { return ctl && (ctl->done || !ctl->need_solve); }
+// (cg_short: the trial of the running pass could not be judged yet -- its PCG needs more steps -- so a set-up that
+// the host enqueued ahead for the NEXT pass must not touch the solve in progress)
+__device__ __forceinline__ bool ctl_skip_solve(const LmCtl* ctl) { return ctl && (ctl->done || !ctl->need_solve || ctl->cg_short); }
 __device__ __forceinline__ bool ctl_skip_trial(const LmCtl* ctl) { return ctl && ctl->done; }
 __device__ __forceinline__ int ctl_cur(const LmCtl* ctl) { return ctl ? ctl->cur : 0; }
 
