@@ -85,6 +85,8 @@ __host__ inline Dual<T> dual(T* a, T* b) { Dual<T> d; d.p[0] = a; d.p[1] = b; re
 // (cg_short: the trial of the running pass could not be judged yet -- its PCG needs more steps -- so a set-up that
 // the host enqueued ahead for the NEXT pass must not touch the solve in progress)
 __device__ __forceinline__ bool ctl_skip_solve(const LmCtl* ctl) { return ctl && (ctl->done || !ctl->need_solve || ctl->cg_short); }
+// the back-substitution belongs to the pass in progress: it runs again when the PCG was continued (cg_short)
+__device__ __forceinline__ bool ctl_skip_backsub(const LmCtl* ctl) { return ctl && (ctl->done || !ctl->need_solve); }
 __device__ __forceinline__ bool ctl_skip_trial(const LmCtl* ctl) { return ctl && ctl->done; }
 __device__ __forceinline__ int ctl_cur(const LmCtl* ctl) { return ctl ? ctl->cur : 0; }
 
@@ -1125,7 +1127,8 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   }
   pdl_prologue();
   if (MODE == kModeMatvec && a.st->done) return;  // uniform over the grid
-  if (MODE != kModeMatvec && ctl_skip_solve(a.ctl)) return;
+  if (MODE == kModeScalars && ctl_skip_solve(a.ctl)) return;
+  if (MODE == kModeBacksub && ctl_skip_backsub(a.ctl)) return;
   const int cur = ctl_cur(a.ctl);
   const double* g_jl = a.jl.sel(cur);
   const double* g_pts = a.pts.sel(cur);

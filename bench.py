@@ -390,7 +390,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "repeats": {"n": len(reps), "reported": "median", "ms_per_step_min": reps[0][0] / max(steps_done, 1),
                             "ms_per_step_max": reps[-1][0] / max(steps_done, 1),
-                            "e2e_ms_total_min": e2e_reps[0][0], "e2e_ms_total_max": e2e_reps[-1][0]},
+                            "e2e_ms_total_min": e2e_reps[0][0], "e2e_ms_total_max": e2e_reps[-1][0],
+                            "ms_total_all": [round(r[0], 3) for r in reps], "e2e_ms_total_all": [round(r[0], 3) for r in e2e_reps]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(res_e2e.iterations, 1),
                         "d2h_bytes_per_step": d2h / max(res_e2e.iterations, 1), "ms_total": ms_e2e,
                         "note": "one call = lba_set_problem from pinned host arrays + K LM iterations + results to host"},
