@@ -177,6 +177,12 @@ struct lba_ctx {
   size_t peer_rs_min = 16384;
   DBuf<unsigned long long> peer_trace;   // LBA_PEER_TRACE: device-side wait/total times of the exchanges
 
+  // lines with more than kTile observations (fragment tiles + fix-up kernels)
+  int n_long = 0, n_frag = 0;
+  DBuf<int> long_line, long_frag0, long_tile0;
+  DBuf<double> fragV, fragT, frag_partial;
+  LongLines long_lines() const { LongLines L; L.n = n_long; L.line = long_line.p; L.frag0 = long_frag0.p; L.tile0 = long_tile0.p; return L; }
+
   // N1: per-2D-line tables resident across the incremental loop (lba_lines2d_set)
   long long n_lines2d = 0;
   DBuf<double> l2d_n, l2d_p0, l2d_p1, l2d_end, l2d_stage;
@@ -772,7 +778,8 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   // (2) per-LINE work on the host: prefix sums and the greedy packing of whole lines into tiles
   std::vector<int> line_ptr((size_t)nl + 1, 0), line_slot((size_t)nl + 1, 0);
   std::vector<TileMeta> meta;
-  int kmax = 0;
+  std::vector<int> long_line, long_frag0, long_tile0;
+  int kmax = 0, n_frag = 0;
   {
     TileMeta cur;
     memset(&cur, 0, sizeof cur);
@@ -781,6 +788,19 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       const int k = line_cnt[l];
       kmax = std::max(kmax, k);
       line_ptr[(size_t)l + 1] = line_ptr[l] + k;
+      if (k > kTile) {
+        // a line that does not fit one tile: consecutive fragment tiles of its own (slots stay consecutive)
+        if (open) { meta.push_back(cur); open = false; }
+        long_line.push_back(l); long_frag0.push_back(n_frag); long_tile0.push_back((int)meta.size());
+        line_slot[l] = (int)meta.size() * kTile;
+        for (int done = 0; done < k; done += kTile) {
+          TileMeta f;
+          memset(&f, 0, sizeof f);
+          f.l0 = l; f.nl = 1; f.nobs = std::min(kTile, k - done); f.frag = ++n_frag; f.lend[0] = (unsigned short)f.nobs;
+          meta.push_back(f);
+        }
+        continue;
+      }
       if (open && (cur.nobs + k > kTile || cur.nl >= kMaxLinesPerTile)) { meta.push_back(cur); open = false; }
       if (!open) { memset(&cur, 0, sizeof cur); cur.l0 = l; open = true; }
       line_slot[l] = (int)meta.size() * kTile + cur.nobs;
@@ -789,8 +809,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     }
     if (open) meta.push_back(cur);
   }
-  if (kmax > LBA_MAX_OBS_PER_LINE)
-    return fail(LBA_ERR_UNSUPPORTED, "a 3D line has %d observations; at most %d are supported", kmax, LBA_MAX_OBS_PER_LINE);
+  long_frag0.push_back(n_frag);
   const int ntiles = (int)meta.size();
   const long long Mp64 = (long long)ntiles * kTile;
   if (Mp64 > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "padded observation count out of range");
@@ -808,6 +827,11 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     CK(cudaMemcpyAsync(d_line_slot, line_slot.data(), ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, LBA_K_MISC, k_init_tidx, ntiles, kTile, ntiles, ctx->meta_stage.p, ctx->tidx.p);
     CK(cudaMemsetAsync(ctx->slot_src.p, 0xFF, (size_t)Mp * 4, ctx->stream));   // -1 = padding
+  }
+  ctx->n_long = (int)long_line.size(); ctx->n_frag = n_frag;
+  if (ctx->n_long > 0) {
+    CKR(upload(ctx, ctx->long_line, long_line)); CKR(upload(ctx, ctx->long_frag0, long_frag0)); CKR(upload(ctx, ctx->long_tile0, long_tile0));
+    CKR(ctx->fragV.alloc((size_t)n_frag * 27)); CKR(ctx->fragT.alloc((size_t)n_frag * 6)); CKR(ctx->frag_partial.alloc((size_t)ctx->n_long * 4));
   }
   if (m > 0) {
     const int* d_order = nullptr;
@@ -972,7 +996,7 @@ static EvalArgs eval_args(lba_ctx* c, const LmCtl* ctl, int which) {
   a.pts = dual<const double>(c->pts.p, c->pts_new.p);
   a.r = dual(c->r.p, c->r_new.p); a.jl = dual(c->jl.p, c->jl_new.p); a.jc = dual(c->jc.p, c->jc_new.p);
   a.V = dual(c->V.p, c->V_new.p); a.gl = dual(c->gl.p, c->gl_new.p); a.gbits = dual(c->gbits.p, c->gbits_new.p);
-  a.ctl = ctl; a.which = which;
+  a.ctl = ctl; a.which = which; a.fragV = c->fragV.p;
   a.cost_partial = c->cost_partial.p;
   a.ticket = c->tickets.p; a.cost_out = &scal_local(c)->cost;
   a.loss = c->loss; a.f_scale = c->f_scale;
@@ -1027,6 +1051,9 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
     a.stg_bufs = c->eval_stg_bufs;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
+    if (c->n_long > 0)   // lines with more than kTile observations: add up their fragments' blocks
+      LAUNCH(c, LBA_K_JACOBIAN, k_frag_blocks, c->n_long, 32, c->long_lines(), (const double*)c->fragV.p, dual(c->V.p, c->V_new.p),
+             dual(c->gl.p, c->gl_new.p), dual(c->gbits.p, c->gbits_new.p), ctl, which);
   } else {
     CK(cudaMemsetAsync(&scal_local(c)->cost, 0, 8, c->stream));
   }
@@ -1109,7 +1136,7 @@ static int solve_setup(lba_ctx* c, const LmCtl* ctl, double lam, double pcg_tol,
   la.w = c->wk.p; la.w2 = c->wr.p; la.y = c->y.p;
   la.gl = dual<const double>(c->gl.p, c->gl_new.p); la.r = dual<const double>(c->r.p, c->r_new.p);
   la.dl = c->dl.p; la.alpha = 1.0;
-  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &scal_local(c)->rjd; la.st = c->cgst.p; la.ctl = ctl;
+  la.partial = c->bs_partial.p; la.ticket = c->tickets.p + 1; la.out4 = &scal_local(c)->rjd; la.st = c->cgst.p; la.ctl = ctl; la.fragT = c->fragT.p;
   if (c->ntiles > 0)
     LAUNCH_DYN(c, LBA_K_LINE_SCALARS, k_line_pass<kModeScalars>, c->grid_lp[2], kTile, c->smem_lp[2], la);
   la.w = c->w.p;
@@ -1165,6 +1192,9 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
     if (c->ntiles > 0) {
       c->window(c->jl.p, (size_t)c->ntiles * 6 * kTile * 8, c->l2_persist / 2);
       LAUNCH_DYN(c, LBA_K_PCG_LINE, k_line_pass<kModeMatvec>, c->grid_lp[0], kTile, c->smem_lp[0], sp->la);
+      if (c->n_long > 0)
+        LAUNCH(c, LBA_K_PCG_LINE, k_frag_matvec, c->n_long, kTile, c->long_lines(), (const TileIdx*)c->tidx.p, sp->la.jl,
+               (const double*)c->Vinv.p, (const double*)c->fragT.p, c->w.p, (const CgState*)c->cgst.p, sp->la.ctl);
     }
     PeerLink pl;
     memset(&pl, 0, sizeof pl);
@@ -1197,6 +1227,10 @@ static int launch_cam_step(lba_ctx* c, const LmCtl* ctl) {
 static int solve_finish(lba_ctx* c, SolvePlan* sp) {
   if (c->ntiles > 0) {
     LAUNCH_DYN(c, LBA_K_BACKSUB, k_line_pass<kModeBacksub>, c->grid_lp[1], kTile, c->smem_lp[1], sp->la);
+    if (c->n_long > 0)
+      LAUNCH(c, LBA_K_BACKSUB, k_frag_backsub, c->n_long, kTile, c->long_lines(), (const TileIdx*)c->tidx.p, sp->la.jl,
+             (const double*)c->Vinv.p, sp->la.gl, sp->la.r, sp->la.pts, c->dl.p, (const double*)c->fragT.p, (const double*)c->w.p,
+             1.0, c->frag_partial.p, c->tickets.p + 5, sp->la.out4, sp->la.ctl);
   } else {
     if (c->nl > 0) CK(cudaMemcpyAsync(c->pts_new.p, c->pts.p, (size_t)c->nl * 48, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemsetAsync(&scal_local(c)->rjd, 0, 32, c->stream));

@@ -51,7 +51,8 @@ struct __align__(16) TileMeta {
   int l0;      // first global line of the tile
   int nl;      // lines in the tile
   int nobs;    // real observations (slots [0,nobs) are used)
-  int pad;
+  int frag;    // 0: the tile holds whole lines; f + 1: the tile is fragment f of a line with more than kTile observations
+               // (nl == 1, l0 = that line): its per-line sums are partial and go to the fragment buffers
   unsigned short lend[kMaxLinesPerTile];  // exclusive end slot of local line ll (start = lend[ll-1] or 0)
 };
 static_assert(sizeof(TileMeta) % 16 == 0, "TileMeta must be bulk-copyable");
@@ -460,6 +461,7 @@ struct EvalArgs {
   Dual<unsigned long long> gbits;  // inf-norm of the gradient, as ordered bits
   const LmCtl* ctl;        // LM loop: control block (NULL for the stand-alone API calls)
   int which;               // 0: the current set, 1: the trial set
+  double* fragV;           // [n_fragments][27] partial V_l | g_l of the fragments of long lines (k_frag_blocks adds them up)
   double* cost_partial;    // [gridDim]
   unsigned int* ticket;    // last-CTA reduction ticket
   double* cost_out;        // 0.5 * sum r^2
@@ -654,12 +656,12 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       // per-line blocks V_l = sum jl jl^T (21) and g_l = sum jl r (6): four register-blocked work
       // items per line (rows {0}, {1}, {2,5}, {3,4} of the upper triangle: 7/6/7/7 FMAs per
       // observation on 7/6/5/4 shared-memory loads), fixed summation order
-      const int l0 = s_meta->l0, nlg = s_meta->nl;
+      const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
       for (int wi = t; wi < nlg * 4; wi += kTile) {
         const int ll = wi >> 2, part = wi & 3;
         const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        double* Vo = g_V + (size_t)(l0 + ll) * 21;
-        double* go = g_gl + (size_t)(l0 + ll) * 6;
+        double* Vo = frag ? a.fragV + (size_t)(frag - 1) * 27 : g_V + (size_t)(l0 + ll) * 21;
+        double* go = frag ? Vo + 21 : g_gl + (size_t)(l0 + ll) * 6;
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         double g0 = 0.0, g1 = 0.0;
         if (part == 0) {
@@ -703,6 +705,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
           Vo[15] = acc[0]; Vo[16] = acc[1]; Vo[17] = acc[2]; go[3] = acc[3];
           Vo[18] = acc[4]; Vo[19] = acc[5]; go[4] = acc[6]; g0 = acc[3]; g1 = acc[6];
         }
+        if (frag) continue;   // partial gradient of a long line: k_frag_blocks takes its norm
         const double ab0 = fabs(g0), ab1 = fabs(g1);
         gmax = (ab0 > gmax || ab0 != ab0) ? ab0 : gmax;   // NaN propagates
         gmax = (ab1 > gmax || ab1 != ab1) ? ab1 : gmax;
@@ -1082,6 +1085,7 @@ struct LinePassArgs {
   double* out4;          // BACKSUB: the four sums
   const CgState* st;     // MATVEC: early exit when done
   const LmCtl* ctl;      // LM loop: control block (NULL for the stand-alone API calls)
+  double* fragT;         // [n_fragments][6] partial t_l of the fragments of long lines (k_frag_matvec / k_frag_backsub)
 };
 
 enum { kModeMatvec = 0, kModeBacksub = 1, kModeScalars = 2 };
@@ -1236,7 +1240,7 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
       // 8 lanes per line: lane b < 6 sums component b, then the 6x6 product by shuffles
       {
         const int sub = t & 7, grp = t >> 3;
-        const int nlg = s_meta->nl, l0 = s_meta->l0;
+        const int nlg = s_meta->nl, l0 = s_meta->l0, frag = s_meta->frag;
         const int rounds = (nlg + (kTile / 8) - 1) / (kTile / 8);
         for (int rd = 0; rd < rounds; ++rd) {
           const int lx = rd * (kTile / 8) + grp;
@@ -1245,7 +1249,13 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
           if (have) {
             const int s0 = lx ? s_meta->lend[lx - 1] : 0, s1 = s_meta->lend[lx];
             for (int q = s0; q < s1; ++q) tv += s_stg[q * kLpRow + sub];
-            if (MODE == kModeBacksub) tv += s_aux[lx * 6 + sub];
+            if (frag) {
+              // fragment of a long line: only the partial sum; w_i = s_i for now, the fix-up kernel finishes the line
+              a.fragT[(size_t)(frag - 1) * 6 + sub] = tv;
+              tv = 0.0;
+            } else if (MODE == kModeBacksub) {
+              tv += s_aux[lx * 6 + sub];
+            }
           }
           double u = 0.0;
           const double* S = s_vinv + (have ? lx : 0) * kVinvStride;
@@ -1255,7 +1265,7 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
             if (have) u += S[sym_idx(sub < b ? sub : b, sub < b ? b : sub)] * tvb;
           }
           if (have) {
-            if (MODE == kModeBacksub) {
+            if (MODE == kModeBacksub && !frag) {
               u = -u;
               const double x = s_pts[lx * 6 + sub];
               // trial point x + alpha dl, rounded like the oracle (no FMA); dl is kept for a retry
@@ -1276,6 +1286,8 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
       }
       if (MODE == kModeMatvec) {
         a.w[i] = active ? s - d : 0.0;
+      } else if (s_meta->frag) {
+        a.w[i] = s;   // kept for k_frag_backsub: (J delta)_i = s_i + jl_i . dl needs the whole line's dl
       } else {
         const double jd = active ? s + d : 0.0;
         const double rr = active ? s_r[t] : 0.0;
@@ -1295,6 +1307,148 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
                             block_sum<kTile>(p3, red)};
     last_cta_reduce<kTile, 4>(sums, a.partial, a.ticket, a.out4, 1.0, red);
   }
+}
+
+// ---- lines with more than kTile observations --------------------------------------------------------------------
+// Such a line occupies ceil(k / kTile) consecutive FRAGMENT tiles of its own (TileMeta::frag).  The tile kernels
+// leave the per-line sums of a fragment partial (fragV, fragT); these kernels, one CTA per long line, add the
+// fragments in order and finish what needs the whole line.  (The reference has no limit on the observations of a
+// line, /root/reference/src/bundle_adjustment.py:194-250.)
+struct LongLines {
+  int n;               // long lines
+  const int* line;     // [n] global line id
+  const int* frag0;    // [n+1] first fragment of each long line (fragments are numbered over all long lines)
+  const int* tile0;    // [n] first tile of each long line (its fragments are consecutive tiles)
+};
+
+// V_l | g_l of a long line = sum of its fragments' partial blocks; line part of the gradient inf-norm
+__global__ void __launch_bounds__(32) k_frag_blocks(const LongLines L, const double* __restrict__ fragV, const Dual<double> V2,
+                                                    const Dual<double> gl2, const Dual<unsigned long long> gbits2,
+                                                    const LmCtl* __restrict__ ctl, int which) {
+  pdl_prologue();
+  if (ctl_skip_trial(ctl)) return;
+  const int set = ctl_cur(ctl) ^ which;
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int line = L.line[q];
+  double v = 0.0;
+  if (t < 27) {
+    for (int f = L.frag0[q]; f < L.frag0[q + 1]; ++f) v += fragV[(size_t)f * 27 + t];
+    if (t < 21) V2.sel(set)[(size_t)line * 21 + t] = v;
+    else gl2.sel(set)[(size_t)line * 6 + t - 21] = v;
+  }
+  double g = (t >= 21 && t < 27) ? fabs(v) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, g, o);
+    g = (other > g || other != other) ? other : g;
+  }
+  if (t == 0 && g != 0.0) atomicMax(gbits2.sel(set), (unsigned long long)__double_as_longlong(g));
+}
+
+// MATVEC of a long line: t_l = sum of the fragments' partial sums, u_l = Vinv_l t_l, w_i -= jl_i . u_l
+// (the tile kernel left w_i = s_i)
+__global__ void __launch_bounds__(kTile) k_frag_matvec(const LongLines L, const TileIdx* __restrict__ tidx,
+                                                       const Dual<const double> jl2, const double* __restrict__ Vinv,
+                                                       const double* __restrict__ fragT, double* __restrict__ w,
+                                                       const CgState* __restrict__ st, const LmCtl* __restrict__ ctl) {
+  pdl_prologue();
+  __shared__ double s_t[6], s_u[6];
+  if (st->done) return;
+  const double* __restrict__ jl = jl2.sel(ctl_cur(ctl));
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int line = L.line[q], f0 = L.frag0[q], f1 = L.frag0[q + 1], tile0 = L.tile0[q];
+  if (t < 6) {
+    double v = 0.0;
+    for (int f = f0; f < f1; ++f) v += fragT[(size_t)f * 6 + t];
+    s_t[t] = v;
+  }
+  __syncthreads();
+  if (t < 6) {
+    const double* S = Vinv + (size_t)line * kVinvStride;
+    double u = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) u += S[sym_idx(t < b ? t : b, t < b ? b : t)] * s_t[b];
+    s_u[t] = u;
+  }
+  __syncthreads();
+  for (int f = 0; f < f1 - f0; ++f) {
+    const int tile = tile0 + f;
+    if (t >= tidx[tile].meta.nobs) continue;
+    double d = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d += jl[((size_t)tile * 6 + k) * kTile + t] * s_u[k];
+    w[(size_t)tile * kTile + t] -= d;
+  }
+}
+
+// BACKSUB of a long line: dl = -Vinv_l (gl_l + t_l), the trial point, (J delta)_i = s_i + jl_i . dl and the line's
+// share of the four sums (added to `out4` by the last CTA, in line order)
+__global__ void __launch_bounds__(kTile) k_frag_backsub(const LongLines L, const TileIdx* __restrict__ tidx,
+                                                        const Dual<const double> jl2, const double* __restrict__ Vinv,
+                                                        const Dual<const double> gl2, const Dual<const double> r2,
+                                                        const Dual<double> pts2, double* __restrict__ dl,
+                                                        const double* __restrict__ fragT, const double* __restrict__ s_obs,
+                                                        double alpha, double* __restrict__ partial /*[n][4]*/,
+                                                        unsigned int* ticket, double* __restrict__ out4,
+                                                        const LmCtl* __restrict__ ctl) {
+  pdl_prologue();
+  __shared__ double s_t[6], s_u[6], red[kTile / 32];
+  if (ctl_skip_backsub(ctl)) return;
+  const int cur = ctl_cur(ctl);
+  if (ctl) alpha = ctl->alpha;
+  const double* __restrict__ jl = jl2.sel(cur);
+  const double* __restrict__ r = r2.sel(cur);
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int line = L.line[q], f0 = L.frag0[q], f1 = L.frag0[q + 1], tile0 = L.tile0[q];
+  if (t < 6) {
+    double v = gl2.sel(cur)[(size_t)line * 6 + t];
+    for (int f = f0; f < f1; ++f) v += fragT[(size_t)f * 6 + t];
+    s_t[t] = v;
+  }
+  __syncthreads();
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  if (t < 6) {
+    const double* S = Vinv + (size_t)line * kVinvStride;
+    double u = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) u += S[sym_idx(t < b ? t : b, t < b ? b : t)] * s_t[b];
+    u = -u;
+    const double x = pts2.sel(cur)[(size_t)line * 6 + t];
+    pts2.sel(cur ^ 1)[(size_t)line * 6 + t] = __dadd_rn(x, __dmul_rn(alpha, u));
+    dl[(size_t)line * 6 + t] = u;
+    s_u[t] = u;
+    p2 = u * u; p3 = x * x;
+  }
+  __syncthreads();
+  for (int f = 0; f < f1 - f0; ++f) {
+    const int tile = tile0 + f;
+    if (t >= tidx[tile].meta.nobs) continue;
+    double d = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d += jl[((size_t)tile * 6 + k) * kTile + t] * s_u[k];
+    const size_t i = (size_t)tile * kTile + t;
+    const double jd = s_obs[i] + d;
+    p0 += r[i] * jd;
+    p1 += jd * jd;
+  }
+  const double sums[4] = {block_sum<kTile>(p0, red), block_sum<kTile>(p1, red), block_sum<kTile>(p2, red), block_sum<kTile>(p3, red)};
+  // like last_cta_reduce, but ADDED to what the tile kernel already wrote
+  __shared__ int s_last;
+  if (t == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) partial[(size_t)q * 4 + c] = sums[c];
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (t < 4) {
+    double acc = out4[t];
+    for (int g = 0; g < (int)gridDim.x; ++g) acc += __ldcg(partial + (size_t)g * 4 + t);
+    out4[t] = acc;
+  }
+  if (t == 0) *ticket = 0u;
 }
 
 // Camera-ordered half of S*p: qpart_c = sum_{j in c} jc_j w_{perm[j]}

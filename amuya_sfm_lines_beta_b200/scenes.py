@@ -108,9 +108,17 @@ def make_synthetic_scene(n_cams, n_lines, obs_per_line=10, seed=0, variant="A",
     omega = Rotation.from_matrix(R).as_rotvec()
     R = _rotvec_to_matrix(omega)
 
-    cam_of = _sample_visibility(rng, n_lines, n_cams, obs_per_line, variant)
-    li = np.repeat(np.arange(n_lines, dtype=np.int64), obs_per_line)
-    ci = cam_of.reshape(-1).astype(np.int64)
+    if np.ndim(obs_per_line) == 0:
+        cam_of = _sample_visibility(rng, n_lines, n_cams, obs_per_line, variant)
+        li = np.repeat(np.arange(n_lines, dtype=np.int64), obs_per_line)
+        ci = cam_of.reshape(-1).astype(np.int64)
+    else:
+        # a different number of (distinct) observing cameras per line, e.g. a few lines seen from hundreds of views
+        ks = np.asarray(obs_per_line, dtype=np.int64)
+        if ks.shape != (n_lines,) or ks.max() > n_cams:
+            raise ValueError("obs_per_line must be an int or one count <= n_cams per line")
+        li = np.repeat(np.arange(n_lines, dtype=np.int64), ks)
+        ci = np.concatenate([np.sort(rng.choice(n_cams, int(k), replace=False)) for k in ks]).astype(np.int64)
     m = li.shape[0]
 
     # observed endpoints slide along the 3D segment (relaxed endpoint constraint)

@@ -322,11 +322,12 @@ class LineBA:
             setattr(o, k, v)
         return o
 
-    def lm_solve(self, camera_params, points_3d, want_residuals=True, out=None, **options) -> LMResult:
+    def lm_solve(self, camera_params, points_3d, want_residuals=True, out=None, residuals_out=None, **options) -> LMResult:
         """Optimise cameras and 3D lines.  ``camera_params`` (Nc,6) interleaved and
         ``points_3d`` (2Nl,3) are not modified; optimised copies are returned (host numpy),
         unless ``out=(cams_buf, pts_buf)`` gives buffers (numpy or torch, any device) that
-        are read as the initial guess and overwritten in place."""
+        are read as the initial guess and overwritten in place; ``residuals_out`` likewise receives ``fun`` at the
+        solution (a pinned buffer avoids the pageable-memory staging of a fresh array per call)."""
         o = self.default_options(**options)
         if out is None:
             cams = np.array(camera_params, dtype=np.float64, order="C", copy=True).reshape(self.n_cameras, 6)
@@ -338,10 +339,16 @@ class LineBA:
             pp, _k1 = _as_ptr(pts, np.float64, "float64", 6 * self.n_lines, ctx=self)
             if (_k0 is not cams) or (_k1 is not pts):
                 raise ValueError("out buffers must be contiguous float64")
-        r = np.empty(self.m, dtype=np.float64) if want_residuals else None
+        if residuals_out is not None:
+            # caller-provided (m,) float64 buffer for fun at the solution, e.g. a pinned tensor reused across calls
+            pr, r = _as_ptr(residuals_out, np.float64, "float64", self.m, ctx=self)
+            if r is not residuals_out:
+                raise ValueError("residuals_out must be contiguous float64")
+        else:
+            r = np.empty(self.m, dtype=np.float64) if want_residuals else None
+            pr = r.ctypes.data if r is not None else None
         rep = LbaReport()
-        check(self._lib.lba_lm_solve(self._h, pc, pp, C.byref(o), C.byref(rep),
-                                     r.ctypes.data if r is not None else None))
+        check(self._lib.lba_lm_solve(self._h, pc, pp, C.byref(o), C.byref(rep), pr))
         n = rep.trace_len
         trace = [dict(it=rep.trace_it[i], alpha=rep.trace_alpha[i], cost=rep.trace_cost[i], cost_new=rep.trace_cost_new[i], lam=rep.trace_lambda[i],
                       pcg=rep.trace_pcg[i], pred=rep.trace_pred[i], accepted=bool(rep.trace_accepted[i]),

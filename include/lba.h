@@ -40,7 +40,6 @@ extern "C" {
 #define LBA_ERR_NONFINITE (-5) /* "Residuals are not finite in the initial point." (scipy least_squares.py:949) */
 #define LBA_ERR_COMM (-6)
 
-#define LBA_MAX_OBS_PER_LINE 256 /* a 3D line may be observed at most this many times (one CTA tile) */
 
 typedef struct lba_ctx lba_ctx;
 
