@@ -26,6 +26,7 @@ EXPORTS = [
     "lba_get_profile", "lba_kernel_class_name", "lba_measure_fp64_peak", "lba_measure_copy_bandwidth",
     "lba_triangulate_lines", "lba_track_table",
     "lba_lines2d_set", "lba_observations_from_tables", "lba_set_problem_lines2d", "lba_triangulate_tracks",
+    "lba_residuals12", "lba_project12", "lba_lm_solve12",
 ]
 
 
@@ -114,6 +115,9 @@ def load():
     lib.lba_observations_from_tables.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
     lib.lba_set_problem_lines2d.argtypes = [vp, i64, i64, i64, vp, vp, vp]
     lib.lba_triangulate_tracks.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.lba_residuals12.argtypes = [vp, vp, vp, vp, C.POINTER(dbl)]
+    lib.lba_project12.argtypes = [vp, i64, vp, vp, vp]
+    lib.lba_lm_solve12.argtypes = [vp, vp, vp, C.POINTER(LbaOptions), C.POINTER(LbaReport), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("lba_version",):

@@ -68,9 +68,13 @@ def project(points, camera_params_, device=0):
     (column 0 = Rodrigues vector, column 1 = centre).  Returns unit bearings (N,3)."""
     points = np.asarray(points, dtype=np.float64).reshape(-1, 3)
     cams = np.asarray(camera_params_, dtype=np.float64)
-    if cams.ndim == 3 and cams.shape[2] == 4:
-        raise NotImplementedError("the 12-parameter [R|c] camera model (reference :43-45) is not supported")
     N = points.shape[0]
+    if cams.ndim == 3 and cams.shape[2] == 4:       # [R|c] rows (reference :43-45)
+        ba = LineBA(device)
+        try:
+            return ba.project12(points, cams.reshape(N, 12))
+        finally:
+            ba.close()
     cams = cams.reshape(N, 6)
     # every row gets its own camera and its own degenerate "3D line" (row, row)
     ba = LineBA(device)
@@ -88,10 +92,10 @@ def fun(params, n_cameras, n_points, camera_indices_pt, pt_indices, points_2d_p,
     """Residual vector (reference :78-139), one scalar per observed 2D line."""
     params = np.asarray(params, dtype=np.float64)
     n_cam_par = int((len(params) - 3 * n_points) / n_cameras)
-    if n_cam_par != 6:
-        raise NotImplementedError("only the 6-parameter Rodrigues camera model is supported")
-    cams = params[:n_cameras * 6].reshape(n_cameras, 6)
-    pts = params[n_cameras * 6:].reshape(n_points, 3)
+    if n_cam_par not in (6, 12):
+        raise ValueError("camera rows must have 6 (Rodrigues vector | centre) or 12 ([R|c]) parameters")
+    cams = params[:n_cameras * n_cam_par].reshape(n_cameras, n_cam_par)
+    pts = params[n_cameras * n_cam_par:].reshape(n_points, 3)
     ci = np.asarray(camera_indices_pt)[0::2].astype(np.int64)
     li = (np.asarray(pt_indices)[0::2] // 2).astype(np.int64)
     n, p0, p1 = _flatten_lines_2d(lines_2d)
@@ -139,8 +143,8 @@ def run_bundle_adjustment(input_bundle_adjustment, loss_f, *, device=0, verbose=
     camera_indices = np.asarray(input_bundle_adjustment['camera_indices'])
     line_indices = np.asarray(input_bundle_adjustment['lines_indices'])
     lines_2d = input_bundle_adjustment['lines_2d']
-    if camera_params.ndim != 2 or camera_params.shape[1] != 6:
-        raise NotImplementedError("only (Nc,6) Rodrigues camera rows are supported (reference :43-45 is optional)")
+    if camera_params.ndim != 2 or camera_params.shape[1] not in (6, 12):
+        raise ValueError("camera_params must be (Nc,6) Rodrigues rows or (Nc,12) [R|c] rows (reference :43-45)")
 
     points_3d, _points_2d_p, _cam_pt, _pt_idx = point_wise_input(lines_3d, lines_2d, camera_indices, line_indices)
     n_cameras = camera_params.shape[0]
@@ -165,5 +169,5 @@ def run_bundle_adjustment(input_bundle_adjustment, loss_f, *, device=0, verbose=
         print("Function evaluations {0}, initial cost {1:.4e}, final cost {2:.4e}.".format(
             res.n_jac + res.n_res, res.cost_init, res.cost))
     print("Optimization took {0:.0f} seconds".format(t1 - t0))
-    out = (res.camera_params.reshape(n_cameras, 6), res.points_3d.reshape(n_points, 3), np.copy(res.residuals))
+    out = (res.camera_params.reshape(n_cameras, camera_params.shape[1]), res.points_3d.reshape(n_points, 3), np.copy(res.residuals))
     return out + (res,) if return_report else out

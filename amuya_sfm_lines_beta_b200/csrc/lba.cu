@@ -8,6 +8,7 @@
 // The same algorithm is restated in numpy in oracle/line_ba_oracle.py (test oracle).
 #include "../../include/lba.h"
 #include "lba_kernels.cuh"
+#include "lba_dense12.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -408,7 +409,7 @@ extern "C" int lba_create(int device, lba_ctx** out) {
   CK(cudaMemsetAsync(c->gbits.p, 0, 8, c->stream));
   CK(cudaMemsetAsync(c->gbits_new.p, 0, 8, c->stream));
   CKR(c->clamped.alloc(1));
-  CKR(c->tickets.alloc(8));
+  CKR(c->tickets.alloc(8));   // 0 eval, 1 backsub, 2 cam step, 3 fused link, 4 two-phase reduce, 5 long lines, 6 dense 12-parameter path
   CK(cudaMemsetAsync(c->tickets.p, 0, 32, c->stream));
   CK(cudaMemsetAsync(c->scal.p, 0, sizeof(Scalars), c->stream));
   CK(cudaMemsetAsync(c->clamped.p, 0, sizeof(int), c->stream));
@@ -1832,6 +1833,230 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
              rep->trace_lambda[k], rep->trace_alpha[k], rep->trace_pcg[k], acc ? "ok" : "rej");
     }
   }
+  rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return take_launch_err(c);
+}
+
+// ---- C ABI: the 12-parameter [R|c] camera rows (see lba_dense12.cuh) ------------------------------
+// cuSOLVER through dlopen, on first use (nothing else in this library needs it)
+struct CusolverApi {
+  void* handle = nullptr;
+  int (*Create)(void**) = nullptr;
+  int (*Destroy)(void*) = nullptr;
+  int (*SetStream)(void*, cudaStream_t) = nullptr;
+  int (*Dpotrf_bufferSize)(void*, int, int, double*, int, int*) = nullptr;
+  int (*Dpotrf)(void*, int, int, double*, int, double*, int, int*) = nullptr;
+  int (*Dpotrs)(void*, int, int, int, const double*, int, double*, int, int*) = nullptr;
+};
+static CusolverApi g_cusolver;
+static int load_cusolver() {
+  if (g_cusolver.handle) return LBA_OK;
+  void* h = dlopen("libcusolver.so.11", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libcusolver.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("/usr/local/cuda/lib64/libcusolver.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(LBA_ERR_UNSUPPORTED, "the 12-parameter camera mode needs libcusolver (dense Cholesky): %s", dlerror());
+  g_cusolver.Create = (decltype(g_cusolver.Create))dlsym(h, "cusolverDnCreate");
+  g_cusolver.Destroy = (decltype(g_cusolver.Destroy))dlsym(h, "cusolverDnDestroy");
+  g_cusolver.SetStream = (decltype(g_cusolver.SetStream))dlsym(h, "cusolverDnSetStream");
+  g_cusolver.Dpotrf_bufferSize = (decltype(g_cusolver.Dpotrf_bufferSize))dlsym(h, "cusolverDnDpotrf_bufferSize");
+  g_cusolver.Dpotrf = (decltype(g_cusolver.Dpotrf))dlsym(h, "cusolverDnDpotrf");
+  g_cusolver.Dpotrs = (decltype(g_cusolver.Dpotrs))dlsym(h, "cusolverDnDpotrs");
+  if (!g_cusolver.Create || !g_cusolver.Destroy || !g_cusolver.SetStream || !g_cusolver.Dpotrf_bufferSize || !g_cusolver.Dpotrf || !g_cusolver.Dpotrs)
+    return fail(LBA_ERR_UNSUPPORTED, "libcusolver is missing required symbols");
+  g_cusolver.handle = h;
+  return LBA_OK;
+}
+
+// a (camera, line) pair observed twice would need a sum in the coupling block
+__global__ void k_dup12(int Mp, const TileIdx* __restrict__ tidx, const int* __restrict__ line_slot, const int* __restrict__ line_cnt,
+                        int* __restrict__ dup) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mp) return;
+  const TileIdx& ti = tidx[i / kTile];
+  const int cam = ti.cam[i % kTile];
+  if (cam < 0) return;
+  const int l = ti.meta.l0 + ti.ll[i % kTile];
+  for (int s = line_slot[l]; s < i; ++s)
+    if (tidx[s / kTile].cam[s % kTile] == cam) { atomicAdd(dup, 1); return; }
+  (void)line_cnt;
+}
+
+struct Dense12 {
+  lba_ctx* c;
+  int n, Mp;
+  DBuf<double> x, x_new, r, r_new, jc, jc_new, jl, jl_new, H, A, g, D, rhs, sums, partial;
+  DBuf<int> info, dup;
+  DBuf<double> work;
+  void* solver = nullptr;
+  ~Dense12() { if (solver) g_cusolver.Destroy(solver); }
+};
+
+static int eval12(lba_ctx* c, Dense12& d, const double* x, double* r, double* jc, double* jl, bool with_jac, int loss, double f_scale) {
+  Eval12Args a;
+  a.Mp = c->Mp; a.ntiles = c->ntiles; a.nc = c->nc; a.nl = c->nl; a.tidx = c->tidx.p; a.cst = c->cst.p; a.x = x;
+  a.r = r; a.jc = jc; a.jl = jl; a.partial = d.partial.p; a.ticket = c->tickets.p + 6; a.cost_out = d.sums.p;
+  a.loss = loss; a.f_scale = f_scale;
+  if (c->ntiles == 0) { CK(cudaMemsetAsync(d.sums.p, 0, 8, c->stream)); return LBA_OK; }
+  if (with_jac) LAUNCH(c, LBA_K_JACOBIAN, k_eval12<true>, c->ntiles, kTile, a);
+  else LAUNCH(c, LBA_K_RESIDUAL, k_eval12<false>, c->ntiles, kTile, a);
+  return LBA_OK;
+}
+
+static int check12(lba_ctx* ctx, const double* cams, const double* pts) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (!ctx->have_problem) return fail(LBA_ERR_STATE, "lba_set_problem has not been called");
+  if (!cams || !pts) return fail(LBA_ERR_ARG, "NULL parameter array");
+  if (ctx->world > 1) return fail(LBA_ERR_UNSUPPORTED, "the 12-parameter camera mode runs on one GPU");
+  return LBA_OK;
+}
+
+extern "C" int lba_residuals12(lba_ctx* ctx, const double* cams12, const double* pts, double* residuals, double* cost) {
+  CKR(check12(ctx, cams12, pts));
+  CK(cudaSetDevice(ctx->device));
+  lba_ctx* c = ctx;
+  Dense12 d; d.c = c; d.n = 12 * c->nc + 6 * c->nl; d.Mp = c->Mp;
+  CKR(d.x.alloc(d.n)); CKR(d.r.alloc(c->Mp)); CKR(d.sums.alloc(8)); CKR(d.partial.alloc(2 * (size_t)std::max(c->ntiles, 1)));
+  CK(cudaMemcpyAsync(d.x.p, cams12, (size_t)c->nc * 96, cudaMemcpyDefault, c->stream));
+  CK(cudaMemcpyAsync(d.x.p + 12 * c->nc, pts, (size_t)c->nl * 48, cudaMemcpyDefault, c->stream));
+  CKR(eval12(c, d, d.x.p, d.r.p, nullptr, nullptr, false, 0, 1.0));
+  CKR(export_residuals(c, d.r.p, residuals));
+  double h = 0.0;
+  CK(cudaMemcpyAsync(&h, d.sums.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (cost) *cost = h;
+  return take_launch_err(c);
+}
+
+extern "C" int lba_project12(lba_ctx* ctx, int64_t n_rows, const double* points, const double* cams12, double* proj) {
+  if (!ctx) return fail(LBA_ERR_ARG, "ctx is NULL");
+  if (n_rows < 0 || (n_rows > 0 && (!points || !cams12 || !proj))) return fail(LBA_ERR_ARG, "bad argument");
+  if (n_rows == 0) return LBA_OK;
+  CK(cudaSetDevice(ctx->device));
+  DBuf<double> dp, dc, dout;
+  const size_t N = (size_t)n_rows;
+  CKR(dp.alloc(3 * N)); CKR(dc.alloc(12 * N)); CKR(dout.alloc(3 * N));
+  CK(cudaMemcpyAsync(dp.p, points, 24 * N, cudaMemcpyDefault, ctx->stream));
+  CK(cudaMemcpyAsync(dc.p, cams12, 96 * N, cudaMemcpyDefault, ctx->stream));
+  LAUNCH(ctx, LBA_K_MISC, k_project12, cdiv(n_rows, 256), 256, (long long)n_rows, (const double*)dp.p, (const double*)dc.p, dout.p);
+  CK(cudaMemcpyAsync(proj, dout.p, 24 * N, cudaMemcpyDefault, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return take_launch_err(ctx);
+}
+
+extern "C" int lba_lm_solve12(lba_ctx* ctx, double* cams12, double* pts_api, const lba_options* opts_in, lba_report* rep,
+                              double* residuals) {
+  CKR(check12(ctx, cams12, pts_api));
+  lba_options o;
+  if (opts_in) o = *opts_in; else lba_default_options(&o);
+  if (o.max_iter < 0 || !(o.lambda0 > 0.0) || o.loss < 0 || o.loss > LBA_LOSS_ARCTAN || !(o.f_scale > 0.0) || o.max_evals < 0 || o.max_backtrack < 0)
+    return fail(LBA_ERR_ARG, "bad options");
+  const auto t0 = std::chrono::steady_clock::now();
+  lba_report local;
+  if (!rep) rep = &local;
+  memset(rep, 0, sizeof(*rep));
+  lba_ctx* c = ctx;
+  CK(cudaSetDevice(c->device));
+  const long long n64 = 12LL * c->nc + 6LL * c->nl;
+  if (n64 > 16384) return fail(LBA_ERR_UNSUPPORTED, "the 12-parameter camera mode solves the dense normal equations: %lld parameters exceed its limit of 16384", n64);
+  CKR(load_cusolver());
+  Dense12 d; d.c = c; d.n = (int)n64; d.Mp = c->Mp;
+  const int n = d.n; const size_t M = (size_t)c->Mp, N = (size_t)n;
+  CKR(d.x.alloc(N)); CKR(d.x_new.alloc(N)); CKR(d.r.alloc(M)); CKR(d.r_new.alloc(M)); CKR(d.jc.alloc(12 * M)); CKR(d.jc_new.alloc(12 * M));
+  CKR(d.jl.alloc(6 * M)); CKR(d.jl_new.alloc(6 * M)); CKR(d.H.alloc(N * N)); CKR(d.A.alloc(N * N)); CKR(d.g.alloc(N)); CKR(d.D.alloc(N));
+  CKR(d.rhs.alloc(N)); CKR(d.sums.alloc(8)); CKR(d.partial.alloc(2 * (size_t)std::max(c->ntiles, 1))); CKR(d.info.alloc(1)); CKR(d.dup.alloc(1));
+  if (g_cusolver.Create(&d.solver) != 0) return fail(LBA_ERR_CUDA, "cusolverDnCreate failed");
+  g_cusolver.SetStream(d.solver, c->stream);
+  int lwork = 0;
+  if (n > 0 && g_cusolver.Dpotrf_bufferSize(d.solver, 0 /*CUBLAS_FILL_MODE_LOWER*/, n, d.A.p, n, &lwork) != 0) return fail(LBA_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+  CKR(d.work.alloc((size_t)std::max(lwork, 1)));
+  const int* d_line_cnt = c->line_tmp.p; const int* d_line_slot = d_line_cnt + 2 * ((size_t)c->nl + 1);
+  if (c->Mp > 0) {
+    CK(cudaMemsetAsync(d.dup.p, 0, 4, c->stream));
+    k_dup12<<<cdiv(c->Mp, 256), 256, 0, c->stream>>>(c->Mp, c->tidx.p, d_line_slot, d_line_cnt, d.dup.p);
+    int dup = 0;
+    CK(cudaMemcpyAsync(&dup, d.dup.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (dup) return fail(LBA_ERR_UNSUPPORTED, "%d observation(s) repeat a (camera, line) pair: not supported with 12-parameter cameras", dup);
+  }
+  CK(cudaMemcpyAsync(d.x.p, cams12, (size_t)c->nc * 96, cudaMemcpyDefault, c->stream));
+  CK(cudaMemcpyAsync(d.x.p + 12 * c->nc, pts_api, (size_t)c->nl * 48, cudaMemcpyDefault, c->stream));
+
+  auto host_scalar = [&](const double* dev, int k, double* out) -> int {
+    CK(cudaMemcpyAsync(out, dev, 8 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return LBA_OK;
+  };
+  // normal equations of the current evaluation (r, jc, jl): H, g; scaling D updated by the next damp
+  auto assemble = [&]() -> int {
+    if (n == 0) return LBA_OK;
+    CK(cudaMemsetAsync(d.H.p, 0, N * N * 8, c->stream));
+    if (c->nc > 0) LAUNCH(c, LBA_K_CAM_BLOCKS, k_h12_cam, c->nc, 192, n, (const int*)c->cam_ptr.p, (const int*)c->cam_perm.p, (const double*)d.jc.p, (const double*)d.r.p, d.H.p, d.g.p);
+    if (c->nl > 0) LAUNCH(c, LBA_K_CAM_BLOCKS, k_h12_line, cdiv((long long)c->nl * 42, 256), 256, n, c->nc, c->nl, d_line_slot, d_line_cnt, (const double*)d.jl.p, (const double*)d.r.p, d.H.p, d.g.p);
+    if (c->Mp > 0) LAUNCH(c, LBA_K_CAM_BLOCKS, k_h12_cross, cdiv(c->Mp, 256), 256, c->Mp, n, c->nc, (const TileIdx*)c->tidx.p, (const double*)d.jc.p, (const double*)d.jl.p, d.H.p);
+    return LBA_OK;
+  };
+
+  CKR(eval12(c, d, d.x.p, d.r.p, d.jc.p, d.jl.p, true, o.loss, o.f_scale));
+  double cost0 = 0.0;
+  CKR(host_scalar(d.sums.p, 1, &cost0));
+  rep->cost_init = cost0;
+  if (!std::isfinite(cost0)) return fail(LBA_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+  CKR(assemble());
+  LmCtl L;
+  memset(&L, 0, sizeof L);
+  L.ftol = o.ftol; L.xtol = o.xtol; L.gtol = o.gtol; L.lambda_min = o.lambda_min; L.lambda_max = o.lambda_max; L.min_ratio = o.min_ratio;
+  L.max_iter = o.max_iter; L.max_evals = o.max_evals; L.pcg_max_iter = 1; L.max_backtrack = o.max_backtrack;
+  L.lam = o.lambda0; L.nu = 2.0; L.sigma = 1.0; L.alpha = 1.0; L.cost = cost0; L.need_solve = 1; L.evals = 1; L.scaling_mode = 2;
+  if (L.max_iter <= 0) L.done = 1;
+  LmTrace* tr = c->h_trace;
+  bool first_scaling = true, new_eval = true;
+  while (!L.done) {
+    if (L.need_solve) {
+      LAUNCH(c, LBA_K_LINE_FACTOR, k_damp12, cdiv((long long)n * n, 256), 256, n, (const double*)d.H.p, d.D.p, first_scaling ? 1 : 0, L.lam, d.A.p, new_eval ? 1 : 0);
+      first_scaling = false; new_eval = false;
+      LAUNCH(c, LBA_K_MISC, k_neg12, cdiv(n, 256), 256, n, (const double*)d.g.p, d.rhs.p);
+      if (g_cusolver.Dpotrf(d.solver, 0, n, d.A.p, n, d.work.p, lwork, d.info.p) != 0) return fail(LBA_ERR_CUDA, "cusolverDnDpotrf failed");
+      if (g_cusolver.Dpotrs(d.solver, 0, n, 1, d.A.p, n, d.rhs.p, n, d.info.p) != 0) return fail(LBA_ERR_CUDA, "cusolverDnDpotrs failed");
+      if (c->ntiles > 0)
+        LAUNCH(c, LBA_K_BACKSUB, k_jd12, c->ntiles, kTile, c->Mp, c->nc, (const TileIdx*)c->tidx.p, (const double*)d.jc.p, (const double*)d.jl.p,
+               (const double*)d.r.p, (const double*)d.rhs.p, d.partial.p, c->tickets.p + 6, d.sums.p + 1);
+      LAUNCH(c, LBA_K_MISC, k_norms12, 1, kTile, n, (const double*)d.rhs.p, (const double*)d.x.p, (const double*)d.g.p, d.sums.p + 3);
+    }
+    LAUNCH(c, LBA_K_MISC, k_step12, cdiv(n, 256), 256, n, (const double*)d.x.p, (const double*)d.rhs.p, L.alpha, d.x_new.p);
+    CKR(eval12(c, d, d.x_new.p, d.r_new.p, d.jc_new.p, d.jl_new.p, true, o.loss, o.f_scale));
+    LmTrial t;
+    CKR(host_scalar(d.sums.p, 1, &t.cost_new));
+    double tail[5];   // rjd, jd2, |delta|^2, |x|^2, |g|_inf of the solve this trial belongs to
+    CKR(host_scalar(d.sums.p + 1, 5, tail));
+    int info = 0;
+    CK(cudaMemcpy(&info, d.info.p, 4, cudaMemcpyDeviceToHost));
+    if (info != 0) return fail(LBA_ERR_CUDA, "dense Cholesky of the damped normal equations failed (info %d)", info);
+    t.rjd = tail[0]; t.jd2 = tail[1]; t.d2 = tail[2]; t.x2 = tail[3]; t.g_norm = tail[4];
+    t.pcg_iters = 0; t.pcg_done = 1;
+    const int cur_before = L.cur;
+    lm_decide(L, t, tr);
+    if (L.cur != cur_before) {   // accepted: the trial evaluation becomes the current one
+      swap_buf(d.x, d.x_new); swap_buf(d.r, d.r_new); swap_buf(d.jc, d.jc_new); swap_buf(d.jl, d.jl_new);
+      CKR(assemble());
+      new_eval = true;
+    }
+  }
+  rep->iterations = L.it; rep->status = L.status; rep->cost = L.cost; rep->n_jac = L.evals; rep->n_accepted = L.n_acc;
+  rep->trace_len = L.trace_len;
+  for (int k = 0; k < L.trace_len; ++k) {
+    rep->trace_it[k] = tr->it[k]; rep->trace_pcg[k] = 0; rep->trace_accepted[k] = tr->accepted[k];
+    rep->trace_cost[k] = tr->cost[k]; rep->trace_cost_new[k] = tr->cost_new[k]; rep->trace_lambda[k] = tr->lam[k];
+    rep->trace_pred[k] = tr->pred[k]; rep->trace_step_norm[k] = tr->step_norm[k]; rep->trace_g_norm[k] = tr->g_norm[k];
+    rep->trace_alpha[k] = tr->alpha[k];
+  }
+  CK(cudaMemcpyAsync(cams12, d.x.p, (size_t)c->nc * 96, cudaMemcpyDefault, c->stream));
+  CK(cudaMemcpyAsync(pts_api, d.x.p + 12 * c->nc, (size_t)c->nl * 48, cudaMemcpyDefault, c->stream));
+  if (residuals) {
+    if (o.loss != 0) CKR(eval12(c, d, d.x.p, d.r.p, nullptr, nullptr, false, 0, 1.0));   // fun itself, not the rescaled residuals
+    CKR(export_residuals(c, d.r.p, residuals));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_eval = false;
   rep->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return take_launch_err(c);
 }

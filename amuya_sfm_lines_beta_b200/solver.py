@@ -106,8 +106,17 @@ class LineBA:
         self.m, self.n_cameras, self.n_lines = m, int(n_cameras), int(n_lines)
         return self
 
-    def _params(self, camera_params, points_3d):
-        pc, kc = _as_ptr(camera_params, np.float64, "float64", 6 * self.n_cameras, ctx=self)
+    @staticmethod
+    def _cam_width(camera_params):
+        """6 (Rodrigues vector | centre, interleaved) or 12 ([R|c] rows, bundle_adjustment.py:43-45)."""
+        n = camera_params.numel() if _is_torch(camera_params) else np.asarray(camera_params).size
+        shape = tuple(camera_params.shape)
+        if len(shape) >= 2 and shape[-1] in (6, 12):
+            return int(shape[-1])
+        return 6
+
+    def _params(self, camera_params, points_3d, width=6):
+        pc, kc = _as_ptr(camera_params, np.float64, "float64", width * self.n_cameras, ctx=self)
         pp, kp = _as_ptr(points_3d, np.float64, "float64", 6 * self.n_lines, ctx=self)
         return pc, pp, (kc, kp)
 
@@ -279,11 +288,23 @@ class LineBA:
         return out
 
     def residuals(self, camera_params, points_3d, want_residuals=True):
-        pc, pp, keep = self._params(camera_params, points_3d)
+        """``fun`` (bundle_adjustment.py:78-139) and the cost; (Nc,6) Rodrigues rows or (Nc,12) [R|c] rows."""
+        w = self._cam_width(camera_params)
+        pc, pp, keep = self._params(camera_params, points_3d, w)
         r = np.empty(self.m, dtype=np.float64) if want_residuals else None
         cost = C.c_double()
-        check(self._lib.lba_residuals(self._h, pc, pp, r.ctypes.data if r is not None else None, C.byref(cost)))
+        fn = self._lib.lba_residuals12 if w == 12 else self._lib.lba_residuals
+        check(fn(self._h, pc, pp, r.ctypes.data if r is not None else None, C.byref(cost)))
         return r, cost.value
+
+    def project12(self, points, camera_rows):
+        """``project`` for [R|c] rows (bundle_adjustment.py:43-63): ``points`` (N,3), ``camera_rows`` (N,12)."""
+        N = int(np.asarray(points).shape[0])
+        pp, k0 = _as_ptr(points, np.float64, "float64", 3 * N, ctx=self)
+        pc, k1 = _as_ptr(camera_rows, np.float64, "float64", 12 * N, ctx=self)
+        out = np.empty((N, 3), dtype=np.float64)
+        check(self._lib.lba_project12(self._h, N, pp, pc, out.ctypes.data))
+        return out
 
     def residuals_jacobian(self, camera_params, points_3d, want_jacobian=True):
         pc, pp, keep = self._params(camera_params, points_3d)
@@ -329,13 +350,14 @@ class LineBA:
         are read as the initial guess and overwritten in place; ``residuals_out`` likewise receives ``fun`` at the
         solution (a pinned buffer avoids the pageable-memory staging of a fresh array per call)."""
         o = self.default_options(**options)
+        w = self._cam_width(out[0] if out is not None else camera_params)
         if out is None:
-            cams = np.array(camera_params, dtype=np.float64, order="C", copy=True).reshape(self.n_cameras, 6)
+            cams = np.array(camera_params, dtype=np.float64, order="C", copy=True).reshape(self.n_cameras, w)
             pts = np.array(points_3d, dtype=np.float64, order="C", copy=True).reshape(2 * self.n_lines, 3)
             pc, pp = cams.ctypes.data, pts.ctypes.data
         else:
             cams, pts = out
-            pc, _k0 = _as_ptr(cams, np.float64, "float64", 6 * self.n_cameras, ctx=self)
+            pc, _k0 = _as_ptr(cams, np.float64, "float64", w * self.n_cameras, ctx=self)
             pp, _k1 = _as_ptr(pts, np.float64, "float64", 6 * self.n_lines, ctx=self)
             if (_k0 is not cams) or (_k1 is not pts):
                 raise ValueError("out buffers must be contiguous float64")
@@ -348,7 +370,8 @@ class LineBA:
             r = np.empty(self.m, dtype=np.float64) if want_residuals else None
             pr = r.ctypes.data if r is not None else None
         rep = LbaReport()
-        check(self._lib.lba_lm_solve(self._h, pc, pp, C.byref(o), C.byref(rep), pr))
+        solve = self._lib.lba_lm_solve12 if w == 12 else self._lib.lba_lm_solve   # 12: [R|c] rows, dense path
+        check(solve(self._h, pc, pp, C.byref(o), C.byref(rep), pr))
         n = rep.trace_len
         trace = [dict(it=rep.trace_it[i], alpha=rep.trace_alpha[i], cost=rep.trace_cost[i], cost_new=rep.trace_cost_new[i], lam=rep.trace_lambda[i],
                       pcg=rep.trace_pcg[i], pred=rep.trace_pred[i], accepted=bool(rep.trace_accepted[i]),

@@ -241,6 +241,18 @@ int lba_schur_solve(lba_ctx* ctx, double lambda, double pcg_tol, int32_t pcg_max
 int lba_lm_solve(lba_ctx* ctx, double* camera_params, double* points_3d, const lba_options* opts,
                  lba_report* report, double* residuals);
 
+/* ---- "next" row N4: the reference's 12-parameter camera rows -----------------------------------------------
+ * camera_params (Nc,12) f64 = [R|c] reshaped from (3,4) (bundle_adjustment.py:43-45; input_bundle_adj with
+ * rotate_model != "Rodrigues", seq_utils.py:168-169,182-184): the nine entries of R are free parameters.
+ * lba_residuals12 = fun, lba_project12 = project (points (N,3), one camera row per point), lba_lm_solve12 = the
+ * least_squares call: analytic Jacobian, dense normal equations + Cholesky (cuSOLVER, loaded on first use), the
+ * same step policy, options and report as lba_lm_solve.  Meant for the reference's problem sizes
+ * (12 Nc + 6 Nl <= 16384, one GPU). */
+int lba_residuals12(lba_ctx* ctx, const double* camera_params12, const double* points_3d, double* residuals, double* cost);
+int lba_project12(lba_ctx* ctx, int64_t n_rows, const double* points, const double* camera_params12, double* proj);
+int lba_lm_solve12(lba_ctx* ctx, double* camera_params12, double* points_3d, const lba_options* opts,
+                   lba_report* report, double* residuals);
+
 /* Multi-GPU: one context per rank, observations sharded at 3D-line boundaries, cameras
  * replicated.  Per-camera partial sums are combined with ncclAllReduce on the context's
  * stream.  rank 0 calls lba_comm_unique_id, ships the 128 bytes to the other ranks (e.g.

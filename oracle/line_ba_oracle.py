@@ -608,6 +608,141 @@ def lm_solve(camera_params, points_3d, ci, li, n, p0, p1, opts: LMOptions | None
 
 
 # ---------------------------------------------------------------------------
+# Part B' -- the 12-parameter [R|c] camera rows (bundle_adjustment.py:43-45): dense LM with the same step policy
+# ---------------------------------------------------------------------------
+
+def residuals12(camera_params12, points_3d, camera_indices, line_indices, n, p0, p1):
+    """``fun`` with (Nc,12) camera rows: ``reshape((3,4))``, R = [:, :3] (nine free entries), c = [:, 3]
+    (bundle_adjustment.py:43-45,111); x = R (X - c) as ``[R | -R c] [X;1]`` (:51-63)."""
+    return residuals_jacobian12(camera_params12, points_3d, camera_indices, line_indices, n, p0, p1, with_jac=False)[0]
+
+
+def residuals_jacobian12(camera_params12, points_3d, ci, li, n, p0, p1, with_jac=True):
+    """r (m,), jc (m,12) in the row layout [M_k0 M_k1 M_k2 c_k], jl (m,6):
+    u = de/dx,  de/dM_kj = u_k d_j,  de/dX = M^T u,  de/dc = -M^T u."""
+    P = np.asarray(camera_params12, dtype=np.float64).reshape(-1, 3, 4)
+    M, c = P[:, :, :3][ci], P[:, :, 3][ci]
+    pts = np.asarray(points_3d, dtype=np.float64).reshape(-1, 6)[li]
+    m = ci.shape[0]
+    r = np.zeros(m)
+    jc = np.zeros((m, 3, 4)); jl = np.zeros((m, 6))
+    l2 = LAMB * LAMB
+    for e, pe in enumerate((p0, p1)):
+        me = cross_nm(n, pe)
+        d = pts[:, 3 * e:3 * e + 3] - c
+        x = np.einsum('nij,nj->ni', M, d)
+        inv_rho = 1.0 / np.sqrt(np.einsum('ni,ni->n', x, x))
+        q = x * inv_rho[:, None]
+        a = np.einsum('ni,ni->n', q, n); b = np.einsum('ni,ni->n', q, me)
+        r += l2 * a * a + b * b
+        if with_jac:
+            g = (2.0 * l2 * a)[:, None] * n + (2.0 * b)[:, None] * me
+            gp = np.einsum('ni,ni->n', g, q)
+            u = (g - gp[:, None] * q) * inv_rho[:, None]
+            je = np.einsum('nij,ni->nj', M, u)
+            jc[:, :, :3] += u[:, :, None] * d[:, None, :]
+            jc[:, :, 3] -= je
+            jl[:, 3 * e:3 * e + 3] = je
+    return r, jc.reshape(m, 12), jl
+
+
+def lm_solve12(camera_params12, points_3d, ci, li, n, p0, p1, opts: LMOptions | None = None, verbose=False):
+    """Levenberg-Marquardt for the 12-parameter camera rows: dense damped normal equations
+    (J^T J + lam D) delta = -J^T r solved by Cholesky, Marquardt scaling D = running max of diag(J^T J), and the
+    step policy of ``lm_solve`` (first trial at sigma, measured length, retry along the same direction).
+    Returns (camera_params12, points_3d, residuals, report)."""
+    opts = opts or LMOptions()
+    ci = np.asarray(ci, dtype=np.int64); li = np.asarray(li, dtype=np.int64)
+    cams = np.asarray(camera_params12, dtype=np.float64).reshape(-1, 12).copy()
+    pts = np.asarray(points_3d, dtype=np.float64).reshape(-1, 6).copy()
+    nc, nl, m = cams.shape[0], pts.shape[0], ci.shape[0]
+    nn = 12 * nc + 6 * nl
+
+    def normal(r, jc, jl):
+        J = np.zeros((m, nn))
+        rows = np.arange(m)
+        for k in range(12):
+            J[rows, 12 * ci + k] = jc[:, k]
+        for k in range(6):
+            J[rows, 12 * nc + 6 * li + k] = jl[:, k]
+        return J, J.T @ J, J.T @ r
+
+    rep = LMReport()
+    r_true, jc, jl = residuals_jacobian12(cams, pts, ci, li, n, p0, p1)
+    rep.n_jac += 1
+    cost = robust_cost(r_true, opts.loss, opts.f_scale)
+    r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
+    rep.cost_init = cost
+    J, H, g = normal(r, jc, jl)
+    D = np.where(np.diag(H) == 0.0, 1.0, np.diag(H))
+    lam, nu, streak, sigma, status, it, nev, done = opts.lambda0, 2.0, 0, 1.0, 0, 0, 1, False
+    while not done and it < opts.max_iter:
+        if opts.max_evals and nev >= opts.max_evals:
+            break
+        g_norm = float(np.abs(g).max()) if nn else 0.0
+        if g_norm < opts.gtol:
+            status = 1
+            break
+        delta = np.linalg.solve(H + lam * np.diag(D), -g)
+        it += 1
+        jd = J @ delta
+        rjd, jd2, d2 = float(r @ jd), float(jd @ jd), float(delta @ delta)
+        x2 = float(np.sum(cams * cams) + np.sum(pts * pts)); x_norm = math.sqrt(x2)
+        alpha, bt = sigma, 0
+        while True:
+            if opts.max_evals and nev >= opts.max_evals:
+                done = True
+                break
+            pred = -alpha * rjd - 0.5 * alpha * alpha * jd2
+            cams_new = cams + alpha * delta[:12 * nc].reshape(nc, 12)
+            pts_new = pts + alpha * delta[12 * nc:].reshape(nl, 6)
+            r_new = residuals12(cams_new, pts_new, ci, li, n, p0, p1)
+            rep.n_res += 1; nev += 1
+            cost_new = robust_cost(r_new, opts.loss, opts.f_scale)
+            step_norm = alpha * math.sqrt(d2)
+            actual = cost - cost_new
+            finite = math.isfinite(cost_new)
+            ratio = actual / pred if (finite and pred > 0.0) else -1.0
+            accepted = finite and ratio > opts.min_ratio
+            a_opt = measured_length(alpha, cost, cost_new, rjd)
+            ftol_ok = finite and (actual < opts.ftol * cost) and (ratio > 0.25)
+            xtol_ok = step_norm < opts.xtol * (opts.xtol + x_norm)
+            rep.trace.append(dict(it=it - 1, cost=cost, cost_new=cost_new, lam=lam, pcg=0, pred=pred, alpha=alpha, ratio=ratio,
+                                  accepted=accepted, step_norm=step_norm, g_norm=g_norm, a_opt=a_opt))
+            if verbose:
+                print(f"{it - 1:4d} cost {cost:.6e} -> {cost_new:.6e} lam {lam:.2e} alpha {alpha:.3f} ratio {ratio:+.3f}")
+            retry = False
+            if accepted:
+                rep.n_accepted += 1
+                cams, pts, cost = cams_new, pts_new, cost_new
+                r_true, jc, jl = residuals_jacobian12(cams, pts, ci, li, n, p0, p1)
+                r, jc, jl = scale_for_robust_loss(r_true, jc, jl, opts.loss, opts.f_scale)
+                rep.n_jac += 1
+                J, H, g = normal(r, jc, jl)
+                D = np.maximum(D, np.where(np.diag(H) == 0.0, 1.0, np.diag(H)))
+                fac, streak, sigma = damping_update(ratio, a_opt, streak)
+                lam = min(max(lam * fac, opts.lambda_min), opts.lambda_max)
+                nu = 2.0
+            elif bt < opts.max_backtrack:
+                bt += 1
+                alpha_next = backtrack_alpha(alpha, a_opt)
+                retry = True
+            else:
+                lam = min(lam * GROWTH_MAX * nu, opts.lambda_max)
+                nu *= 2.0
+                streak = 0
+            status = 4 if (ftol_ok and xtol_ok) else (2 if ftol_ok else (3 if xtol_ok else 0))
+            if status:
+                done = True
+                break
+            if not retry:
+                break
+            alpha = alpha_next
+    rep.iterations, rep.status, rep.cost = it, status, cost
+    return cams, pts.reshape(-1, 3), r_true, rep
+
+
+# ---------------------------------------------------------------------------
 # Part C -- vectorised port of the reference's scipy call (timed CPU baseline)
 # ---------------------------------------------------------------------------
 

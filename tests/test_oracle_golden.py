@@ -232,3 +232,46 @@ def test_p5_oracle_lm_ends_below_the_reference_on_every_fixture():
         rep = orc.lm_solve(*s.arrays(), opts=orc.LMOptions())[3]
         assert abs(rep.cost_init - ref["cost_init"]) <= 1e-9 * ref["cost_init"]
         assert rep.cost < ref["as_shipped_cost"], (name, rep.cost, ref)
+
+
+# ---------------------------------------------------------------- 12-parameter [R|c] camera rows
+def test_p12_residuals_match_reference_fun():
+    """The restatement of ``fun`` with (Nc,12) camera rows against the reference's own outputs at two points
+    (fixture made by tests/golden/make_p12_golden.py from input_bundle_adj(rotate_model != "Rodrigues"))."""
+    q = np.load(os.path.join(GOLDEN, "toy1_lv2_p12.npz"))
+    nc = q["camera_params"].shape[0]
+    assert q["camera_params"].shape[1] == 12
+    for key in ("x0", "x1"):
+        x = q["ref_" + key]
+        r = orc.residuals12(x[:12 * nc].reshape(nc, 12), x[12 * nc:].reshape(-1, 3), q["camera_indices"], q["lines_indices"],
+                            q["n"], q["p0"], q["p1"])
+        ref = q["ref_fun_" + key]
+        assert np.all(np.abs(r - ref) <= 1e-9 * np.abs(ref) + 16 * np.finfo(float).eps * np.sqrt(np.abs(ref)))
+
+
+def test_p12_jacobian_and_solver():
+    """Analytic 12-parameter Jacobian against central differences of the restated fun; the dense LM ends below the
+    reference's own run_bundle_adjustment on the same input (recorded residual vector)."""
+    q = np.load(os.path.join(GOLDEN, "toy1_lv2_p12.npz"))
+    cams, pts = q["camera_params"], q["points_3d_raw"].astype(np.float64)
+    a = (q["camera_indices"], q["lines_indices"], q["n"], q["p0"], q["p1"])
+    r, jc, jl = orc.residuals_jacobian12(cams, pts, *a)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, len(r), 6):
+        cam, line = a[0][i], a[1][i]
+        for k in range(12):
+            h = 1e-6
+            cp = cams.copy(); cp[cam, k] += h
+            cm = cams.copy(); cm[cam, k] -= h
+            fd = (orc.residuals12(cp, pts, *a)[i] - orc.residuals12(cm, pts, *a)[i]) / (2 * h)
+            assert abs(fd - jc[i, k]) <= 1e-6 * max(1.0, np.abs(jc).max())
+        for k in range(6):
+            h = 1e-6
+            pp = pts.copy().reshape(-1, 6); pp[line, k] += h
+            pm = pts.copy().reshape(-1, 6); pm[line, k] -= h
+            fd = (orc.residuals12(cams, pp, *a)[i] - orc.residuals12(cams, pm, *a)[i]) / (2 * h)
+            assert abs(fd - jl[i, k]) <= 1e-6 * max(1.0, np.abs(jl).max())
+    out = orc.lm_solve12(cams, pts, *a, opts=orc.LMOptions(max_iter=15))
+    ref_cost = 0.5 * float(np.sum(q["ref_ba_residual"] ** 2))
+    assert out[3].cost < ref_cost
+    assert out[0].shape == (3, 12)
