@@ -122,7 +122,7 @@ struct lba_ctx {
   int grid_eval_j = 1, grid_eval_r = 1, grid_lp[3] = {1, 1, 1};
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
   bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
-  int eval_stages_j = 3, eval_stages_r = 3, eval_stg_bufs = 1;
+  int eval_stages_j = 3, eval_stages_r = 3;
 
   // state
   DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
@@ -900,31 +900,31 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       if (dbg) fprintf(stderr, "[lba_set_problem] fits? threads %d smem %d -> %d block(s)/SM\n", threads, smem, nb);
       return nb >= 1;
     };
-    // preferred: 2 sub-groups per CTA sharing a shared-memory camera table (1 CTA / SM), with two
-    // staging buffers (one barrier per tile) when shared memory allows
+    // preferred: 2 sub-groups per CTA sharing a shared-memory camera table (1 CTA / SM).  Two pipeline stages per
+    // sub-group: a third fits (the staging rows live inside the stages) but measured 2.5 % SLOWER on config 4
+    // (138.7 vs 135.3 us) -- the mbarrier wait of this kernel is not load latency, and the extra 45 KB of shared
+    // memory come out of the L1 that serves its scattered stores; LBA_EVAL_STAGES=3|4 selects them anyway.
     ctx->eval_tab_smem = false;
-    ctx->eval_stg_bufs = 1;
-    const bool tab_r = nc > 0 && fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, false, 2, 2, nc, 1));
-    if (tab_r && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, true, 2, 2, nc, 2))) {
-      ctx->eval_tab_smem = true; ctx->eval_stg_bufs = 2;
-    } else if (tab_r && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, true, 2, 2, nc, 1))) {
+    int sj = 0, smax = 0;
+    for (int st : {4, 3, 2})
+      if (nc > 0 && !smax && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc)) &&
+          fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc))) smax = st;
+    if (smax) sj = 2;
+    if (const char* e = getenv("LBA_EVAL_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= smax) sj = v; }
+    if (sj) {
       ctx->eval_tab_smem = true;
-    }
-    if (ctx->eval_tab_smem) {
-      ctx->eval_stages_j = 2;
-      ctx->eval_stages_r = fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, false, 3, 2, nc, 1)) ? 3 : 2;
-      ctx->smem_eval_j = eval_smem_bytes(lmax, true, ctx->eval_stages_j, 2, nc, ctx->eval_stg_bufs);
-      ctx->smem_eval_r = eval_smem_bytes(lmax, false, ctx->eval_stages_r, 2, nc, 1);
+      ctx->eval_stages_j = ctx->eval_stages_r = sj;
+      ctx->smem_eval_j = ctx->smem_eval_r = eval_smem_bytes(lmax, sj, 2, nc);
       CKR(plan(k_eval<true, 2, true>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 2, true>, 2 * kTile, ctx->smem_eval_r, 2, &ctx->grid_eval_r));
     } else {
       ctx->eval_stages_j = ctx->eval_stages_r = 3;
-      ctx->eval_stg_bufs = 2;
-      ctx->smem_eval_j = eval_smem_bytes(lmax, true, 3, 1, 0, 2);
-      ctx->smem_eval_r = eval_smem_bytes(lmax, false, 3, 1, 0, 1);
+      ctx->smem_eval_j = ctx->smem_eval_r = eval_smem_bytes(lmax, 3, 1, 0);
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
+    if (dbg) fprintf(stderr, "[lba_set_problem] evaluation kernel: %s, %d stages, %d B shared memory\n",
+                     ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_stages_j, ctx->smem_eval_j);
     {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
        // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
        // they get narrow CTAs (measured, accumulate + finish: 1000 cameras x 2000 obs 31 us at 64 threads vs 35 at 128;
@@ -991,7 +991,7 @@ static inline double* bpart_of(lba_ctx* c) { return c->Mpart.p + (size_t)c->nc *
 // pick one from the device control block, or set `which` when no LM solve is running (ctl == NULL).
 static EvalArgs eval_args(lba_ctx* c, const LmCtl* ctl, int which) {
   EvalArgs a;
-  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3; a.stg_bufs = 1;
+  a.Mp = c->Mp; a.ntiles = c->ntiles; a.lmax = c->lmax; a.nc = c->nc; a.nstages = 3;
   a.tidx = c->tidx.p; a.cst = c->cst.p;
   a.recs = dual<const CamRec>(c->recs.p, c->recs_new.p);
   a.pts = dual<const double>(c->pts.p, c->pts_new.p);
@@ -1049,7 +1049,6 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
   if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, ctl, which);
     a.nstages = c->eval_stages_j;
-    a.stg_bufs = c->eval_stg_bufs;
     if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
     if (c->n_long > 0)   // lines with more than kTile observations: add up their fragments' blocks

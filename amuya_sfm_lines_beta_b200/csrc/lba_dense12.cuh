@@ -18,7 +18,7 @@ namespace lba {
 struct Eval12Args {
   int Mp, ntiles, nc, nl;
   const TileIdx* tidx;
-  const double* cst;      // [ntiles][9][256]: n, m0 = n x p0, m1 = n x p1
+  const double* cst;      // [ntiles][256][9]: n, m0 = n x p0, m1 = n x p1 per slot
   const double* x;        // [12 nc + 6 nl]: camera rows (3x4 row-major), then [X0, X1] per line
   double* r;              // [Mp]
   double* jc;             // [Mp][12] in the row layout of the camera parameters (NULL: residuals only)
@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(kTile) k_eval12(const Eval12Args a) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) jl[k] = 0.0;
   if (cam >= 0) {
-    const double* cst = a.cst + (size_t)tile * 9 * kTile;
+    const double* cst = a.cst + ((size_t)tile * kTile + t) * 9;
     double n[3], m[2][3], M[9], c[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { n[k] = cst[k * kTile + t]; m[0][k] = cst[(3 + k) * kTile + t]; m[1][k] = cst[(6 + k) * kTile + t]; }
+    for (int k = 0; k < 3; ++k) { n[k] = cst[k]; m[0][k] = cst[3 + k]; m[1][k] = cst[6 + k]; }
     const double* cp = a.x + (size_t)cam * 12;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { M[3 * k] = cp[4 * k]; M[3 * k + 1] = cp[4 * k + 1]; M[3 * k + 2] = cp[4 * k + 2]; c[k] = cp[4 * k + 3]; }

@@ -69,7 +69,11 @@ __device__ __forceinline__ double endpoint_term(const double R[9], const double 
   const double x1 = R[3] * d0 + R[4] * d1 + R[5] * d2;
   const double x2 = R[6] * d0 + R[7] * d1 + R[8] * d2;
   const double rho2 = x0 * x0 + x1 * x1 + x2 * x2;
+#ifdef __CUDA_ARCH__
+  const double inv_rho = rsqrt(rho2);   // one reciprocal-square-root sequence (1 ulp) instead of a square root and a division
+#else
   const double inv_rho = 1.0 / sqrt(rho2);
+#endif
   const double q0 = x0 * inv_rho, q1 = x1 * inv_rho, q2 = x2 * inv_rho;
   const double a = q0 * n[0] + q1 * n[1] + q2 * n[2];
   const double b = q0 * me[0] + q1 * me[1] + q2 * me[2];

@@ -8,7 +8,9 @@
 //   per-observation data are packed TILE-MAJOR so that everything one kernel needs of a tile is
 //   a handful of contiguous, 16 B-aligned blocks, each moved by ONE bulk-async copy (TMA,
 //   cp.async.bulk):
-//     cst[ntiles][9][256] = n, m0 = n x p0, m1 = n x p1 (18 KB per tile);  jl[ntiles][6][256]
+//     cst[ntiles][256][9] = per slot n, m0 = n x p0, m1 = n x p1 (18 KB per tile, one 72 B row per slot: the
+//     evaluation kernel reuses the row of a slot as its staging row once the constants are in registers);
+//     jl[ntiles][6][256]
 //     (12 KB per tile);  TileIdx[ntiles] = {line table, local line id, camera, camera-order
 //     position} (2.5 KB per tile);  r, w, wk, wr: [Mp] (2 KB per tile)
 // CAMERA ORDER (stable counting sort of the same observations by camera), dense m entries:
@@ -300,7 +302,7 @@ __device__ __forceinline__ double peer_sum(const PeerLink& pl, size_t e) {
 // setup kernels
 // ---------------------------------------------------------------------------------
 
-// AoS (m,3) n/p0/p1 in caller order -> SoA cst[9][Mp] in slot order, with m_e = n x p_e
+// AoS (m,3) n/p0/p1 in caller order -> cst[Mp][9] rows in slot order, with m_e = n x p_e
 // (np.cross at bundle_adjustment.py:126,133, hoisted out of the evaluation loop).
 __global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, const double* __restrict__ n,
                                   const double* __restrict__ p0, const double* __restrict__ p1,
@@ -309,19 +311,19 @@ __global__ void k_setup_constants(int Mp, const int* __restrict__ slot_src, cons
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mp) return;
   const int src = slot_src[i];
-  double* o = cst + tm_index(9, 0, (size_t)i);   // rows of this slot are kTile apart
+  double* o = cst + (size_t)i * 9;
   if (src < 0) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) o[k * kTile] = 0.0;
+    for (int k = 0; k < 9; ++k) o[k] = 0.0;
     return;
   }
   const size_t s = (size_t)src;
   const double nx = n[3 * s], ny = n[3 * s + 1], nz = n[3 * s + 2];
   const double ax = p0[3 * s], ay = p0[3 * s + 1], az = p0[3 * s + 2];
   const double bx = p1[3 * s], by = p1[3 * s + 1], bz = p1[3 * s + 2];
-  o[0 * kTile] = nx; o[1 * kTile] = ny; o[2 * kTile] = nz;
-  o[3 * kTile] = ny * az - nz * ay; o[4 * kTile] = nz * ax - nx * az; o[5 * kTile] = nx * ay - ny * ax;
-  o[6 * kTile] = ny * bz - nz * by; o[7 * kTile] = nz * bx - nx * bz; o[8 * kTile] = nx * by - ny * bx;
+  o[0] = nx; o[1] = ny; o[2] = nz;
+  o[3] = ny * az - nz * ay; o[4] = nz * ax - nx * az; o[5] = nx * ay - ny * ax;
+  o[6] = ny * bz - nz * by; o[7] = nz * bx - nx * bz; o[8] = nx * by - ny * bx;
 }
 
 // (Nc,6) interleaved [w0,c0,w1,c1,w2,c2] <-> internal [w,c]
@@ -447,9 +449,8 @@ __global__ void k_point_wise_indices(int Mp, const int* __restrict__ slot_src, c
 struct EvalArgs {
   int Mp, ntiles, lmax;    // lmax: max lines per tile rounded up to 8 (sizes the smem stage)
   int nc, nstages;         // cameras (size of the shared-memory table), pipeline depth (<= kMaxStages)
-  int stg_bufs;            // 1 or 2 staging buffers for the per-line sums (2: one barrier per tile instead of two)
   const TileIdx* tidx;     // [ntiles]
-  const double* cst;       // [ntiles][9][256]
+  const double* cst;       // [ntiles][256][9]
   // the two evaluation sets; the kernel works on set (ctl ? ctl->cur ^ which : which)
   Dual<const CamRec> recs;
   Dual<const double> pts;  // [nl][6]
@@ -484,13 +485,14 @@ __device__ __forceinline__ void sub_sync(int sub) {
 constexpr int kEvOffIdx = 9 * kTile * 8;
 constexpr int kEvOffPts = kEvOffIdx + (int)sizeof(TileIdx);
 __host__ __device__ inline int eval_stage_bytes(int lmax) { return (kEvOffPts + lmax * 48 + 127) & ~127; }
-constexpr int kEvRow = 7;  // staging row: (jl[6], r) = 56 B, an odd number of 8 B words: conflict-free per half-warp
-__host__ __device__ inline int eval_sub_bytes(int lmax, bool with_jac, int nstages, int stg_bufs) {
-  return nstages * eval_stage_bytes(lmax) + (with_jac ? stg_bufs * kTile * kEvRow * 8 : 0);
-}
+// The staging row of a slot for the per-line sums, (jl[6], r), overwrites the slot's own constants row in the stage
+// (9 doubles = 72 B: an odd number of 8 B words, conflict-free per half-warp) once the thread holds the constants in
+// registers -- no separate staging buffers, so a third pipeline stage fits beside the camera table.
+constexpr int kEvRow = 9;
+__host__ __device__ inline int eval_sub_bytes(int lmax, int nstages) { return nstages * eval_stage_bytes(lmax); }
 __host__ __device__ inline int eval_tab_bytes(int nc) { return (nc * (int)sizeof(CamRec) + 127) & ~127; }
-__host__ __device__ inline int eval_smem_bytes(int lmax, bool with_jac, int nstages, int nsub, int nc_tab, int stg_bufs) {
-  return eval_tab_bytes(nc_tab) + nsub * eval_sub_bytes(lmax, with_jac, nstages, stg_bufs) + 128;
+__host__ __device__ inline int eval_smem_bytes(int lmax, int nstages, int nsub, int nc_tab) {
+  return eval_tab_bytes(nc_tab) + nsub * eval_sub_bytes(lmax, nstages) + 128;
 }
 
 // Fused residual (+ Jacobian + per-line blocks) over the tiles.  A CTA is NSUB independent
@@ -505,12 +507,11 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   const int stage_bytes = eval_stage_bytes(a.lmax);
   const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile;
   const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
-  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, WITH_JAC, S, a.stg_bufs);
-  double* s_stg0 = reinterpret_cast<double*>(sbase + (size_t)S * stage_bytes);  // stg_bufs x [256][kEvRow], WITH_JAC only
-  // With two staging buffers the only barrier of a tile is the one between staging the rows and the
-  // per-line sums; the stage of tile it-1 is then refilled right after the barrier of tile it (every
-  // warp has passed the sums of tile it-1 by then).
-  const bool deferred = WITH_JAC && a.stg_bufs == 2;
+  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, S);
+  // With the Jacobian the only barrier of a tile is the one between staging the rows and the per-line sums; the
+  // stage of tile it-1 (its staging rows included) is refilled right after the barrier of tile it -- every warp has
+  // passed the sums of tile it-1 by then -- with tile it-1+S, which so has more than a whole tile time to land.
+  const bool deferred = WITH_JAC;
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
 
@@ -560,14 +561,14 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   for (int it = 0; it < my_n; ++it) {
     const int tile = first + it * stride;
     unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
-    const double* s_cst = reinterpret_cast<const double*>(st);
+    double* s_cst = reinterpret_cast<double*>(st);
     const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
     const int* s_cam = s_idx->cam;
     const int* s_pos = s_idx->pos;
     const unsigned char* s_ll = s_idx->ll;
     const TileMeta* s_meta = &s_idx->meta;
     const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
-    double* s_stg = s_stg0 + (deferred ? (size_t)(it & 1) * kTile * kEvRow : 0);
+    double* s_stg = s_cst;   // staging rows alias the constants rows of the same slots
     int cur_l0 = 0, cur_nl = 0;
     {  // prefetch the scalars for the issue after next
       const int nxt = deferred ? it + S : it + S + 1;
@@ -587,9 +588,9 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       double n[3], m0[3], m1[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        n[k] = s_cst[k * kTile + t];
-        m0[k] = s_cst[(3 + k) * kTile + t];
-        m1[k] = s_cst[(6 + k) * kTile + t];
+        n[k] = s_cst[t * 9 + k];
+        m0[k] = s_cst[t * 9 + 3 + k];
+        m1[k] = s_cst[t * 9 + 6 + k];
       }
       double w[3], c[3], A, B, C;
       if (TAB_SMEM) {
@@ -665,6 +666,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         double g0 = 0.0, g1 = 0.0;
         if (part == 0) {
+#pragma unroll 4
           for (int s = s0; s < s1; ++s) {
             const double* row = s_stg + s * kEvRow;
             const double x0 = row[0];
@@ -676,6 +678,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
           for (int b = 0; b < 6; ++b) Vo[b] = acc[b];
           go[0] = acc[6]; g0 = acc[6];
         } else if (part == 1) {
+#pragma unroll 4
           for (int s = s0; s < s1; ++s) {
             const double* row = s_stg + s * kEvRow;
             const double x1 = row[1];
@@ -687,6 +690,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
           for (int b = 1; b < 6; ++b) Vo[5 + b] = acc[b];   // sym_idx(1,b) = 6 + (b-1)
           go[1] = acc[6]; g0 = acc[6];
         } else if (part == 2) {
+#pragma unroll 4
           for (int s = s0; s < s1; ++s) {
             const double* row = s_stg + s * kEvRow;
             const double x2 = row[2], x3 = row[3], x4 = row[4], x5 = row[5], rr = row[6];
@@ -696,6 +700,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
           Vo[11] = acc[0]; Vo[12] = acc[1]; Vo[13] = acc[2]; Vo[14] = acc[3]; go[2] = acc[4];
           Vo[20] = acc[5]; go[5] = acc[6]; g0 = acc[4]; g1 = acc[6];
         } else {
+#pragma unroll 4
           for (int s = s0; s < s1; ++s) {
             const double* row = s_stg + s * kEvRow;
             const double x3 = row[3], x4 = row[4], x5 = row[5], rr = row[6];
