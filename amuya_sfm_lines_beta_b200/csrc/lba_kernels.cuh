@@ -737,6 +737,219 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   last_cta_reduce<kTile * NSUB, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
 }
 
+// ---- Jacobian evaluation with rotating summing warps ------------------------------------------------------------
+// Same arithmetic, same stage layout and the same outputs (bit for bit) as k_eval<true, ...>, but no warp ever waits
+// for the other warps of its sub-group.  The per-line sums V_l = sum jl jl^T, g_l = sum jl r of tile `it` belong to
+// ONE warp, warp it mod 8 (lane = line, 27 accumulators, slot order, no divergence); the other seven ARRIVE on the
+// tile's named barrier without waiting (bar.arrive) and go on to the next tile.  The owning warp takes the sums LAG
+// tiles late -- after its own rows of tile it + LAG -- when every other warp has long arrived, so its bar.sync does not
+// block either; it then refills the stage with tile it + S (it owns the TMA issue of "its" tiles).  Every warp does
+// the same work per 8 tiles (8 tiles of rows + 1 tile of sums), nobody is on a critical chain, and a stage has a
+// whole tile time to land.  (k_eval did the sums with 4 divergent work items per line on warps 0..3 of the
+// sub-group while warps 4..7 waited at the next CTA barrier: 18 % of its stall samples were that barrier.)
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int NSUB, bool TAB_SMEM>
+__global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(const EvalArgs a) {
+  constexpr int kThreads = kTile * NSUB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[kThreads / 32];
+  __shared__ uint64_t full[NSUB][kMaxStages];
+  const int S = a.nstages;
+  const int lag = S >= 3 ? 1 : 0;
+  const int stage_bytes = eval_stage_bytes(a.lmax);
+  const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5, lane = t & 31;
+  const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
+  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, S);
+  const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[sub][s], 1);
+    fence_barrier_init();
+  }
+  pdl_prologue();
+  if (ctl_skip_trial(a.ctl)) return;   // uniform over the grid
+  const int set = ctl_cur(a.ctl) ^ a.which;
+  const CamRec* g_recs = a.recs.sel(set);
+  const double* g_pts = a.pts.sel(set);
+  double* g_r = a.r.sel(set);
+  double* g_jl = a.jl.sel(set);
+  double* g_jc = a.jc.sel(set);
+  double* g_V = a.V.sel(set);
+  double* g_gl = a.gl.sel(set);
+  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : g_recs;
+  if (TAB_SMEM) {
+    const double2* src = reinterpret_cast<const double2*>(g_recs);
+    double2* dst = reinterpret_cast<double2*>(smem);
+    for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kThreads) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();
+
+  auto issue = [&](int it, int nl, int l0) {
+    const int tile = first + it * stride;
+    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    uint64_t* bar = &full[sub][it % S];
+    mbar_expect_tx(bar, 9 * kTile * 8 + (uint32_t)sizeof(TileIdx) + nl * 48);
+    bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
+    bulk_g2s(st + kEvOffIdx, a.tidx + tile, (uint32_t)sizeof(TileIdx), bar);
+    if (nl > 0) bulk_g2s(st + kEvOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
+  };
+  if (t == 0) {
+    for (int it = 0; it < S && it < my_n; ++it) {
+      const TileMeta* mt = &a.tidx[first + it * stride].meta;
+      issue(it, mt->nl, mt->l0);
+    }
+  }
+
+  double cost_acc = 0.0, gmax = 0.0;
+  // per-line blocks of tile `it` (this warp owns it), then the refill of its stage
+  auto line_sums = [&](int it) {
+    int nx_l0 = 0, nx_nl = 0;
+    const bool refill = it + S < my_n;
+    if (lane == 0 && refill) {   // (l0, nl) of the refilling tile: loaded now, used after the sums
+      const int2 v = __ldg(reinterpret_cast<const int2*>(&a.tidx[first + (it + S) * stride].meta));
+      nx_l0 = v.x; nx_nl = v.y;
+    }
+    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    const double* s_stg = reinterpret_cast<const double*>(st);
+    const TileMeta* s_meta = &reinterpret_cast<const TileIdx*>(st + kEvOffIdx)->meta;
+    named_sync(1 + sub * kMaxStages + it % S, kTile);   // every row of the tile is staged
+    const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
+    if (!frag) {
+      for (int lb = 0; lb < nlg; lb += 32) {
+        const int ll = lb + lane;
+        if (ll >= nlg) continue;
+        const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
+        double v[21], g[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) v[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] = 0.0;
+#pragma unroll 2
+        for (int s = s0; s < s1; ++s) {
+          const double* row = s_stg + s * kEvRow;
+          double x[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) x[k] = row[k];
+          const double rr = row[6];
+          int e = 0;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+#pragma unroll
+            for (int b = p; b < 6; ++b) { v[e] += x[p] * x[b]; ++e; }
+            g[p] += x[p] * rr;
+          }
+        }
+        double* Vo = g_V + (size_t)(l0 + ll) * 21;
+        double* go = g_gl + (size_t)(l0 + ll) * 6;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Vo[k] = v[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          go[k] = g[k];
+          const double ab = fabs(g[k]);
+          gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+        }
+      }
+    } else if (lane < 27) {
+      // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
+      // fragments and takes the gradient norm
+      const int s1 = s_meta->lend[0];
+      const int pa = lane < 21 ? c_sym_a[lane] : lane - 21, pb = lane < 21 ? c_sym_b[lane] : 6;
+      double acc = 0.0;
+      for (int s = 0; s < s1; ++s) acc += s_stg[s * kEvRow + pa] * s_stg[s * kEvRow + pb];
+      a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && refill) issue(it + S, nx_nl, nx_l0);
+  };
+
+  for (int it = 0; it < my_n; ++it) {
+    const int tile = first + it * stride;
+    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    double* s_cst = reinterpret_cast<double*>(st);
+    const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
+    const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
+    mbar_wait(&full[sub][it % S], (it / S) & 1);
+
+    const int cam = s_idx->cam[t];
+    const size_t i = (size_t)tile * kTile + t;
+    double r = 0.0, rho_cost = 0.0;
+    double jl[6] = {0, 0, 0, 0, 0, 0};
+    if (cam >= 0) {
+      double n[3], m0[3], m1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        n[k] = s_cst[t * 9 + k];
+        m0[k] = s_cst[t * 9 + 3 + k];
+        m1[k] = s_cst[t * 9 + 6 + k];
+      }
+      double w[3], c[3], A, B, C;
+      if (TAB_SMEM) {
+        const double2* p = reinterpret_cast<const double2*>(recs + cam);
+        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
+        A = v3.x; B = v3.y; C = v4.x;
+      } else {
+        load_camrec(recs, cam, w, c, A, B, C);
+      }
+      const double* X = s_pts + (int)s_idx->ll[t] * 6;
+      double X0[3] = {X[0], X[1], X[2]}, X1[3] = {X[3], X[4], X[5]};
+      double R[9];
+      build_R(w, A, B, R);
+      double tq[3] = {0, 0, 0};
+      const double e0 = endpoint_term<true>(R, c, X0, n, m0, jl, tq);
+      const double e1 = endpoint_term<true>(R, c, X1, n, m1, jl + 3, tq);
+      r = e0 + e1;
+      if (a.loss) {   // scipy's robust-loss scaling, as in k_eval
+        const double rs = r / a.f_scale;
+        const double z = rs * rs;
+        double r0, r1, r2;
+        robust_rho(a.loss, z, r0, r1, r2);
+        rho_cost = a.f_scale * a.f_scale * r0;
+        double js = r1 + 2.0 * r2 * z;
+        js = sqrt(js < 2.220446049250313e-16 ? 2.220446049250313e-16 : js);
+        r = r * r1 / js;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) jl[k] *= js;
+        tq[0] *= js; tq[1] *= js; tq[2] *= js;
+      } else {
+        rho_cost = r * r;
+      }
+      double G[9];
+      build_G(w, B, C, G);
+      double2* dst = reinterpret_cast<double2*>(g_jc + (size_t)s_idx->pos[t] * 6);
+      dst[0] = make_double2(G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2], G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2]);
+      dst[1] = make_double2(G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2], -(jl[0] + jl[3]));
+      dst[2] = make_double2(-(jl[1] + jl[4]), -(jl[2] + jl[5]));
+    }
+    g_r[i] = r;
+    cost_acc += rho_cost;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
+    // the slot's own constants row becomes its staging row (jl, r)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_cst[t * kEvRow + k] = jl[k];
+    s_cst[t * kEvRow + 6] = r;
+    fence_proxy_async();
+    if (warp != (it & 7)) named_arrive(1 + sub * kMaxStages + it % S, kTile);
+    if (it >= lag && warp == ((it - lag) & 7)) line_sums(it - lag);
+  }
+  if (lag && my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, gmax, o);
+    gmax = (other > gmax || other != other) ? other : gmax;
+  }
+  if (lane == 0 && gmax != 0.0) atomicMax(a.gbits.sel(set), (unsigned long long)__double_as_longlong(gmax));
+  const double cs[1] = {block_sum<kThreads>(cost_acc, red)};
+  last_cta_reduce<kThreads, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
+}
+
 // project(): p_hat rows 2i+e in the caller's observation order (API parity only; cold path)
 struct ProjectArgs {
   int Mp;
