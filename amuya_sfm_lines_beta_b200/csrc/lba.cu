@@ -123,7 +123,7 @@ struct lba_ctx {
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
   bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
   int eval_stages_j = 3, eval_stages_r = 3;
-  bool eval_ws = true;          // Jacobian evaluation by the warp-specialised kernel (k_eval_ws; LBA_EVAL_WS=0: k_eval<true>)
+  bool eval_ws = true;          // Jacobian evaluation with rotating summing warps (k_eval_ws; LBA_EVAL_WS=0: k_eval<true>, the round-1 kernel, kept for A/B runs)
 
   // state
   DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
@@ -907,8 +907,9 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     // memory come out of the L1 that serves its scattered stores; LBA_EVAL_STAGES=3|4 selects them anyway.
     ctx->eval_tab_smem = false;
     int sj = 0, smax = 0;
+    const bool no_tab = getenv("LBA_EVAL_TAB") && atoi(getenv("LBA_EVAL_TAB")) == 0;   // force the global-gather variant
     for (int st : {4, 3, 2})
-      if (nc > 0 && !smax && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc)) &&
+      if (nc > 0 && !smax && !no_tab && fits(k_eval<true, 2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc)) &&
           fits(k_eval<false, 2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc))) smax = st;
     if (smax) sj = 2;
     if (const char* e = getenv("LBA_EVAL_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= smax) sj = v; }
@@ -929,26 +930,28 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     ctx->eval_ws = !(getenv("LBA_EVAL_WS") && atoi(getenv("LBA_EVAL_WS")) == 0);
     if (ctx->eval_ws) {
       int want = 3;
-      if (const char* e = getenv("LBA_EVAL_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStages) want = v; }
+      if (const char* e = getenv("LBA_EVAL_STAGES")) { const int v = atoi(e); if (v == 2 || v == 3) want = v; }
       if (ctx->eval_tab_smem) {
-        int st = want;
-        while (st > 2 && !fits(k_eval_ws<2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc))) --st;
-        if (fits(k_eval_ws<2, true>, 2 * kTile, eval_smem_bytes(lmax, st, 2, nc))) {
-          ctx->eval_stages_j = st;
-          ctx->smem_eval_j = eval_smem_bytes(lmax, st, 2, nc);
-          CKR(plan(k_eval_ws<2, true>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
+        if (want == 3 && fits(k_eval_ws<2, true, 3>, 2 * kTile, eval_smem_bytes(lmax, 3, 2, nc))) {
+          ctx->eval_stages_j = 3;
+          ctx->smem_eval_j = eval_smem_bytes(lmax, 3, 2, nc);
+          CKR(plan(k_eval_ws<2, true, 3>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
+        } else if (fits(k_eval_ws<2, true, 2>, 2 * kTile, eval_smem_bytes(lmax, 2, 2, nc))) {
+          ctx->eval_stages_j = 2;
+          ctx->smem_eval_j = eval_smem_bytes(lmax, 2, 2, nc);
+          CKR(plan(k_eval_ws<2, true, 2>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
         } else {
           ctx->eval_ws = false;
         }
       } else {
-        ctx->eval_stages_j = want;
-        ctx->smem_eval_j = eval_smem_bytes(lmax, want, 1, 0);
-        CKR(plan(k_eval_ws<1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
+        ctx->eval_stages_j = 3;
+        ctx->smem_eval_j = eval_smem_bytes(lmax, 3, 1, 0);
+        CKR(plan(k_eval_ws<1, false, 3>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       }
     }
     if (dbg) fprintf(stderr, "[lba_set_problem] evaluation kernel: %s, %d stages, %d B shared memory\n",
                      ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_stages_j, ctx->smem_eval_j);
-    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_ws ? "warp-specialised (k_eval_ws)" : "k_eval<true>");
+    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_ws ? "k_eval_ws" : "k_eval<true>");
     {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
        // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
        // they get narrow CTAs (measured, accumulate + finish: 1000 cameras x 2000 obs 31 us at 64 threads vs 35 at 128;
@@ -1074,8 +1077,9 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
     EvalArgs a = eval_args(c, ctl, which);
     a.nstages = c->eval_stages_j;
     if (c->eval_ws) {
-      if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
-      else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
+      if (c->eval_tab_smem && c->eval_stages_j == 3) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 3>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
+      else if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 2>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
+      else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<1, false, 3>), c->grid_eval_j, kTile, c->smem_eval_j, a);
     } else if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
     if (c->n_long > 0)   // lines with more than kTile observations: add up their fragments' blocks

@@ -46,7 +46,12 @@ namespace lba {
 
 constexpr int kTile = 256;             // slots per tile == threads per line-order CTA
 constexpr int kMaxLinesPerTile = 128;
-constexpr int kLpStages = 2;    // k_line_pass pipeline depth (3 CTAs/SM)
+// k_line_pass pipeline depth (3 CTAs/SM).  The Schur-weights pass has no sums and no staging rows -- it only streams --
+// and spent half of its warp time waiting for tile data with two stages (ncu source view): it gets more.
+#ifndef LBA_LP_STAGES_SCALARS
+#define LBA_LP_STAGES_SCALARS 3
+#endif
+__host__ __device__ constexpr int lp_stages(int mode) { return mode == 2 /* kModeScalars */ ? LBA_LP_STAGES_SCALARS : 2; }
 constexpr int kVinvStride = 22;        // 21 packed entries + 1 pad -> 176 B rows (16 B aligned)
 
 struct __align__(16) TileMeta {
@@ -124,7 +129,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // global -> shared bulk copy, completion counted in bytes on `bar`; 16 B aligned, size % 16 == 0
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
@@ -741,23 +746,60 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
 // Same arithmetic, same stage layout and the same outputs (bit for bit) as k_eval<true, ...>, but no warp ever waits
 // for the other warps of its sub-group.  The per-line sums V_l = sum jl jl^T, g_l = sum jl r of tile `it` belong to
 // ONE warp, warp it mod 8 (lane = line, 27 accumulators, slot order, no divergence); the other seven ARRIVE on the
-// tile's named barrier without waiting (bar.arrive) and go on to the next tile.  The owning warp takes the sums LAG
-// tiles late -- after its own rows of tile it + LAG -- when every other warp has long arrived, so its bar.sync does not
+// tile's named barrier without waiting (bar.arrive) and go on to the next tile.  The owning warp takes the sums one
+// tile late -- after its own rows of tile it + 1 -- when every other warp has long arrived, so its bar.sync does not
 // block either; it then refills the stage with tile it + S (it owns the TMA issue of "its" tiles).  Every warp does
-// the same work per 8 tiles (8 tiles of rows + 1 tile of sums), nobody is on a critical chain, and a stage has a
-// whole tile time to land.  (k_eval did the sums with 4 divergent work items per line on warps 0..3 of the
-// sub-group while warps 4..7 waited at the next CTA barrier: 18 % of its stall samples were that barrier.)
+// the same work per 8 tiles (8 tiles of rows + 1 tile of sums) and nobody is on a critical chain.  (k_eval did the
+// sums with 4 divergent work items per line on warps 0..3 of the sub-group while warps 4..7 waited at the next CTA
+// barrier: 18 % of its stall samples were that barrier.)  Measured dead ends, config 4: the sums
+// shared by two warps; staging rows in buffers of their own with the stage refilled at the start of a tile; a fourth
+// stage without the shared-memory camera table -- all slower than this form.
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int NSUB, bool TAB_SMEM>
+// rows [P0, P1) of the upper triangle of V_l = sum jl jl^T and of g_l = sum jl r over the staged rows [s0, s1) of one
+// line (slot order, one FMA chain per sum: the same bits whichever warp takes which rows)
+template <int P0, int P1, int ROW>
+__device__ __forceinline__ void line_block_rows(const double* __restrict__ s_stg, int s0, int s1, double* __restrict__ Vo,
+                                                double* __restrict__ go, double& gmax) {
+  constexpr int NV = (P1 - P0) * 6 - (P1 * (P1 - 1) - P0 * (P0 - 1)) / 2;
+  double v[NV], g[P1 - P0];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < P1 - P0; ++q) g[q] = 0.0;
+#pragma unroll 2
+  for (int s = s0; s < s1; ++s) {
+    const double* row = s_stg + s * ROW;
+    double x[6 - P0];
+#pragma unroll
+    for (int q = 0; q < 6 - P0; ++q) x[q] = row[P0 + q];
+    const double rr = row[6];
+    int e = 0;
+#pragma unroll
+    for (int p = P0; p < P1; ++p) {
+#pragma unroll
+      for (int c = p; c < 6; ++c) { v[e] += x[p - P0] * x[c - P0]; ++e; }
+      g[p - P0] += x[p - P0] * rr;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NV; ++q) Vo[sym_idx(P0, P0) + q] = v[q];
+#pragma unroll
+  for (int q = 0; q < P1 - P0; ++q) {
+    go[P0 + q] = g[q];
+    const double ab = fabs(g[q]);
+    gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+  }
+}
+
+template <int NSUB, bool TAB_SMEM, int S>   // S: pipeline stages per sub-group (compile time: it % S, it / S are everywhere)
 __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(const EvalArgs a) {
   constexpr int kThreads = kTile * NSUB;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kThreads / 32];
   __shared__ uint64_t full[NSUB][kMaxStages];
-  const int S = a.nstages;
-  const int lag = S >= 3 ? 1 : 0;
+  constexpr int lag = S >= 3 ? 1 : 0;
   const int stage_bytes = eval_stage_bytes(a.lmax);
   const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5, lane = t & 31;
   const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
@@ -812,46 +854,20 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
       const int2 v = __ldg(reinterpret_cast<const int2*>(&a.tidx[first + (it + S) * stride].meta));
       nx_l0 = v.x; nx_nl = v.y;
     }
-    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
+    const int sidx = it % S;
+    unsigned char* st = sbase + (size_t)sidx * stage_bytes;
     const double* s_stg = reinterpret_cast<const double*>(st);
     const TileMeta* s_meta = &reinterpret_cast<const TileIdx*>(st + kEvOffIdx)->meta;
-    named_sync(1 + sub * kMaxStages + it % S, kTile);   // every row of the tile is staged
+    named_sync(1 + sub * kMaxStages + sidx, kTile);   // every row of the tile is staged
     const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
     if (!frag) {
       for (int lb = 0; lb < nlg; lb += 32) {
         const int ll = lb + lane;
         if (ll >= nlg) continue;
         const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        double v[21], g[6];
-#pragma unroll
-        for (int k = 0; k < 21; ++k) v[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) g[k] = 0.0;
-#pragma unroll 2
-        for (int s = s0; s < s1; ++s) {
-          const double* row = s_stg + s * kEvRow;
-          double x[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) x[k] = row[k];
-          const double rr = row[6];
-          int e = 0;
-#pragma unroll
-          for (int p = 0; p < 6; ++p) {
-#pragma unroll
-            for (int b = p; b < 6; ++b) { v[e] += x[p] * x[b]; ++e; }
-            g[p] += x[p] * rr;
-          }
-        }
         double* Vo = g_V + (size_t)(l0 + ll) * 21;
         double* go = g_gl + (size_t)(l0 + ll) * 6;
-#pragma unroll
-        for (int k = 0; k < 21; ++k) Vo[k] = v[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          go[k] = g[k];
-          const double ab = fabs(g[k]);
-          gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
-        }
+        line_block_rows<0, 6, kEvRow>(s_stg, s0, s1, Vo, go, gmax);
       }
     } else if (lane < 27) {
       // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
@@ -862,9 +878,11 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
       for (int s = 0; s < s1; ++s) acc += s_stg[s * kEvRow + pa] * s_stg[s * kEvRow + pb];
       a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
     }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0 && refill) issue(it + S, nx_nl, nx_l0);
+    if (refill) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) issue(it + S, nx_nl, nx_l0);
+    }
   };
 
   for (int it = 0; it < my_n; ++it) {
@@ -879,7 +897,10 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
     const size_t i = (size_t)tile * kTile + t;
     double r = 0.0, rho_cost = 0.0;
     double jl[6] = {0, 0, 0, 0, 0, 0};
+    double jw[3] = {0, 0, 0};
+    int pos = 0;
     if (cam >= 0) {
+      pos = s_idx->pos[t];
       double n[3], m0[3], m1[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -921,13 +942,18 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
       }
       double G[9];
       build_G(w, B, C, G);
-      double2* dst = reinterpret_cast<double2*>(g_jc + (size_t)s_idx->pos[t] * 6);
-      dst[0] = make_double2(G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2], G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2]);
-      dst[1] = make_double2(G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2], -(jl[0] + jl[3]));
+      jw[0] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
+      jw[1] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
+      jw[2] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
+    }
+    cost_acc += rho_cost;
+    if (cam >= 0) {   // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
+      double2* dst = reinterpret_cast<double2*>(g_jc + (size_t)pos * 6);
+      dst[0] = make_double2(jw[0], jw[1]);
+      dst[1] = make_double2(jw[2], -(jl[0] + jl[3]));
       dst[2] = make_double2(-(jl[1] + jl[4]), -(jl[2] + jl[5]));
     }
     g_r[i] = r;
-    cost_acc += rho_cost;
 #pragma unroll
     for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
     // the slot's own constants row becomes its staging row (jl, r)
@@ -1321,7 +1347,7 @@ __host__ __device__ inline int lp_stage_bytes(int lmax, int mode) {
 }
 constexpr int kLpRow = 7;  // staging row stride in doubles (6 + pad): 56 B, conflict-free per half-warp
 __host__ __device__ inline int lp_smem_bytes(int lmax, int mode) {
-  return kLpStages * lp_stage_bytes(lmax, mode) + lmax * 48 /* ul */ + (mode == kModeScalars ? 0 : kTile * kLpRow * 8) + 128;
+  return lp_stages(mode) * lp_stage_bytes(lmax, mode) + lmax * 48 /* ul */ + (mode == kModeScalars ? 0 : kTile * kLpRow * 8) + 128;
 }
 
 // Line-ordered half of S*p (MATVEC), the back-substitution (BACKSUB) and the per-observation
@@ -1332,6 +1358,7 @@ __host__ __device__ inline int lp_smem_bytes(int lmax, int mode) {
 //   SCALARS: wk_i = 1 - jl_i^T Vinv_l jl_i,  wr_i = jl_i . y_l
 template <int MODE>
 __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
+  constexpr int kLpStages = lp_stages(MODE);
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kTile / 32];
   __shared__ uint64_t full[kLpStages];
