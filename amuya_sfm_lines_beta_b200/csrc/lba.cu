@@ -123,6 +123,7 @@ struct lba_ctx {
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
   bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
   int eval_stages_j = 3, eval_stages_r = 3;
+  bool eval_z = true;           // Jacobian evaluation with the load pipeline decoupled from the per-line sums (k_eval_z; LBA_EVAL_Z=0: k_eval_ws)
   bool eval_ws = true;          // Jacobian evaluation with rotating summing warps (k_eval_ws; LBA_EVAL_WS=0: k_eval<true>, the round-1 kernel, kept for A/B runs)
 
   // state
@@ -949,9 +950,23 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
         CKR(plan(k_eval_ws<1, false, 3>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       }
     }
+    ctx->eval_z = !(getenv("LBA_EVAL_Z") && atoi(getenv("LBA_EVAL_Z")) == 0);
+    if (ctx->eval_z) {
+      if (ctx->eval_tab_smem) {
+        if (fits(k_eval_z<2, true>, 2 * kTile, eval_z_smem_bytes(lmax, 2, nc))) {
+          ctx->smem_eval_j = eval_z_smem_bytes(lmax, 2, nc);
+          CKR(plan(k_eval_z<2, true>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
+        } else {
+          ctx->eval_z = false;
+        }
+      } else {
+        ctx->smem_eval_j = eval_z_smem_bytes(lmax, 1, 0);
+        CKR(plan(k_eval_z<1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
+      }
+    }
     if (dbg) fprintf(stderr, "[lba_set_problem] evaluation kernel: %s, %d stages, %d B shared memory\n",
                      ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_stages_j, ctx->smem_eval_j);
-    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_ws ? "k_eval_ws" : "k_eval<true>");
+    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_z ? "k_eval_z" : ctx->eval_ws ? "k_eval_ws" : "k_eval<true>");
     {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
        // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
        // they get narrow CTAs (measured, accumulate + finish: 1000 cameras x 2000 obs 31 us at 64 threads vs 35 at 128;
@@ -1076,7 +1091,10 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
   if (c->ntiles > 0) {
     EvalArgs a = eval_args(c, ctl, which);
     a.nstages = c->eval_stages_j;
-    if (c->eval_ws) {
+    if (c->eval_z) {
+      if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_z<2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
+      else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_z<1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
+    } else if (c->eval_ws) {
       if (c->eval_tab_smem && c->eval_stages_j == 3) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 3>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
       else if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 2>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
       else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<1, false, 3>), c->grid_eval_j, kTile, c->smem_eval_j, a);

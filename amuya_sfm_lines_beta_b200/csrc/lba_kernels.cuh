@@ -41,6 +41,7 @@
 #include "lba_policy.cuh"
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace lba {
 
@@ -754,42 +755,38 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
 // barrier: 18 % of its stall samples were that barrier.)  Measured dead ends, config 4: the sums
 // shared by two warps; staging rows in buffers of their own with the stage refilled at the start of a tile; a fourth
 // stage without the shared-memory camera table -- all slower than this form.
+// 16 B / 32 B global stores (naturally aligned); the 256-bit form is sm_100's STG.256
+__device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// rows [P0, P1) of the upper triangle of V_l = sum jl jl^T and of g_l = sum jl r over the staged rows [s0, s1) of one
-// line (slot order, one FMA chain per sum: the same bits whichever warp takes which rows)
-template <int P0, int P1, int ROW>
-__device__ __forceinline__ void line_block_rows(const double* __restrict__ s_stg, int s0, int s1, double* __restrict__ Vo,
-                                                double* __restrict__ go, double& gmax) {
-  constexpr int NV = (P1 - P0) * 6 - (P1 * (P1 - 1) - P0 * (P0 - 1)) / 2;
-  double v[NV], g[P1 - P0];
+// upper triangle of V_l = sum jl jl^T (21) and g_l = sum jl r (6) over the staged rows [s0, s1) of one line (slot order,
+// one FMA chain per sum)
+template <int ROW>
+__device__ __forceinline__ void line_block_acc(const double* __restrict__ s_stg, int s0, int s1, double (&v)[21], double (&g)[6]) {
 #pragma unroll
-  for (int q = 0; q < NV; ++q) v[q] = 0.0;
+  for (int q = 0; q < 21; ++q) v[q] = 0.0;
 #pragma unroll
-  for (int q = 0; q < P1 - P0; ++q) g[q] = 0.0;
+  for (int q = 0; q < 6; ++q) g[q] = 0.0;
 #pragma unroll 2
   for (int s = s0; s < s1; ++s) {
     const double* row = s_stg + s * ROW;
-    double x[6 - P0];
+    double x[6];
 #pragma unroll
-    for (int q = 0; q < 6 - P0; ++q) x[q] = row[P0 + q];
+    for (int q = 0; q < 6; ++q) x[q] = row[q];
     const double rr = row[6];
     int e = 0;
 #pragma unroll
-    for (int p = P0; p < P1; ++p) {
+    for (int p = 0; p < 6; ++p) {
 #pragma unroll
-      for (int c = p; c < 6; ++c) { v[e] += x[p - P0] * x[c - P0]; ++e; }
-      g[p - P0] += x[p - P0] * rr;
+      for (int c = p; c < 6; ++c) { v[e] += x[p] * x[c]; ++e; }
+      g[p] += x[p] * rr;
     }
-  }
-#pragma unroll
-  for (int q = 0; q < NV; ++q) Vo[sym_idx(P0, P0) + q] = v[q];
-#pragma unroll
-  for (int q = 0; q < P1 - P0; ++q) {
-    go[P0 + q] = g[q];
-    const double ab = fabs(g[q]);
-    gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
   }
 }
 
@@ -798,6 +795,9 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
   constexpr int kThreads = kTile * NSUB;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kThreads / 32];
+#ifdef LBA_AB_CLOCK
+  __shared__ long long ck_issue[NSUB][kMaxStages];
+#endif
   __shared__ uint64_t full[NSUB][kMaxStages];
   constexpr int lag = S >= 3 ? 1 : 0;
   const int stage_bytes = eval_stage_bytes(a.lmax);
@@ -837,6 +837,9 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
     bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
     bulk_g2s(st + kEvOffIdx, a.tidx + tile, (uint32_t)sizeof(TileIdx), bar);
     if (nl > 0) bulk_g2s(st + kEvOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
+#ifdef LBA_AB_CLOCK
+    ck_issue[sub][it % S] = clock64();
+#endif
   };
   if (t == 0) {
     for (int it = 0; it < S && it < my_n; ++it) {
@@ -846,6 +849,10 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
   }
 
   double cost_acc = 0.0, gmax = 0.0;
+#ifdef LBA_AB_CLOCK
+  long long ck_wait = 0, ck_sums = 0, ck_nsync = 0, ck_store = 0, ck_lat = 0, ck_nlat = 0, ck_lat_all = 0, ck_acc = 0, ck_vg = 0, ck_nsums = 0;
+  const long long ck_start = clock64();
+#endif
   // per-line blocks of tile `it` (this warp owns it), then the refill of its stage
   auto line_sums = [&](int it) {
     int nx_l0 = 0, nx_nl = 0;
@@ -858,16 +865,73 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
     unsigned char* st = sbase + (size_t)sidx * stage_bytes;
     const double* s_stg = reinterpret_cast<const double*>(st);
     const TileMeta* s_meta = &reinterpret_cast<const TileIdx*>(st + kEvOffIdx)->meta;
+#ifdef LBA_AB_CLOCK
+    const long long ck0 = clock64();
+#endif
     named_sync(1 + sub * kMaxStages + sidx, kTile);   // every row of the tile is staged
+#ifdef LBA_AB_CLOCK
+    ck_nsync += clock64() - ck0;
+#endif
     const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
     if (!frag) {
       for (int lb = 0; lb < nlg; lb += 32) {
         const int ll = lb + lane;
-        if (ll >= nlg) continue;
-        const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        double* Vo = g_V + (size_t)(l0 + ll) * 21;
-        double* go = g_gl + (size_t)(l0 + ll) * 6;
-        line_block_rows<0, 6, kEvRow>(s_stg, s0, s1, Vo, go, gmax);
+        const int nb = nlg - lb < 32 ? nlg - lb : 32;
+        const bool live = ll < nlg;
+        double v[21], g[6];
+        const int s0 = live && ll ? s_meta->lend[ll - 1] : 0, s1 = live ? s_meta->lend[ll] : 0;
+#ifdef LBA_AB_CLOCK
+        const long long cka = clock64();
+#endif
+#ifndef LBA_AB_NOSUMS
+        line_block_acc<kEvRow>(s_stg, s0, s1, v, g);
+#endif
+#ifdef LBA_AB_CLOCK
+        if (v[0] == 1.2345) printf("x");
+        const long long ckb = clock64();
+        ck_acc += ckb - cka; ++ck_nsums;
+#endif
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const double ab = fabs(g[q]);
+            gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+          }
+        }
+        double* Vo = g_V + (size_t)(l0 + lb) * 21;
+        double* go = g_gl + (size_t)(l0 + lb) * 6;
+        // The 27 sums of a line sit in one lane: stored from there, every store instruction would touch one 128 B
+        // line per lane (27 x ~25 L1 wavefronts per tile, as many as the whole jc scatter).  The rows summed so far
+        // are dead, so the warp transposes through them -- lane-major records of 27 doubles (odd stride) -- and
+        // writes the batch's V_l and g_l, which are contiguous in global memory, with lane-strided stores.
+        const int rows_done = s_meta->lend[lb + nb - 1];
+        if (3 * nb <= rows_done) {   // 27 doubles per line fit in the 9-double rows below the next batch's first row
+          double* stg = const_cast<double*>(s_stg);
+          __syncwarp();
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 21; ++q) stg[lane * 27 + q] = v[q];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) stg[lane * 27 + 21 + q] = g[q];
+          }
+          __syncwarp();
+          for (int e = lane; e < nb * 21; e += 32) {
+            const int li = e / 21;
+            Vo[e] = stg[li * 27 + (e - li * 21)];
+          }
+          for (int e = lane; e < nb * 6; e += 32) {
+            const int li = e / 6;
+            go[e] = stg[li * 27 + 21 + (e - li * 6)];
+          }
+        } else if (live) {   // lines of one or two observations: straight from the registers
+#pragma unroll
+          for (int q = 0; q < 21; ++q) Vo[lane * 21 + q] = v[q];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) go[lane * 6 + q] = g[q];
+        }
+#ifdef LBA_AB_CLOCK
+        ck_vg += clock64() - ckb;
+#endif
       }
     } else if (lane < 27) {
       // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
@@ -883,6 +947,9 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
       __syncwarp();
       if (lane == 0) issue(it + S, nx_nl, nx_l0);
     }
+#ifdef LBA_AB_CLOCK
+    ck_sums += clock64() - ck0;
+#endif
   };
 
   for (int it = 0; it < my_n; ++it) {
@@ -891,7 +958,18 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
     double* s_cst = reinterpret_cast<double*>(st);
     const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
     const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
+#ifdef LBA_AB_CLOCK
+    const long long ckw = clock64();
+#endif
     mbar_wait(&full[sub][it % S], (it / S) & 1);
+#ifdef LBA_AB_CLOCK
+    {
+      const long long now = clock64();
+      ck_wait += now - ckw;
+      ck_lat_all += now - ck_issue[sub][it % S];
+      if (now - ckw > 200) { ck_lat += now - ck_issue[sub][it % S]; ++ck_nlat; }
+    }
+#endif
 
     const int cam = s_idx->cam[t];
     const size_t i = (size_t)tile * kTile + t;
@@ -919,6 +997,307 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
       }
       const double* X = s_pts + (int)s_idx->ll[t] * 6;
       double X0[3] = {X[0], X[1], X[2]}, X1[3] = {X[3], X[4], X[5]};
+#ifdef LBA_AB_NOMATH
+      double tq[3] = {w[0] + c[0], w[1] + c[1], w[2] + c[2] + A + B + C};
+      jl[0] = X0[0] + n[0]; jl[1] = X0[1] + n[1]; jl[2] = X0[2] + n[2]; jl[3] = X1[0] + m0[0]; jl[4] = X1[1] + m0[1]; jl[5] = X1[2] + m0[2];
+      r = m1[0] + m1[1] + m1[2];
+      jw[0] = tq[0]; jw[1] = tq[1]; jw[2] = tq[2];
+      rho_cost = r * r;
+#else
+      double R[9];
+      build_R(w, A, B, R);
+      double tq[3] = {0, 0, 0};
+      const double e0 = endpoint_term<true>(R, c, X0, n, m0, jl, tq);
+      const double e1 = endpoint_term<true>(R, c, X1, n, m1, jl + 3, tq);
+      r = e0 + e1;
+      if (a.loss) {   // scipy's robust-loss scaling, as in k_eval
+        const double rs = r / a.f_scale;
+        const double z = rs * rs;
+        double r0, r1, r2;
+        robust_rho(a.loss, z, r0, r1, r2);
+        rho_cost = a.f_scale * a.f_scale * r0;
+        double js = r1 + 2.0 * r2 * z;
+        js = sqrt(js < 2.220446049250313e-16 ? 2.220446049250313e-16 : js);
+        r = r * r1 / js;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) jl[k] *= js;
+        tq[0] *= js; tq[1] *= js; tq[2] *= js;
+      } else {
+        rho_cost = r * r;
+      }
+      double G[9];
+      build_G(w, B, C, G);
+      jw[0] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
+      jw[1] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
+      jw[2] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
+#endif
+    }
+    cost_acc += rho_cost;
+#ifdef LBA_AB_CLOCK
+    const long long cks = clock64();
+#endif
+#ifndef LBA_AB_NOJC
+    if (cam >= 0) {   // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
+      // 48 B records: an even position starts a 32 B sector, an odd one ends one -- one 32 B and one 16 B store, both
+      // naturally aligned (two scattered store instructions per warp instead of three)
+      const double c0 = -(jl[0] + jl[3]), c1 = -(jl[1] + jl[4]), c2 = -(jl[2] + jl[5]);
+      double* dst = g_jc + (size_t)pos * 6;
+      const bool odd = pos & 1;
+      st_global_v2(dst + (odd ? 0 : 4), odd ? jw[0] : c1, odd ? jw[1] : c2);
+      st_global_v4(dst + (odd ? 2 : 0), odd ? jw[2] : jw[0], odd ? c0 : jw[1], odd ? c1 : jw[2], odd ? c2 : c0);
+    }
+#else
+    cost_acc += jw[0] + jw[1] + jw[2] + pos;
+#endif
+    g_r[i] = r;
+#ifndef LBA_AB_NOJL
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
+#endif
+    // the slot's own constants row becomes its staging row (jl, r)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_cst[t * kEvRow + k] = jl[k];
+    s_cst[t * kEvRow + 6] = r;
+    fence_proxy_async();
+    if (warp != (it & 7)) named_arrive(1 + sub * kMaxStages + it % S, kTile);
+#ifdef LBA_AB_CLOCK
+    ck_store += clock64() - cks;
+#endif
+    if (it >= lag && warp == ((it - lag) & 7)) line_sums(it - lag);
+  }
+  if (lag && my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
+#ifdef LBA_AB_CLOCK
+  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("cta %d sub %d warp %d tiles %d: total %lld  wait %lld  store %lld  sums %lld (named_sync %lld)  waited %lld times, issue->ready then %lld; issue->use avg %lld\n", blockIdx.x, sub, warp, my_n,
+           clock64() - ck_start, ck_wait, ck_store, ck_sums, ck_nsync, ck_nlat, ck_nlat ? ck_lat / ck_nlat : 0, ck_lat_all / (my_n ? my_n : 1)),
+    printf("      sums calls %lld: accumulate %lld, V/g out %lld per call\n", ck_nsums, ck_acc / (ck_nsums ? ck_nsums : 1), ck_vg / (ck_nsums ? ck_nsums : 1));
+#endif
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, gmax, o);
+    gmax = (other > gmax || other != other) ? other : gmax;
+  }
+  if (lane == 0 && gmax != 0.0) atomicMax(a.gbits.sel(set), (unsigned long long)__double_as_longlong(gmax));
+  const double cs[1] = {block_sum<kThreads>(cost_acc, red)};
+  last_cta_reduce<kThreads, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_eval_z: the Jacobian evaluation with the load pipeline decoupled from the per-line sums.
+//
+// Clock counters in k_eval_ws (config 4) showed where its time went: 39 % of every warp's cycles waiting for tile data,
+// although a bulk load takes only ~3000 cycles from issue to arrival.  There the staging rows of the per-line sums live
+// INSIDE the load stage, so a stage is refilled only after the owning warp has finished its rows of the NEXT tile and
+// then the sums of this one (~5000 cycles on one warp): arrival of tile k+2 = arrival of tile k + rows + sums + load,
+// whatever the number of stages.  Here a stage is dead as soon as every warp holds its slot's constants in registers
+// -- a few hundred cycles after the tile has arrived -- and is refilled right then (seven warps bar.arrive, a rotating
+// issuer warp bar.syncs and issues the bulk copies of tile k+2): two stages suffice.  The staging rows (jl, r: 56 B per
+// slot) have two buffers of their own; the sums of tile k are still taken one tile late by warp k mod 8, which then
+// releases the buffer through an mbarrier that the writers of tile k+2 wait on (passed long before in steady state).
+// The tile's line table is copied into a small ring next to the staging buffers before the stage is refilled.
+// Same arithmetic and the same order of every sum as k_eval_ws / k_eval<true>: the outputs are bit-identical.
+constexpr int kEzRow = 7;        // staging row (jl[6], r): 56 B, an odd number of 8 B words
+constexpr int kEzMetaRing = 4;   // line tables of the last four tiles
+__host__ __device__ inline int eval_z_stg_bytes() { return kTile * kEzRow * 8; }
+__host__ __device__ inline int eval_z_sub_bytes(int lmax) {
+  return 2 * eval_stage_bytes(lmax) + 2 * eval_z_stg_bytes() + ((kEzMetaRing * (int)sizeof(TileMeta) + 127) & ~127);
+}
+__host__ __device__ inline int eval_z_smem_bytes(int lmax, int nsub, int nc_tab) {
+  return eval_tab_bytes(nc_tab) + nsub * eval_z_sub_bytes(lmax) + 128;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NSUB, bool TAB_SMEM>
+__global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const EvalArgs a) {
+  constexpr int kThreads = kTile * NSUB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[kThreads / 32];
+  __shared__ uint64_t full[NSUB][2], sfree[NSUB][2];
+  const int stage_bytes = eval_stage_bytes(a.lmax);
+  const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5, lane = t & 31;
+  const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
+  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_z_sub_bytes(a.lmax);
+  unsigned char* gbase = sbase + 2 * stage_bytes;                       // two staging buffers
+  TileMeta* mring = reinterpret_cast<TileMeta*>(gbase + 2 * eval_z_stg_bytes());
+  const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  // named barriers of the sub-group: 1 + 4 sub + s: stage s consumed;  1 + 4 sub + 2 + b: rows of staging buffer b staged
+  const int bar0 = 1 + sub * 4;
+
+  if (t == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[sub][s], 1); mbar_init(&sfree[sub][s], 1); }
+    fence_barrier_init();
+  }
+  pdl_prologue();
+  if (ctl_skip_trial(a.ctl)) return;   // uniform over the grid
+  const int set = ctl_cur(a.ctl) ^ a.which;
+  const CamRec* g_recs = a.recs.sel(set);
+  const double* g_pts = a.pts.sel(set);
+  double* g_r = a.r.sel(set);
+  double* g_jl = a.jl.sel(set);
+  double* g_jc = a.jc.sel(set);
+  double* g_V = a.V.sel(set);
+  double* g_gl = a.gl.sel(set);
+  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : g_recs;
+  if (TAB_SMEM) {
+    const double2* src = reinterpret_cast<const double2*>(g_recs);
+    double2* dst = reinterpret_cast<double2*>(smem);
+    for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kThreads) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();
+
+  auto issue = [&](int it, int nl, int l0) {
+    const int tile = first + it * stride;
+    unsigned char* st = sbase + (size_t)(it & 1) * stage_bytes;
+    uint64_t* bar = &full[sub][it & 1];
+    mbar_expect_tx(bar, 9 * kTile * 8 + (uint32_t)sizeof(TileIdx) + nl * 48);
+    bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
+    bulk_g2s(st + kEvOffIdx, a.tidx + tile, (uint32_t)sizeof(TileIdx), bar);
+    if (nl > 0) bulk_g2s(st + kEvOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
+  };
+  if (t == 0) {
+    for (int it = 0; it < 2 && it < my_n; ++it) {
+      const TileMeta* mt = &a.tidx[first + it * stride].meta;
+      issue(it, mt->nl, mt->l0);
+    }
+  }
+
+  double cost_acc = 0.0, gmax = 0.0;
+  // per-line blocks of tile `it` (this warp owns it) from its staging buffer, which is then released
+  auto line_sums = [&](int it) {
+    const int b = it & 1;
+    double* stg = reinterpret_cast<double*>(gbase + (size_t)b * eval_z_stg_bytes());
+    const TileMeta* s_meta = mring + (it & (kEzMetaRing - 1));
+    named_sync(bar0 + 2 + b, kTile);   // every row of the tile is staged (and its line table is in the ring)
+    const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
+    if (!frag) {
+      for (int lb = 0; lb < nlg; lb += 32) {
+        const int ll = lb + lane;
+        const int nb = nlg - lb < 32 ? nlg - lb : 32;
+        const bool live = ll < nlg;
+        double v[21], g[6];
+        const int s0 = live && ll ? s_meta->lend[ll - 1] : 0, s1 = live ? s_meta->lend[ll] : 0;
+        line_block_acc<kEzRow>(stg, s0, s1, v, g);
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const double ab = fabs(g[q]);
+            gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+          }
+        }
+        double* Vo = g_V + (size_t)(l0 + lb) * 21;
+        double* go = g_gl + (size_t)(l0 + lb) * 6;
+        // The 27 sums of a line sit in one lane; stored from there every instruction would touch one 128 B line per
+        // lane.  The rows summed so far are dead: the warp transposes through them (lane-major records of 27 doubles,
+        // an odd stride) and writes the batch's V_l and g_l, contiguous in global memory, with lane-strided stores.
+        const int rows_done = s_meta->lend[lb + nb - 1];
+        if (27 * nb <= kEzRow * rows_done) {
+          __syncwarp();
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 21; ++q) stg[lane * 27 + q] = v[q];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) stg[lane * 27 + 21 + q] = g[q];
+          }
+          __syncwarp();
+          const int nv = nb * 21, ng = nb * 6;
+#pragma unroll 4
+          for (int e = lane; e < nv; e += 32) {
+            const int li = e / 21;
+            Vo[e] = stg[e + li * 6];
+          }
+#pragma unroll 2
+          for (int e = lane; e < ng; e += 32) {
+            const int li = e / 6;
+            go[e] = stg[e + li * 21 + 21];
+          }
+        } else if (live) {   // lines of one to three observations: straight from the registers
+#pragma unroll
+          for (int q = 0; q < 21; ++q) Vo[lane * 21 + q] = v[q];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) go[lane * 6 + q] = g[q];
+        }
+      }
+    } else if (lane < 27) {
+      // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
+      // fragments and takes the gradient norm
+      const int s1 = s_meta->lend[0];
+      const int pa = lane < 21 ? c_sym_a[lane] : lane - 21, pb = lane < 21 ? c_sym_b[lane] : 6;
+      double acc = 0.0;
+      for (int s = 0; s < s1; ++s) acc += stg[s * kEzRow + pa] * stg[s * kEzRow + pb];
+      a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sfree[sub][b]);   // the buffer may take the rows of tile it + 2
+  };
+
+  int nx_l0 = 0, nx_nl = 0;   // (l0, nl) of the tile this warp will issue next (lane 0)
+  if (lane == 0 && warp == 4 && 2 < my_n) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(&a.tidx[first + 2 * stride].meta));
+    nx_l0 = v.x; nx_nl = v.y;
+  }
+  for (int it = 0; it < my_n; ++it) {
+    const int tile = first + it * stride;
+    const int s = it & 1;
+    unsigned char* st = sbase + (size_t)s * stage_bytes;
+    const double* s_cst = reinterpret_cast<const double*>(st);
+    const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
+    const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
+    double* stg = reinterpret_cast<double*>(gbase + (size_t)s * eval_z_stg_bytes());
+    // the issuer of the NEXT iteration fetches what its bulk copies need now
+    if (lane == 0 && warp == ((it + 5) & 7) && it + 3 < my_n) {
+      const int2 v = __ldg(reinterpret_cast<const int2*>(&a.tidx[first + (it + 3) * stride].meta));
+      nx_l0 = v.x; nx_nl = v.y;
+    }
+    mbar_wait(&full[sub][s], (it >> 1) & 1);
+
+    // everything this slot needs of the stage, into registers
+    const int cam = s_idx->cam[t];
+    const size_t i = (size_t)tile * kTile + t;
+    int pos = 0;
+    double n[3] = {0, 0, 0}, m0[3] = {0, 0, 0}, m1[3] = {0, 0, 0}, X0[3] = {0, 0, 0}, X1[3] = {0, 0, 0};
+    if (cam >= 0) {
+      pos = s_idx->pos[t];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        n[k] = s_cst[t * 9 + k];
+        m0[k] = s_cst[t * 9 + 3 + k];
+        m1[k] = s_cst[t * 9 + 6 + k];
+      }
+      const double* X = s_pts + (int)s_idx->ll[t] * 6;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { X0[k] = X[k]; X1[k] = X[3 + k]; }
+    }
+    if (warp == ((it + 4) & 7)) {
+      // issuer: when all eight warps hold their constants, keep the line table and refill the stage with tile it + 2
+      named_sync(bar0 + s, kTile);
+      if (lane < (int)(sizeof(TileMeta) / 16))
+        reinterpret_cast<int4*>(mring + (it & (kEzMetaRing - 1)))[lane] = reinterpret_cast<const int4*>(&s_idx->meta)[lane];
+      if (it + 2 < my_n) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) issue(it + 2, nx_nl, nx_l0);
+      }
+    } else {
+      named_arrive(bar0 + s, kTile);
+    }
+
+    double r = 0.0, rho_cost = 0.0;
+    double jl[6] = {0, 0, 0, 0, 0, 0};
+    double jw[3] = {0, 0, 0};
+    if (cam >= 0) {
+      double w[3], c[3], A, B, C;
+      if (TAB_SMEM) {
+        const double2* p = reinterpret_cast<const double2*>(recs + cam);
+        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
+        A = v3.x; B = v3.y; C = v4.x;
+      } else {
+        load_camrec(recs, cam, w, c, A, B, C);
+      }
       double R[9];
       build_R(w, A, B, R);
       double tq[3] = {0, 0, 0};
@@ -948,23 +1327,25 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(cons
     }
     cost_acc += rho_cost;
     if (cam >= 0) {   // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
-      double2* dst = reinterpret_cast<double2*>(g_jc + (size_t)pos * 6);
-      dst[0] = make_double2(jw[0], jw[1]);
-      dst[1] = make_double2(jw[2], -(jl[0] + jl[3]));
-      dst[2] = make_double2(-(jl[1] + jl[4]), -(jl[2] + jl[5]));
+      // an even position starts a 32 B sector, an odd one ends one: one 32 B and one 16 B store, both naturally aligned
+      const double c0 = -(jl[0] + jl[3]), c1 = -(jl[1] + jl[4]), c2 = -(jl[2] + jl[5]);
+      double* dst = g_jc + (size_t)pos * 6;
+      const bool odd = pos & 1;
+      st_global_v2(dst + (odd ? 0 : 4), odd ? jw[0] : c1, odd ? jw[1] : c2);
+      st_global_v4(dst + (odd ? 2 : 0), odd ? jw[2] : jw[0], odd ? c0 : jw[1], odd ? c1 : jw[2], odd ? c2 : c0);
     }
     g_r[i] = r;
 #pragma unroll
     for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
-    // the slot's own constants row becomes its staging row (jl, r)
+    // staging rows: the buffer was last read by the sums of tile it - 2
+    if (it >= 2) mbar_wait(&sfree[sub][s], ((it >> 1) - 1) & 1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s_cst[t * kEvRow + k] = jl[k];
-    s_cst[t * kEvRow + 6] = r;
-    fence_proxy_async();
-    if (warp != (it & 7)) named_arrive(1 + sub * kMaxStages + it % S, kTile);
-    if (it >= lag && warp == ((it - lag) & 7)) line_sums(it - lag);
+    for (int k = 0; k < 6; ++k) stg[t * kEzRow + k] = jl[k];
+    stg[t * kEzRow + 6] = r;
+    if (warp != (it & 7)) named_arrive(bar0 + 2 + s, kTile);
+    if (it >= 1 && warp == ((it - 1) & 7)) line_sums(it - 1);
   }
-  if (lag && my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
+  if (my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
