@@ -123,8 +123,7 @@ struct lba_ctx {
   int smem_eval_j = 0, smem_eval_r = 0, smem_lp[3] = {0, 0, 0};
   bool eval_tab_smem = false;   // camera table resident in shared memory (fits up to ~1.3k cameras)
   int eval_stages_j = 3, eval_stages_r = 3;
-  bool eval_z = true;           // Jacobian evaluation with the load pipeline decoupled from the per-line sums (k_eval_z; LBA_EVAL_Z=0: k_eval_ws)
-  bool eval_ws = true;          // Jacobian evaluation with rotating summing warps (k_eval_ws; LBA_EVAL_WS=0: k_eval<true>, the round-1 kernel, kept for A/B runs)
+  bool eval_z = true;           // Jacobian evaluation with the load pipeline decoupled from the per-line sums (k_eval_z; LBA_EVAL_Z=0: k_eval<true>, the round-1 kernel, kept for A/B runs)
 
   // state
   DBuf<double> cams, cams_new, pts, pts_new, Gm, Gm_new, api_tmp;
@@ -926,30 +925,6 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       CKR(plan(k_eval<true, 1, false>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
       CKR(plan(k_eval<false, 1, false>, kTile, ctx->smem_eval_r, 1, &ctx->grid_eval_r));
     }
-    // The Jacobian evaluation runs warp-specialised by default (k_eval_ws: the sub-groups never wait at a CTA
-    // barrier, so stages ahead of them pay off: three per sub-group when they fit beside the camera table).
-    ctx->eval_ws = !(getenv("LBA_EVAL_WS") && atoi(getenv("LBA_EVAL_WS")) == 0);
-    if (ctx->eval_ws) {
-      int want = 3;
-      if (const char* e = getenv("LBA_EVAL_STAGES")) { const int v = atoi(e); if (v == 2 || v == 3) want = v; }
-      if (ctx->eval_tab_smem) {
-        if (want == 3 && fits(k_eval_ws<2, true, 3>, 2 * kTile, eval_smem_bytes(lmax, 3, 2, nc))) {
-          ctx->eval_stages_j = 3;
-          ctx->smem_eval_j = eval_smem_bytes(lmax, 3, 2, nc);
-          CKR(plan(k_eval_ws<2, true, 3>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
-        } else if (fits(k_eval_ws<2, true, 2>, 2 * kTile, eval_smem_bytes(lmax, 2, 2, nc))) {
-          ctx->eval_stages_j = 2;
-          ctx->smem_eval_j = eval_smem_bytes(lmax, 2, 2, nc);
-          CKR(plan(k_eval_ws<2, true, 2>, 2 * kTile, ctx->smem_eval_j, 2, &ctx->grid_eval_j));
-        } else {
-          ctx->eval_ws = false;
-        }
-      } else {
-        ctx->eval_stages_j = 3;
-        ctx->smem_eval_j = eval_smem_bytes(lmax, 3, 1, 0);
-        CKR(plan(k_eval_ws<1, false, 3>, kTile, ctx->smem_eval_j, 1, &ctx->grid_eval_j));
-      }
-    }
     ctx->eval_z = !(getenv("LBA_EVAL_Z") && atoi(getenv("LBA_EVAL_Z")) == 0);
     if (ctx->eval_z) {
       if (ctx->eval_tab_smem) {
@@ -966,7 +941,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
     }
     if (dbg) fprintf(stderr, "[lba_set_problem] evaluation kernel: %s, %d stages, %d B shared memory\n",
                      ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_stages_j, ctx->smem_eval_j);
-    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_z ? "k_eval_z" : ctx->eval_ws ? "k_eval_ws" : "k_eval<true>");
+    if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_z ? "k_eval_z" : "k_eval<true>");
     {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
        // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
        // they get narrow CTAs (measured, accumulate + finish: 1000 cameras x 2000 obs 31 us at 64 threads vs 35 at 128;
@@ -1008,7 +983,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   CKR(ctx->r.alloc(M)); CKR(ctx->r_new.alloc(M)); CKR(ctx->jl.alloc(6 * M)); CKR(ctx->jc.alloc(6 * (size_t)m));
   CKR(ctx->jl_new.alloc(6 * M)); CKR(ctx->jc_new.alloc(6 * (size_t)m));
   CKR(ctx->w.alloc(M)); CKR(ctx->wk.alloc(M)); CKR(ctx->wr.alloc(M)); CKR(ctx->dense_tmp.alloc((size_t)m));
-  CKR(ctx->V.alloc(NL * 21)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->V_new.alloc(NL * 21)); CKR(ctx->gl_new.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
+  CKR(ctx->V.alloc(NL * kVStride)); CKR(ctx->gl.alloc(NL * 6 + 2)); CKR(ctx->V_new.alloc(NL * kVStride)); CKR(ctx->gl_new.alloc(NL * 6 + 2)); CKR(ctx->Vinv.alloc(NL * kVinvStride + 2));
   CKR(ctx->y.alloc(NL * 6 + 2)); CKR(ctx->Dl.alloc(NL * 6)); CKR(ctx->dl.alloc(NL * 6 + 2));
   CKR(ctx->U.alloc(NC * 27)); CKR(ctx->gc.alloc(NC * 6)); CKR(ctx->Dc.alloc(NC * 6));
   CKR(ctx->Mpart.alloc(NC * 39)); CKR(ctx->Minv.alloc(NC * 21)); CKR(ctx->b.alloc(NC * 6));
@@ -1094,10 +1069,6 @@ static int run_jacobian(lba_ctx* c, const LmCtl* ctl, int which) {
     if (c->eval_z) {
       if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_z<2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
       else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_z<1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
-    } else if (c->eval_ws) {
-      if (c->eval_tab_smem && c->eval_stages_j == 3) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 3>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
-      else if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<2, true, 2>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
-      else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval_ws<1, false, 3>), c->grid_eval_j, kTile, c->smem_eval_j, a);
     } else if (c->eval_tab_smem) LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 2, true>), c->grid_eval_j, 2 * kTile, c->smem_eval_j, a);
     else LAUNCH_DYN(c, LBA_K_JACOBIAN, (k_eval<true, 1, false>), c->grid_eval_j, kTile, c->smem_eval_j, a);
     if (c->n_long > 0)   // lines with more than kTile observations: add up their fragments' blocks
@@ -1734,7 +1705,7 @@ extern "C" int lba_normal_equations(lba_ctx* ctx, double* U, double* gc, double*
   CKR(run_blocks(ctx, true));
   if (U && ctx->nc) CK(cudaMemcpyAsync(U, ctx->U.p, (size_t)ctx->nc * 21 * 8, cudaMemcpyDefault, ctx->stream));
   if (gc && ctx->nc) CK(cudaMemcpyAsync(gc, ctx->gc.p, (size_t)ctx->nc * 6 * 8, cudaMemcpyDefault, ctx->stream));
-  if (V && ctx->nl) CK(cudaMemcpyAsync(V, ctx->V.p, (size_t)ctx->nl * 21 * 8, cudaMemcpyDefault, ctx->stream));
+  if (V && ctx->nl) CK(cudaMemcpy2DAsync(V, 21 * 8, ctx->V.p, kVStride * 8, 21 * 8, (size_t)ctx->nl, cudaMemcpyDefault, ctx->stream));   // rows are padded to 22 on the device
   if (gl && ctx->nl) CK(cudaMemcpyAsync(gl, ctx->gl.p, (size_t)ctx->nl * 6 * 8, cudaMemcpyDefault, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return take_launch_err(ctx);

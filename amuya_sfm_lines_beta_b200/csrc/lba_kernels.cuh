@@ -41,7 +41,6 @@
 #include "lba_policy.cuh"
 #include <stddef.h>
 #include <stdint.h>
-#include <stdio.h>
 
 namespace lba {
 
@@ -54,6 +53,7 @@ constexpr int kMaxLinesPerTile = 128;
 #endif
 __host__ __device__ constexpr int lp_stages(int mode) { return mode == 2 /* kModeScalars */ ? LBA_LP_STAGES_SCALARS : 2; }
 constexpr int kVinvStride = 22;        // 21 packed entries + 1 pad -> 176 B rows (16 B aligned)
+constexpr int kVStride = 22;           // V_l rows likewise: a tile's rows are one aligned bulk store of the Jacobian kernel
 
 struct __align__(16) TileMeta {
   int l0;      // first global line of the tile
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
       for (int wi = t; wi < nlg * 4; wi += kTile) {
         const int ll = wi >> 2, part = wi & 3;
         const int s0 = ll ? s_meta->lend[ll - 1] : 0, s1 = s_meta->lend[ll];
-        double* Vo = frag ? a.fragV + (size_t)(frag - 1) * 27 : g_V + (size_t)(l0 + ll) * 21;
+        double* Vo = frag ? a.fragV + (size_t)(frag - 1) * 27 : g_V + (size_t)(l0 + ll) * kVStride;
         double* go = frag ? Vo + 21 : g_gl + (size_t)(l0 + ll) * 6;
         double acc[7] = {0, 0, 0, 0, 0, 0, 0};
         double g0 = 0.0, g1 = 0.0;
@@ -743,18 +743,7 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval(const E
   last_cta_reduce<kTile * NSUB, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
 }
 
-// ---- Jacobian evaluation with rotating summing warps ------------------------------------------------------------
-// Same arithmetic, same stage layout and the same outputs (bit for bit) as k_eval<true, ...>, but no warp ever waits
-// for the other warps of its sub-group.  The per-line sums V_l = sum jl jl^T, g_l = sum jl r of tile `it` belong to
-// ONE warp, warp it mod 8 (lane = line, 27 accumulators, slot order, no divergence); the other seven ARRIVE on the
-// tile's named barrier without waiting (bar.arrive) and go on to the next tile.  The owning warp takes the sums one
-// tile late -- after its own rows of tile it + 1 -- when every other warp has long arrived, so its bar.sync does not
-// block either; it then refills the stage with tile it + S (it owns the TMA issue of "its" tiles).  Every warp does
-// the same work per 8 tiles (8 tiles of rows + 1 tile of sums) and nobody is on a critical chain.  (k_eval did the
-// sums with 4 divergent work items per line on warps 0..3 of the sub-group while warps 4..7 waited at the next CTA
-// barrier: 18 % of its stall samples were that barrier.)  Measured dead ends, config 4: the sums
-// shared by two warps; staging rows in buffers of their own with the stage refilled at the start of a tile; a fourth
-// stage without the shared-memory camera table -- all slower than this form.
+// ---- helpers of the Jacobian evaluation kernel (k_eval_z below) ---------------------------------------------------
 // 16 B / 32 B global stores (naturally aligned); the 256-bit form is sm_100's STG.256
 __device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
@@ -765,347 +754,76 @@ __device__ __forceinline__ void st_global_v4(double* p, double a, double b, doub
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// upper triangle of V_l = sum jl jl^T (21) and g_l = sum jl r (6) over the staged rows [s0, s1) of one line (slot order,
-// one FMA chain per sum)
-template <int ROW>
-__device__ __forceinline__ void line_block_acc(const double* __restrict__ s_stg, int s0, int s1, double (&v)[21], double (&g)[6]) {
+// One half of the 27 sums of a line: rows [P0, P1) of the upper triangle of V_l and the same entries of g_l
+// (P0 = 0, P1 = 2: 11 + 2 sums; P0 = 2, P1 = 6: 10 + 4 sums), each sum one FMA chain in slot order.  NV values of V_l
+// starting at packed index sym_idx(P0, P0), then P1 - P0 values of g_l.
+template <int ROW, int P0, int P1>
+__device__ __forceinline__ void line_block_half(const double* __restrict__ s_stg, int s0, int s1,
+                                                double (&v)[(P1 - P0) * 6 - (P1 * (P1 - 1) - P0 * (P0 - 1)) / 2], double (&g)[P1 - P0]) {
+  constexpr int NV = (P1 - P0) * 6 - (P1 * (P1 - 1) - P0 * (P0 - 1)) / 2;
 #pragma unroll
-  for (int q = 0; q < 21; ++q) v[q] = 0.0;
+  for (int q = 0; q < NV; ++q) v[q] = 0.0;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) g[q] = 0.0;
+  for (int q = 0; q < P1 - P0; ++q) g[q] = 0.0;
 #pragma unroll 2
   for (int s = s0; s < s1; ++s) {
     const double* row = s_stg + s * ROW;
-    double x[6];
+    double x[6 - P0];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) x[q] = row[q];
+    for (int q = 0; q < 6 - P0; ++q) x[q] = row[P0 + q];
     const double rr = row[6];
     int e = 0;
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
+    for (int p = P0; p < P1; ++p) {
 #pragma unroll
-      for (int c = p; c < 6; ++c) { v[e] += x[p] * x[c]; ++e; }
-      g[p] += x[p] * rr;
+      for (int c = p; c < 6; ++c) { v[e] += x[p - P0] * x[c - P0]; ++e; }
+      g[p - P0] += x[p - P0] * rr;
     }
   }
-}
-
-template <int NSUB, bool TAB_SMEM, int S>   // S: pipeline stages per sub-group (compile time: it % S, it / S are everywhere)
-__global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_ws(const EvalArgs a) {
-  constexpr int kThreads = kTile * NSUB;
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ double red[kThreads / 32];
-#ifdef LBA_AB_CLOCK
-  __shared__ long long ck_issue[NSUB][kMaxStages];
-#endif
-  __shared__ uint64_t full[NSUB][kMaxStages];
-  constexpr int lag = S >= 3 ? 1 : 0;
-  const int stage_bytes = eval_stage_bytes(a.lmax);
-  const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5, lane = t & 31;
-  const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
-  unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_sub_bytes(a.lmax, S);
-  const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
-  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-
-  if (t == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&full[sub][s], 1);
-    fence_barrier_init();
-  }
-  pdl_prologue();
-  if (ctl_skip_trial(a.ctl)) return;   // uniform over the grid
-  const int set = ctl_cur(a.ctl) ^ a.which;
-  const CamRec* g_recs = a.recs.sel(set);
-  const double* g_pts = a.pts.sel(set);
-  double* g_r = a.r.sel(set);
-  double* g_jl = a.jl.sel(set);
-  double* g_jc = a.jc.sel(set);
-  double* g_V = a.V.sel(set);
-  double* g_gl = a.gl.sel(set);
-  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : g_recs;
-  if (TAB_SMEM) {
-    const double2* src = reinterpret_cast<const double2*>(g_recs);
-    double2* dst = reinterpret_cast<double2*>(smem);
-    for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kThreads) dst[q] = __ldg(src + q);
-  }
-  __syncthreads();
-
-  auto issue = [&](int it, int nl, int l0) {
-    const int tile = first + it * stride;
-    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
-    uint64_t* bar = &full[sub][it % S];
-    mbar_expect_tx(bar, 9 * kTile * 8 + (uint32_t)sizeof(TileIdx) + nl * 48);
-    bulk_g2s(st, a.cst + (size_t)tile * 9 * kTile, 9 * kTile * 8, bar);
-    bulk_g2s(st + kEvOffIdx, a.tidx + tile, (uint32_t)sizeof(TileIdx), bar);
-    if (nl > 0) bulk_g2s(st + kEvOffPts, g_pts + (size_t)l0 * 6, nl * 48, bar);
-#ifdef LBA_AB_CLOCK
-    ck_issue[sub][it % S] = clock64();
-#endif
-  };
-  if (t == 0) {
-    for (int it = 0; it < S && it < my_n; ++it) {
-      const TileMeta* mt = &a.tidx[first + it * stride].meta;
-      issue(it, mt->nl, mt->l0);
-    }
-  }
-
-  double cost_acc = 0.0, gmax = 0.0;
-#ifdef LBA_AB_CLOCK
-  long long ck_wait = 0, ck_sums = 0, ck_nsync = 0, ck_store = 0, ck_lat = 0, ck_nlat = 0, ck_lat_all = 0, ck_acc = 0, ck_vg = 0, ck_nsums = 0;
-  const long long ck_start = clock64();
-#endif
-  // per-line blocks of tile `it` (this warp owns it), then the refill of its stage
-  auto line_sums = [&](int it) {
-    int nx_l0 = 0, nx_nl = 0;
-    const bool refill = it + S < my_n;
-    if (lane == 0 && refill) {   // (l0, nl) of the refilling tile: loaded now, used after the sums
-      const int2 v = __ldg(reinterpret_cast<const int2*>(&a.tidx[first + (it + S) * stride].meta));
-      nx_l0 = v.x; nx_nl = v.y;
-    }
-    const int sidx = it % S;
-    unsigned char* st = sbase + (size_t)sidx * stage_bytes;
-    const double* s_stg = reinterpret_cast<const double*>(st);
-    const TileMeta* s_meta = &reinterpret_cast<const TileIdx*>(st + kEvOffIdx)->meta;
-#ifdef LBA_AB_CLOCK
-    const long long ck0 = clock64();
-#endif
-    named_sync(1 + sub * kMaxStages + sidx, kTile);   // every row of the tile is staged
-#ifdef LBA_AB_CLOCK
-    ck_nsync += clock64() - ck0;
-#endif
-    const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
-    if (!frag) {
-      for (int lb = 0; lb < nlg; lb += 32) {
-        const int ll = lb + lane;
-        const int nb = nlg - lb < 32 ? nlg - lb : 32;
-        const bool live = ll < nlg;
-        double v[21], g[6];
-        const int s0 = live && ll ? s_meta->lend[ll - 1] : 0, s1 = live ? s_meta->lend[ll] : 0;
-#ifdef LBA_AB_CLOCK
-        const long long cka = clock64();
-#endif
-#ifndef LBA_AB_NOSUMS
-        line_block_acc<kEvRow>(s_stg, s0, s1, v, g);
-#endif
-#ifdef LBA_AB_CLOCK
-        if (v[0] == 1.2345) printf("x");
-        const long long ckb = clock64();
-        ck_acc += ckb - cka; ++ck_nsums;
-#endif
-        if (live) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const double ab = fabs(g[q]);
-            gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
-          }
-        }
-        double* Vo = g_V + (size_t)(l0 + lb) * 21;
-        double* go = g_gl + (size_t)(l0 + lb) * 6;
-        // The 27 sums of a line sit in one lane: stored from there, every store instruction would touch one 128 B
-        // line per lane (27 x ~25 L1 wavefronts per tile, as many as the whole jc scatter).  The rows summed so far
-        // are dead, so the warp transposes through them -- lane-major records of 27 doubles (odd stride) -- and
-        // writes the batch's V_l and g_l, which are contiguous in global memory, with lane-strided stores.
-        const int rows_done = s_meta->lend[lb + nb - 1];
-        if (3 * nb <= rows_done) {   // 27 doubles per line fit in the 9-double rows below the next batch's first row
-          double* stg = const_cast<double*>(s_stg);
-          __syncwarp();
-          if (live) {
-#pragma unroll
-            for (int q = 0; q < 21; ++q) stg[lane * 27 + q] = v[q];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) stg[lane * 27 + 21 + q] = g[q];
-          }
-          __syncwarp();
-          for (int e = lane; e < nb * 21; e += 32) {
-            const int li = e / 21;
-            Vo[e] = stg[li * 27 + (e - li * 21)];
-          }
-          for (int e = lane; e < nb * 6; e += 32) {
-            const int li = e / 6;
-            go[e] = stg[li * 27 + 21 + (e - li * 6)];
-          }
-        } else if (live) {   // lines of one or two observations: straight from the registers
-#pragma unroll
-          for (int q = 0; q < 21; ++q) Vo[lane * 21 + q] = v[q];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) go[lane * 6 + q] = g[q];
-        }
-#ifdef LBA_AB_CLOCK
-        ck_vg += clock64() - ckb;
-#endif
-      }
-    } else if (lane < 27) {
-      // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
-      // fragments and takes the gradient norm
-      const int s1 = s_meta->lend[0];
-      const int pa = lane < 21 ? c_sym_a[lane] : lane - 21, pb = lane < 21 ? c_sym_b[lane] : 6;
-      double acc = 0.0;
-      for (int s = 0; s < s1; ++s) acc += s_stg[s * kEvRow + pa] * s_stg[s * kEvRow + pb];
-      a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
-    }
-    if (refill) {
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) issue(it + S, nx_nl, nx_l0);
-    }
-#ifdef LBA_AB_CLOCK
-    ck_sums += clock64() - ck0;
-#endif
-  };
-
-  for (int it = 0; it < my_n; ++it) {
-    const int tile = first + it * stride;
-    unsigned char* st = sbase + (size_t)(it % S) * stage_bytes;
-    double* s_cst = reinterpret_cast<double*>(st);
-    const TileIdx* s_idx = reinterpret_cast<const TileIdx*>(st + kEvOffIdx);
-    const double* s_pts = reinterpret_cast<const double*>(st + kEvOffPts);
-#ifdef LBA_AB_CLOCK
-    const long long ckw = clock64();
-#endif
-    mbar_wait(&full[sub][it % S], (it / S) & 1);
-#ifdef LBA_AB_CLOCK
-    {
-      const long long now = clock64();
-      ck_wait += now - ckw;
-      ck_lat_all += now - ck_issue[sub][it % S];
-      if (now - ckw > 200) { ck_lat += now - ck_issue[sub][it % S]; ++ck_nlat; }
-    }
-#endif
-
-    const int cam = s_idx->cam[t];
-    const size_t i = (size_t)tile * kTile + t;
-    double r = 0.0, rho_cost = 0.0;
-    double jl[6] = {0, 0, 0, 0, 0, 0};
-    double jw[3] = {0, 0, 0};
-    int pos = 0;
-    if (cam >= 0) {
-      pos = s_idx->pos[t];
-      double n[3], m0[3], m1[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        n[k] = s_cst[t * 9 + k];
-        m0[k] = s_cst[t * 9 + 3 + k];
-        m1[k] = s_cst[t * 9 + 6 + k];
-      }
-      double w[3], c[3], A, B, C;
-      if (TAB_SMEM) {
-        const double2* p = reinterpret_cast<const double2*>(recs + cam);
-        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
-        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
-        A = v3.x; B = v3.y; C = v4.x;
-      } else {
-        load_camrec(recs, cam, w, c, A, B, C);
-      }
-      const double* X = s_pts + (int)s_idx->ll[t] * 6;
-      double X0[3] = {X[0], X[1], X[2]}, X1[3] = {X[3], X[4], X[5]};
-#ifdef LBA_AB_NOMATH
-      double tq[3] = {w[0] + c[0], w[1] + c[1], w[2] + c[2] + A + B + C};
-      jl[0] = X0[0] + n[0]; jl[1] = X0[1] + n[1]; jl[2] = X0[2] + n[2]; jl[3] = X1[0] + m0[0]; jl[4] = X1[1] + m0[1]; jl[5] = X1[2] + m0[2];
-      r = m1[0] + m1[1] + m1[2];
-      jw[0] = tq[0]; jw[1] = tq[1]; jw[2] = tq[2];
-      rho_cost = r * r;
-#else
-      double R[9];
-      build_R(w, A, B, R);
-      double tq[3] = {0, 0, 0};
-      const double e0 = endpoint_term<true>(R, c, X0, n, m0, jl, tq);
-      const double e1 = endpoint_term<true>(R, c, X1, n, m1, jl + 3, tq);
-      r = e0 + e1;
-      if (a.loss) {   // scipy's robust-loss scaling, as in k_eval
-        const double rs = r / a.f_scale;
-        const double z = rs * rs;
-        double r0, r1, r2;
-        robust_rho(a.loss, z, r0, r1, r2);
-        rho_cost = a.f_scale * a.f_scale * r0;
-        double js = r1 + 2.0 * r2 * z;
-        js = sqrt(js < 2.220446049250313e-16 ? 2.220446049250313e-16 : js);
-        r = r * r1 / js;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) jl[k] *= js;
-        tq[0] *= js; tq[1] *= js; tq[2] *= js;
-      } else {
-        rho_cost = r * r;
-      }
-      double G[9];
-      build_G(w, B, C, G);
-      jw[0] = G[0] * tq[0] + G[3] * tq[1] + G[6] * tq[2];
-      jw[1] = G[1] * tq[0] + G[4] * tq[1] + G[7] * tq[2];
-      jw[2] = G[2] * tq[0] + G[5] * tq[1] + G[8] * tq[2];
-#endif
-    }
-    cost_acc += rho_cost;
-#ifdef LBA_AB_CLOCK
-    const long long cks = clock64();
-#endif
-#ifndef LBA_AB_NOJC
-    if (cam >= 0) {   // d r/d w = G^T tq ;  d r/d c = -(jl0 + jl1): one 48 B record at the camera-order position
-      // 48 B records: an even position starts a 32 B sector, an odd one ends one -- one 32 B and one 16 B store, both
-      // naturally aligned (two scattered store instructions per warp instead of three)
-      const double c0 = -(jl[0] + jl[3]), c1 = -(jl[1] + jl[4]), c2 = -(jl[2] + jl[5]);
-      double* dst = g_jc + (size_t)pos * 6;
-      const bool odd = pos & 1;
-      st_global_v2(dst + (odd ? 0 : 4), odd ? jw[0] : c1, odd ? jw[1] : c2);
-      st_global_v4(dst + (odd ? 2 : 0), odd ? jw[2] : jw[0], odd ? c0 : jw[1], odd ? c1 : jw[2], odd ? c2 : c0);
-    }
-#else
-    cost_acc += jw[0] + jw[1] + jw[2] + pos;
-#endif
-    g_r[i] = r;
-#ifndef LBA_AB_NOJL
-#pragma unroll
-    for (int k = 0; k < 6; ++k) g_jl[((size_t)tile * 6 + k) * kTile + t] = jl[k];
-#endif
-    // the slot's own constants row becomes its staging row (jl, r)
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s_cst[t * kEvRow + k] = jl[k];
-    s_cst[t * kEvRow + 6] = r;
-    fence_proxy_async();
-    if (warp != (it & 7)) named_arrive(1 + sub * kMaxStages + it % S, kTile);
-#ifdef LBA_AB_CLOCK
-    ck_store += clock64() - cks;
-#endif
-    if (it >= lag && warp == ((it - lag) & 7)) line_sums(it - lag);
-  }
-  if (lag && my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
-#ifdef LBA_AB_CLOCK
-  if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-    printf("cta %d sub %d warp %d tiles %d: total %lld  wait %lld  store %lld  sums %lld (named_sync %lld)  waited %lld times, issue->ready then %lld; issue->use avg %lld\n", blockIdx.x, sub, warp, my_n,
-           clock64() - ck_start, ck_wait, ck_store, ck_sums, ck_nsync, ck_nlat, ck_nlat ? ck_lat / ck_nlat : 0, ck_lat_all / (my_n ? my_n : 1)),
-    printf("      sums calls %lld: accumulate %lld, V/g out %lld per call\n", ck_nsums, ck_acc / (ck_nsums ? ck_nsums : 1), ck_vg / (ck_nsums ? ck_nsums : 1));
-#endif
-
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double other = __shfl_xor_sync(0xffffffffu, gmax, o);
-    gmax = (other > gmax || other != other) ? other : gmax;
-  }
-  if (lane == 0 && gmax != 0.0) atomicMax(a.gbits.sel(set), (unsigned long long)__double_as_longlong(gmax));
-  const double cs[1] = {block_sum<kThreads>(cost_acc, red)};
-  last_cta_reduce<kThreads, 1>(cs, a.cost_partial, a.ticket, a.cost_out, 0.5, red);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_eval_z: the Jacobian evaluation with the load pipeline decoupled from the per-line sums.
 //
-// Clock counters in k_eval_ws (config 4) showed where its time went: 39 % of every warp's cycles waiting for tile data,
-// although a bulk load takes only ~3000 cycles from issue to arrival.  There the staging rows of the per-line sums live
-// INSIDE the load stage, so a stage is refilled only after the owning warp has finished its rows of the NEXT tile and
-// then the sums of this one (~5000 cycles on one warp): arrival of tile k+2 = arrival of tile k + rows + sums + load,
-// whatever the number of stages.  Here a stage is dead as soon as every warp holds its slot's constants in registers
-// -- a few hundred cycles after the tile has arrived -- and is refilled right then (seven warps bar.arrive, a rotating
-// issuer warp bar.syncs and issues the bulk copies of tile k+2): two stages suffice.  The staging rows (jl, r: 56 B per
-// slot) have two buffers of their own; the sums of tile k are still taken one tile late by warp k mod 8, which then
-// releases the buffer through an mbarrier that the writers of tile k+2 wait on (passed long before in steady state).
-// The tile's line table is copied into a small ring next to the staging buffers before the stage is refilled.
-// Same arithmetic and the same order of every sum as k_eval_ws / k_eval<true>: the outputs are bit-identical.
+// Its predecessor (round 2's first "rotating summing warps" kernel, 112 us on config 4) kept the staging rows of the
+// per-line sums INSIDE the load stage, so a stage was refilled only after the owning warp had finished its rows of
+// the NEXT tile and then the sums of this one.  Clock counters showed the consequence: 39 % of every warp's cycles
+// waiting for tile data although a bulk load takes ~3000 cycles from issue to arrival -- arrival of tile k+2 =
+// arrival of tile k + rows + sums + load, whatever the number of stages.  Here
+//  * a stage is dead as soon as every warp holds its slot's constants in registers, a few hundred cycles after the
+//    tile has arrived, and is refilled right then (seven warps bar.arrive, a rotating issuer warp bar.syncs, keeps
+//    the tile's line table in a small ring and issues the bulk copies of tile k+2): two stages suffice;
+//  * the staging rows (jl, r: 56 B per slot) have two buffers of their own; the sums of tile k are taken one tile late
+//    by two warps (half the 27 sums each), which release the buffer through an mbarrier that the writers of tile k+2
+//    wait on, and leave through a small output buffer and the bulk-copy engine (shared -> global);
+//  * the shared-memory camera table holds 64 B records (w, c, A, B); C is recomputed per observation.
+// Measured on config 4 (ablation builds, same run): the arithmetic is free (replacing it by moves changes nothing);
+// without the jc scatter 80 us, without the jl stores 83 us, without both 76 us, all of them at ~4.2 TB/s of DRAM
+// traffic -- the kernel sits on the LSU data pipe (60 % busy, two thirds of it shared-memory loads) and the memory
+// system together, not on any one of them.  The order of every sum is that of k_eval<true>.
 constexpr int kEzRow = 7;        // staging row (jl[6], r): 56 B, an odd number of 8 B words
 constexpr int kEzMetaRing = 4;   // line tables of the last four tiles
 __host__ __device__ inline int eval_z_stg_bytes() { return kTile * kEzRow * 8; }
+constexpr int kEzOutBytes = 32 * (kVStride + 6) * 8;   // V_l | g_l rows of one batch of 32 lines, laid out as in global memory
+constexpr int kEzRecBytes = 64;  // shared-memory camera record: w, c, A, B (C is recomputed: the table is what limits the camera count)
 __host__ __device__ inline int eval_z_sub_bytes(int lmax) {
-  return 2 * eval_stage_bytes(lmax) + 2 * eval_z_stg_bytes() + ((kEzMetaRing * (int)sizeof(TileMeta) + 127) & ~127);
+  return 2 * eval_stage_bytes(lmax) + 2 * eval_z_stg_bytes() + kEzOutBytes + ((kEzMetaRing * (int)sizeof(TileMeta) + 127) & ~127);
 }
+__host__ __device__ inline int eval_z_tab_bytes(int nc) { return (nc * kEzRecBytes + 127) & ~127; }
 __host__ __device__ inline int eval_z_smem_bytes(int lmax, int nsub, int nc_tab) {
-  return eval_tab_bytes(nc_tab) + nsub * eval_z_sub_bytes(lmax) + 128;
+  return eval_z_tab_bytes(nc_tab) + nsub * eval_z_sub_bytes(lmax) + 128;
 }
+// C = (t - sin t) / t^3 from t^2 and A = sin t / t (the series of rodrigues_coeffs below t = 0.1)
+__device__ __forceinline__ double coeff_C(double t2, double A) {
+  const double ser = 1.0 / 6 + t2 * (-1.0 / 120 + t2 * (1.0 / 5040 + t2 * (-1.0 / 362880 + t2 * (1.0 / 39916800))));
+  return t2 < 0.01 ? ser : (1.0 - A) / t2;
+}
+// shared -> global bulk copy (16 B aligned, size % 16 == 0), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -1115,20 +833,22 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
   constexpr int kThreads = kTile * NSUB;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[kThreads / 32];
-  __shared__ uint64_t full[NSUB][2], sfree[NSUB][2];
+  __shared__ uint64_t full[NSUB][2], sfree[NSUB][2], ofree[NSUB];
   const int stage_bytes = eval_stage_bytes(a.lmax);
   const int sub = threadIdx.x / kTile, t = threadIdx.x % kTile, warp = t >> 5, lane = t & 31;
-  const int tab_bytes = TAB_SMEM ? eval_tab_bytes(a.nc) : 0;
+  const int tab_bytes = TAB_SMEM ? eval_z_tab_bytes(a.nc) : 0;
   unsigned char* sbase = smem + tab_bytes + (size_t)sub * eval_z_sub_bytes(a.lmax);
   unsigned char* gbase = sbase + 2 * stage_bytes;                       // two staging buffers
-  TileMeta* mring = reinterpret_cast<TileMeta*>(gbase + 2 * eval_z_stg_bytes());
+  double* obuf = reinterpret_cast<double*>(gbase + 2 * eval_z_stg_bytes());   // V_l | g_l rows on their way out
+  TileMeta* mring = reinterpret_cast<TileMeta*>(gbase + 2 * eval_z_stg_bytes() + kEzOutBytes);
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
   // named barriers of the sub-group: 1 + 4 sub + s: stage s consumed;  1 + 4 sub + 2 + b: rows of staging buffer b staged
-  const int bar0 = 1 + sub * 4;
+  const int bar0 = 1 + sub * 6;
 
   if (t == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[sub][s], 1); mbar_init(&sfree[sub][s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[sub][s], 1); mbar_init(&sfree[sub][s], 2); }
+    mbar_init(&ofree[sub], 1);
     fence_barrier_init();
   }
   pdl_prologue();
@@ -1141,11 +861,10 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
   double* g_jc = a.jc.sel(set);
   double* g_V = a.V.sel(set);
   double* g_gl = a.gl.sel(set);
-  const CamRec* recs = TAB_SMEM ? reinterpret_cast<const CamRec*>(smem) : g_recs;
-  if (TAB_SMEM) {
+  if (TAB_SMEM) {   // w, c, A, B of every camera: the first four of the record's five 16 B words
     const double2* src = reinterpret_cast<const double2*>(g_recs);
     double2* dst = reinterpret_cast<double2*>(smem);
-    for (int q = threadIdx.x; q < a.nc * (int)(sizeof(CamRec) / 16); q += kThreads) dst[q] = __ldg(src + q);
+    for (int q = threadIdx.x; q < a.nc * 4; q += kThreads) dst[q] = __ldg(src + (q >> 2) * 5 + (q & 3));
   }
   __syncthreads();
 
@@ -1166,11 +885,18 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
   }
 
   double cost_acc = 0.0, gmax = 0.0;
-  // per-line blocks of tile `it` (this warp owns it) from its staging buffer, which is then released
-  auto line_sums = [&](int it) {
+  // Per-line blocks of tile `it` from its staging buffer, by TWO warps (half 0: warp it mod 8, rows 0-1 of V_l and
+  // g_l[0..1]; half 1: warp (it + 4) mod 8, rows 2-5 and g_l[2..5]): a summing warp falls behind the others by the time
+  // its sums take, and the stage refill two tiles on waits for the last warp to pick up its constants -- half the sums,
+  // half the delay.  The buffer is released (mbarrier, two arrivals) as soon as the last batch of lines has been summed.
+  // The sums of a line sit in one lane; stored from there every instruction would touch one 128 B line per lane, so both
+  // warps lay their entries of the batch's V_l rows (176 B each, as in global memory) and g_l rows (48 B) out in a small
+  // buffer and lane 0 of half 0 hands the two blocks to the bulk-copy engine (shared -> global).
+  auto line_sums = [&](int it, int half) {
     const int b = it & 1;
-    double* stg = reinterpret_cast<double*>(gbase + (size_t)b * eval_z_stg_bytes());
+    const double* stg = reinterpret_cast<const double*>(gbase + (size_t)b * eval_z_stg_bytes());
     const TileMeta* s_meta = mring + (it & (kEzMetaRing - 1));
+    const int pair_id = bar0 + 4 + b;
     named_sync(bar0 + 2 + b, kTile);   // every row of the tile is staged (and its line table is in the ring)
     const int l0 = s_meta->l0, nlg = s_meta->nl, frag = s_meta->frag;
     if (!frag) {
@@ -1178,60 +904,70 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
         const int ll = lb + lane;
         const int nb = nlg - lb < 32 ? nlg - lb : 32;
         const bool live = ll < nlg;
-        double v[21], g[6];
         const int s0 = live && ll ? s_meta->lend[ll - 1] : 0, s1 = live ? s_meta->lend[ll] : 0;
-        line_block_acc<kEzRow>(stg, s0, s1, v, g);
-        if (live) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const double ab = fabs(g[q]);
-            gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+        double* sg = obuf + nb * kVStride;
+        auto buffer_free = [&]() {   // the rows of the previous batch / tile have left the buffer
+          if (lb == 0) { if (it >= 1) mbar_wait(&ofree[sub], (it - 1) & 1); }
+          else {
+            if (half == 0) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+            named_sync(pair_id, 64);
           }
-        }
-        double* Vo = g_V + (size_t)(l0 + lb) * 21;
-        double* go = g_gl + (size_t)(l0 + lb) * 6;
-        // The 27 sums of a line sit in one lane; stored from there every instruction would touch one 128 B line per
-        // lane.  The rows summed so far are dead: the warp transposes through them (lane-major records of 27 doubles,
-        // an odd stride) and writes the batch's V_l and g_l, contiguous in global memory, with lane-strided stores.
-        const int rows_done = s_meta->lend[lb + nb - 1];
-        if (27 * nb <= kEzRow * rows_done) {
-          __syncwarp();
+        };
+        if (half == 0) {
+          double v[11], g[2];
+          line_block_half<kEzRow, 0, 2>(stg, s0, s1, v, g);
+          if (lb + 32 >= nlg) { __syncwarp(); if (lane == 0) mbar_arrive(&sfree[sub][b]); }
+          buffer_free();
           if (live) {
 #pragma unroll
-            for (int q = 0; q < 21; ++q) stg[lane * 27 + q] = v[q];
+            for (int q = 0; q < 2; ++q) {
+              const double ab = fabs(g[q]);
+              gmax = (ab > gmax || ab != ab) ? ab : gmax;   // NaN propagates
+            }
 #pragma unroll
-            for (int q = 0; q < 6; ++q) stg[lane * 27 + 21 + q] = g[q];
+            for (int q = 0; q < 11; ++q) obuf[lane * kVStride + q] = v[q];
+            sg[lane * 6] = g[0]; sg[lane * 6 + 1] = g[1];
           }
-          __syncwarp();
-          const int nv = nb * 21, ng = nb * 6;
-#pragma unroll 4
-          for (int e = lane; e < nv; e += 32) {
-            const int li = e / 21;
-            Vo[e] = stg[e + li * 6];
-          }
-#pragma unroll 2
-          for (int e = lane; e < ng; e += 32) {
-            const int li = e / 6;
-            go[e] = stg[e + li * 21 + 21];
-          }
-        } else if (live) {   // lines of one to three observations: straight from the registers
+        } else {
+          double v[10], g[4];
+          line_block_half<kEzRow, 2, 6>(stg, s0, s1, v, g);
+          if (lb + 32 >= nlg) { __syncwarp(); if (lane == 0) mbar_arrive(&sfree[sub][b]); }
+          buffer_free();
+          if (live) {
 #pragma unroll
-          for (int q = 0; q < 21; ++q) Vo[lane * 21 + q] = v[q];
+            for (int q = 0; q < 4; ++q) {
+              const double ab = fabs(g[q]);
+              gmax = (ab > gmax || ab != ab) ? ab : gmax;
+            }
 #pragma unroll
-          for (int q = 0; q < 6; ++q) go[lane * 6 + q] = g[q];
+            for (int q = 0; q < 10; ++q) obuf[lane * kVStride + 11 + q] = v[q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sg[lane * 6 + 2 + q] = g[q];
+          }
+        }
+        fence_proxy_async();
+        named_sync(pair_id, 64);   // both halves of the batch are in the buffer
+        if (half == 0 && lane == 0) {
+          bulk_s2g(g_V + (size_t)(l0 + lb) * kVStride, obuf, nb * kVStride * 8);
+          bulk_s2g(g_gl + (size_t)(l0 + lb) * 6, sg, nb * 48);
+          bulk_commit();
         }
       }
-    } else if (lane < 27) {
-      // fragment of a long line: lane k owns sum k over the tile's slots (slot order); k_frag_blocks adds the
+      if (nlg == 0) { __syncwarp(); if (lane == 0) mbar_arrive(&sfree[sub][b]); }
+      if (half == 0 && lane == 0) { bulk_wait_read(); mbar_arrive(&ofree[sub]); }
+    } else {
+      // fragment of a long line: lane k of half 0 owns sum k over the tile's slots (slot order); k_frag_blocks adds the
       // fragments and takes the gradient norm
-      const int s1 = s_meta->lend[0];
-      const int pa = lane < 21 ? c_sym_a[lane] : lane - 21, pb = lane < 21 ? c_sym_b[lane] : 6;
-      double acc = 0.0;
-      for (int s = 0; s < s1; ++s) acc += stg[s * kEzRow + pa] * stg[s * kEzRow + pb];
-      a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
+      if (half == 0 && lane < 27) {
+        const int s1 = s_meta->lend[0];
+        const int pa = lane < 21 ? c_sym_a[lane] : lane - 21, pb = lane < 21 ? c_sym_b[lane] : 6;
+        double acc = 0.0;
+        for (int s = 0; s < s1; ++s) acc += stg[s * kEzRow + pa] * stg[s * kEzRow + pb];
+        a.fragV[(size_t)(frag - 1) * 27 + lane] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&sfree[sub][b]); if (half == 0) mbar_arrive(&ofree[sub]); }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sfree[sub][b]);   // the buffer may take the rows of tile it + 2
   };
 
   int nx_l0 = 0, nx_nl = 0;   // (l0, nl) of the tile this warp will issue next (lane 0)
@@ -1291,13 +1027,14 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
     if (cam >= 0) {
       double w[3], c[3], A, B, C;
       if (TAB_SMEM) {
-        const double2* p = reinterpret_cast<const double2*>(recs + cam);
-        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4];
+        const double2* p = reinterpret_cast<const double2*>(smem + (size_t)cam * kEzRecBytes);
+        const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
         w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; c[0] = v1.y; c[1] = v2.x; c[2] = v2.y;
-        A = v3.x; B = v3.y; C = v4.x;
+        A = v3.x; B = v3.y;
       } else {
-        load_camrec(recs, cam, w, c, A, B, C);
+        load_camrec(g_recs, cam, w, c, A, B, C);
       }
+      C = coeff_C(w[0] * w[0] + w[1] * w[1] + w[2] * w[2], A);   // both variants: the result does not depend on where the table lives
       double R[9];
       build_R(w, A, B, R);
       double tq[3] = {0, 0, 0};
@@ -1342,10 +1079,16 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
 #pragma unroll
     for (int k = 0; k < 6; ++k) stg[t * kEzRow + k] = jl[k];
     stg[t * kEzRow + 6] = r;
-    if (warp != (it & 7)) named_arrive(bar0 + 2 + s, kTile);
-    if (it >= 1 && warp == ((it - 1) & 7)) line_sums(it - 1);
+    if (warp != (it & 7) && warp != ((it + 4) & 7)) named_arrive(bar0 + 2 + s, kTile);
+    if (it >= 1) {
+      if (warp == ((it - 1) & 7)) line_sums(it - 1, 0);
+      else if (warp == ((it + 3) & 7)) line_sums(it - 1, 1);
+    }
   }
-  if (my_n >= 1 && warp == ((my_n - 1) & 7)) line_sums(my_n - 1);
+  if (my_n >= 1) {
+    if (warp == ((my_n - 1) & 7)) line_sums(my_n - 1, 0);
+    else if (warp == ((my_n + 3) & 7)) line_sums(my_n - 1, 1);
+  }
 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1559,7 +1302,7 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
   const int l0 = blockIdx.x * kLfLines;
   const int n = min(kLfLines, nl - l0);
   const int t = threadIdx.x;
-  for (int q = t; q < n * 21; q += kLfLines) sV[q] = __ldg(V + (size_t)l0 * 21 + q);
+  for (int q = t; q < n * kVStride; q += kLfLines) sV[q] = __ldg(V + (size_t)l0 * kVStride + q);
   for (int q = t; q < n * 6; q += kLfLines) {
     sg[q] = __ldg(gl + (size_t)l0 * 6 + q);
     if (scaling_mode != 2) sD[q] = Dl[(size_t)l0 * 6 + q];
@@ -1569,7 +1312,7 @@ __global__ void __launch_bounds__(kLfLines) k_line_factor(int nl, double lam, co
   int cl = 0;
   if (t < n) {
 #pragma unroll
-    for (int e = 0; e < 21; ++e) S[e] = sV[t * 21 + e];
+    for (int e = 0; e < 21; ++e) S[e] = sV[t * kVStride + e];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       double D;
@@ -1959,7 +1702,7 @@ __global__ void __launch_bounds__(32) k_frag_blocks(const LongLines L, const dou
   double v = 0.0;
   if (t < 27) {
     for (int f = L.frag0[q]; f < L.frag0[q + 1]; ++f) v += fragV[(size_t)f * 27 + t];
-    if (t < 21) V2.sel(set)[(size_t)line * 21 + t] = v;
+    if (t < 21) V2.sel(set)[(size_t)line * kVStride + t] = v;
     else gl2.sel(set)[(size_t)line * 6 + t - 21] = v;
   }
   double g = (t >= 21 && t < 27) ? fabs(v) : 0.0;
