@@ -146,6 +146,8 @@ struct lba_ctx {
   DBuf<GridBar> gridbar;
   DBuf<double> cg_partial;
   int cg_ctas = 1, cam_step_ctas = 1;
+  int cg_cluster = 0;      // > 0: the CG vector kernels run as ONE cluster of this many CTAs (<= 1024 cameras, one GPU; LBA_CG_CLUSTER=0: grid kernels)
+  int next_cluster = 0;    // cluster size of the next launch (consumed by launch_kernel)
   bool use_pdl = true;     // programmatic dependent launch between kernels (LBA_PDL=0|1|2, see lba_create)
   // CTA sizes of the one-CTA-per-camera kernels: block sums (k_cam_accum / k_cam_grad) and the PCG product
   int cam_threads = 128, pcg_threads = 128, cam_threads_sel = 128;
@@ -244,8 +246,14 @@ static inline void launch_kernel(lba_ctx* c, void (*kern)(KArgs...), dim3 grid, 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
-  cudaLaunchAttribute at[2];
+  cudaLaunchAttribute at[3];
   int na = 0;
+  if (c->next_cluster) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)c->next_cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    c->next_cluster = 0;
+  }
   if (c->use_pdl && !c->profiling) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
@@ -964,6 +972,9 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cg_step, kCgBlock, 0));
       const int want = cdiv((long long)std::max(nc, 1) * 8, kCgBlock);
       ctx->cg_ctas = std::max(1, std::min({want, kCgMaxCtas, std::max(1, nb) * ctx->n_sm}));
+      const int ncl = cdiv((long long)std::max(nc, 1) * 8, kCgClBlock);
+      ctx->cg_cluster = (ncl <= kCgClMaxCtas && !(getenv("LBA_CG_CLUSTER") && atoi(getenv("LBA_CG_CLUSTER")) == 0)) ? ncl : 0;
+      if (dbg) fprintf(stderr, "[lba_set_problem] CG vector kernels: %s\n", ctx->cg_cluster ? "one cluster (single-GPU solves)" : "grid with software barrier");
     }
     ctx->smem_lp[0] = lp_smem_bytes(lmax, kModeMatvec);
     ctx->smem_lp[1] = lp_smem_bytes(lmax, kModeBacksub);
@@ -1191,7 +1202,12 @@ static int solve_setup(lba_ctx* c, const LmCtl* ctl, double lam, double pcg_tol,
   ca.x = c->cgx.p; ca.r = c->cgr.p; ca.z = c->cgz.p; ca.p = c->cgp.p; ca.tab = c->tab.p; ca.st = c->cgst.p;
   ca.partial = c->cg_partial.p; ca.gb = c->gridbar.p;
   memset(&ca.pl, 0, sizeof ca.pl);
-  LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, c->cg_ctas, kCgBlock, ca);
+  if (c->cg_cluster && c->world == 1) {
+    c->next_cluster = c->cg_cluster;
+    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin_cl, c->cg_cluster, kCgClBlock, ca);
+  } else {
+    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_begin, c->cg_ctas, kCgBlock, ca);
+  }
   sp->issued = 0;
   return LBA_OK;
 }
@@ -1230,7 +1246,12 @@ static int solve_iterate(lba_ctx* c, SolvePlan* sp, int n) {
       if (!pl.seq) CKR(reduce_finish(c, kRgnQ, c->qpart.p, n6));
     }
     sp->ca.pl = pl;
-    LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
+    if (c->cg_cluster && c->world == 1) {
+      c->next_cluster = c->cg_cluster;
+      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step_cl, c->cg_cluster, kCgClBlock, sp->ca);
+    } else {
+      LAUNCH(c, LBA_K_PCG_UPDATE, k_cg_step, c->cg_ctas, kCgBlock, sp->ca);
+    }
   }
   return LBA_OK;
 }
@@ -1740,8 +1761,10 @@ static int enqueue_trial_tail(lba_ctx* c, const LmCtl* ctl) {
   CKR(run_jacobian(c, ctl, 1));
   // cost, rjd, jd2, dl2, x2_lines are contiguous; the gradient norm of the state the solve started from rides along
   CKR(allreduce_scalars(c, 5, ctl));
+  // the decision kernel also posts the pass's scalars to the host mirror (what k_publish does for the other calls)
+  const unsigned long long seq = ++c->publish_seq;
   LAUNCH(c, LBA_K_MISC, k_lm_decide, 1, 32, c->ctl.p, (const Scalars*)c->scal.p, (const CgState*)c->cgst.p,
-         dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), c->trace.p);
+         dual<const unsigned long long>(c->gbits.p, c->gbits_new.p), c->trace.p, (const int*)c->clamped.p, c->d_mirror, seq);
   return LBA_OK;
 }
 
@@ -1799,8 +1822,7 @@ extern "C" int lba_lm_solve(lba_ctx* ctx, double* cams_api, double* pts_api, con
       } else {
         CKR(launch_cam_step(c, ctl));   // same direction, shorter step: both halves of the trial point
       }
-      CKR(enqueue_trial_tail(c, ctl));
-      CKR(publish_scalars(c));
+      CKR(enqueue_trial_tail(c, ctl));   // ends with the decision kernel, which publishes
       if (ahead) {
         const int issued = sp.issued;
         CKR(solve_setup(c, ctl, 0.0, o.pcg_tol, o.pcg_max_iter, &sp, true));

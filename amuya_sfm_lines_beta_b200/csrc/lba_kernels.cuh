@@ -2070,6 +2070,117 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_step(const CgArgs a) {
   }
 }
 
+// ---- the same two kernels for problems of up to 1024 cameras on one GPU: ONE thread-block cluster ------------------
+// 8 CTAs x 1024 threads hold one lane per (camera, component), so every vector element lives in a register from its
+// load to its store; the two dot products of a step are block sums exchanged through distributed shared memory and
+// added in rank order after a hardware cluster barrier (a few hundred ns, against ~3 us for the software grid barrier
+// above: store, fence, atomic, poll, fence, reload).  Same formulas; the block sums partition the cameras differently,
+// so the scalars differ from the grid kernels' in the last bits.
+constexpr int kCgClBlock = 1024;
+constexpr int kCgClMaxCtas = 8;   // portable cluster size
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem(const double* local, unsigned rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+// sum over the cluster, the same bits in every thread of every CTA (`slot`: one double of shared memory per use)
+__device__ __forceinline__ double cluster_sum(double v, double* red, double* slot) {
+  const double mine = block_sum<kCgClBlock>(v, red);
+  if (threadIdx.x == 0) *slot = mine;
+  cluster_sync_all();
+  const unsigned lane = threadIdx.x & 31;
+  const double part = lane < cluster_nctarank() ? ld_dsmem(slot, lane) : 0.0;
+  return warp_sum(part);
+}
+
+__global__ void __launch_bounds__(kCgClBlock) k_cg_begin_cl(const CgArgs a) {
+  pdl_prologue();
+  __shared__ double red[kCgClBlock / 32];
+  __shared__ double slot[1];
+  if (ctl_skip_solve(a.ctl)) return;   // uniform over the cluster
+  const double* Gm = a.Gm.sel(ctl_cur(a.ctl));
+  const double* cams = a.cams.sel(ctl_cur(a.ctl));
+  const int gt = cluster_ctarank() * kCgClBlock + threadIdx.x;
+  const int k = gt & 7, c = gt >> 3;
+  const bool act = c < a.nc && k < 6;
+  const size_t cc = act ? c : 0, e = cc * 6 + (act ? k : 0);
+  const double rk = act ? a.b[e] : 0.0;
+  const double zk = group_minv(a.Minv + cc * 21, rk, k, act);
+  if (act) { a.x[e] = 0.0; a.r[e] = rk; a.z[e] = zk; a.p[e] = zk; }
+  group_table(Gm + cc * 9, cams + cc * 6, zk, k, act, a.tab + cc * 6);
+  const double rz = cluster_sum(act ? rk * zk : 0.0, red, &slot[0]);
+  if (gt == 0) {
+    a.st->rz = rz; a.st->rz0 = rz; a.st->pq = 0.0; a.st->k = 0;
+    a.st->breakdown = 0;
+    a.st->done = !(rz > 0.0);
+  }
+  cluster_sync_all();   // no CTA leaves while its slot may still be read
+}
+
+__global__ void __launch_bounds__(kCgClBlock) k_cg_step_cl(const CgArgs a) {
+  pdl_prologue();
+  __shared__ double red[kCgClBlock / 32];
+  __shared__ double slot[2];
+  if (a.st->done) return;   // uniform over the cluster (written by the previous launch)
+  const double* Gm = a.Gm.sel(ctl_cur(a.ctl));
+  const double* cams = a.cams.sel(ctl_cur(a.ctl));
+  const double lam = a.ctl ? a.ctl->lam : a.lam;
+  const int max_iter = a.ctl ? a.ctl->pcg_max_iter : a.max_iter;
+  const double rz = a.st->rz, rz0 = a.st->rz0;
+  const int k_new = a.st->k + 1;
+  const int gt = cluster_ctarank() * kCgClBlock + threadIdx.x;
+  const int k = gt & 7, c = gt >> 3;
+  const bool act = c < a.nc && k < 6;
+  const size_t cc = act ? c : 0, e = cc * 6 + (act ? k : 0);
+  // everything the lane needs, loaded once
+  const double pp = act ? a.p[e] : 0.0;
+  const double q = act ? a.qpart[e] + lam * a.Dc[e] * pp : 0.0;
+  double xk = act ? a.x[e] : 0.0;
+  double rk = act ? a.r[e] : 0.0;
+  double mrow[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) mrow[j] = act ? a.Minv[cc * 21 + sym_idx(k < j ? k : j, k < j ? j : k)] : 0.0;
+  const double pq = cluster_sum(pp * q, red, &slot[0]);
+  const bool ok = pq > 0.0;
+  const double alpha = ok ? rz / pq : 0.0;
+  xk += alpha * pp;
+  rk = rk - alpha * q;
+  double zk = 0.0;
+  {
+    const int base = (threadIdx.x & 31) & 24;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const double rj = __shfl_sync(0xffffffffu, rk, base + j);
+      zk += mrow[j] * rj;
+    }
+  }
+  const double rz_new = cluster_sum(act ? rk * zk : 0.0, red, &slot[1]);
+  const bool stop = !ok || rz_new <= a.tol2 * rz0 || k_new >= max_iter;
+  const double beta = stop ? 0.0 : rz_new / rz;
+  const double vk = stop ? xk : zk + beta * pp;
+  if (act) {
+    a.x[e] = xk; a.r[e] = rk; a.z[e] = zk;
+    if (!stop) a.p[e] = vk;
+  }
+  group_table(Gm + cc * 9, cams + cc * 6, vk, k, act, a.tab + cc * 6);
+  cluster_sync_all();   // every CTA has read the CG state; no CTA leaves while its slots may still be read
+  if (gt == 0) {
+    a.st->pq = pq;
+    a.st->k = k_new;
+    a.st->rz = rz_new;
+    if (!ok) a.st->breakdown = 1;
+    if (stop) a.st->done = 1;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------
@@ -2126,8 +2237,10 @@ __global__ void k_lm_init(LmCtl* __restrict__ L, const LmCtl opts, const Scalars
 }
 
 // The decision after a trial evaluation (lba_policy.cuh): one thread.
+// It also posts what the host wants to see of the pass (h != NULL): one launch less per trial than k_publish behind it.
 __global__ void k_lm_decide(LmCtl* __restrict__ L, const Scalars* __restrict__ s, const CgState* __restrict__ cg,
-                            const Dual<const unsigned long long> gbits, LmTrace* __restrict__ tr) {
+                            const Dual<const unsigned long long> gbits, LmTrace* __restrict__ tr,
+                            const int* __restrict__ clamped, HostMirror* __restrict__ h, unsigned long long seq) {
   pdl_prologue();
   if (threadIdx.x != 0) return;
   LmCtl c = *L;
@@ -2139,6 +2252,16 @@ __global__ void k_lm_decide(LmCtl* __restrict__ L, const Scalars* __restrict__ s
   t.pcg_iters = cg->k; t.pcg_done = cg->done;
   lm_decide(c, t, tr);
   *L = c;
+  if (h) {
+    h->scal = *s;
+    h->cg = *cg;
+    h->ctl = c;
+    h->gbits = *gbits.sel(c.cur);
+    h->clamped = *clamped;
+    h->spin_error = g_spin_error;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&h->seq) = seq;
+  }
 }
 
 // Trial point on the camera side: cams_new = cams + alpha dc, its camera records and SO(3) Jacobians, the step /
