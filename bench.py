@@ -44,7 +44,7 @@ N_CAMERAS = 1000
 # algorithmic HBM bytes per observation (fp64, int32 indices, 10 observations per line)
 BYTES_PER_OBS = {
     "residual": 72 + 8 + 8 + 4.8,                     # constants, indices, r out, line endpoints (48 B / 10 obs)
-    "jacobian": 72 + 10 + 8 + 96 + 4.8 + 21.6,        # + pos, J row out (12 doubles), V_l,g_l out (27*8/10)
+    "jacobian": 72 + 10 + 8 + 96 + 4.8 + 22.4,        # + pos, J row out (12 doubles), V_l (176 B rows), g_l out (224 B / 10 obs)
     "pcg_line": 48 + 6 + 4.8 + 17.6 + 8,              # jl, indices (ll, cam, meta), endpoints, Vinv (22*8/10), w out
     "pcg_cam": 48 + 4 + 8,                            # jc, cam_perm, w gather
 }
@@ -53,7 +53,7 @@ BYTES_PER_OBS = {
 SURVEY_BYTES_PER_OBS = {"jacobian": 188.8, "pcg_pair": 104.0, "residual": 92.8}
 
 
-NCU_KERNEL_OF_CLASS = {"jacobian": "k_eval<1, 2, 1>", "residual": "k_eval<0, 2, 1>", "pcg_line": "k_line_pass<0>",
+NCU_KERNEL_OF_CLASS = {"jacobian": "k_eval_z<2, 1>", "residual": "k_eval<0, 2, 1>", "pcg_line": "k_line_pass<0>",
                        "pcg_cam": "k_pcg_cam"}
 
 
