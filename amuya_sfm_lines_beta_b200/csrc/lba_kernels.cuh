@@ -267,11 +267,14 @@ struct PeerLink {
   unsigned long long seq;   // 0: peer path inactive (single GPU or NCCL transport)
   unsigned int* ticket;
 };
+// Every CTA orders its writes before its ticket at GPU scope; only the last CTA, which has observed all tickets, pays
+// the system-scope fence before it raises the peers' flags (causality order is cumulative: what it has observed
+// becomes visible to whoever acquires the flag).
 __device__ __forceinline__ void peer_signal_last_cta(const PeerLink& pl) {
   __shared__ int s_last_peer;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();
     s_last_peer = (atomicAdd(pl.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
