@@ -948,7 +948,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       }
     }
     if (dbg) fprintf(stderr, "[lba_set_problem] evaluation kernel: %s, %d stages, %d B shared memory\n",
-                     ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_stages_j, ctx->smem_eval_j);
+                     ctx->eval_tab_smem ? "camera table in shared memory" : "camera table gathered from L2", ctx->eval_z ? 2 : ctx->eval_stages_j, ctx->smem_eval_j);
     if (dbg) fprintf(stderr, "[lba_set_problem] Jacobian evaluation: %s\n", ctx->eval_z ? "k_eval_z" : "k_eval<true>");
     {  // one CTA per camera.  The PCG product (6 sums) is HBM-bound on the jc stream and likes 128 threads once
        // there are >= 4 CTAs per SM; the block sums (27-39 sums per camera) pay for their CTA-wide reduction, so
