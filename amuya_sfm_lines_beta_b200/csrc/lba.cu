@@ -825,7 +825,7 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
   if (Mp64 > 0x7fffffffLL / 12) return fail(LBA_ERR_ARG, "padded observation count out of range");
   const int Mp = (int)Mp64;
   int lmax = 8;
-  for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 7) & ~7);
+  for (const TileMeta& t : meta) lmax = std::max(lmax, (t.nl + 1) & ~1);   // sizes the per-line parts of the shared-memory stages (16 B granules)
   lap("host tiling (per line)");
 
   // (3) back on the device: slot assignment of every observation
