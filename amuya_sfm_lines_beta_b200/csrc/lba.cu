@@ -895,6 +895,13 @@ extern "C" int lba_set_problem(lba_ctx* ctx, int64_t m64, int64_t nc64, int64_t 
       int nb = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, (size_t)smem));
       if (nb < 1) return fail(LBA_ERR_UNSUPPORTED, "line-order kernel does not fit on an SM (%d B shared memory)", smem);
+      {  // ask for no more shared memory per SM than the resident CTAs need: what is left is L1 for the table gathers
+        int smem_sm = 0;
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+        const long long need = (long long)nb * (smem + 1024);
+        if (smem_sm > 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min(100LL, (need * 100 + smem_sm - 1) / smem_sm));
+        if (dbg) fprintf(stderr, "[lba_set_problem] plan: %d CTA(s)/SM x %d B shared memory\n", nb, smem);
+      }
       *grid = std::max(1, std::min((ntiles + nsub - 1) / nsub, nb * ctx->n_sm));
       return LBA_OK;
     };

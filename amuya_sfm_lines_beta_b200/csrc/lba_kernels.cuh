@@ -1474,7 +1474,7 @@ __host__ __device__ inline int lp_stage_bytes(int lmax, int mode) {
 }
 constexpr int kLpRow = 7;  // staging row stride in doubles (6 + pad): 56 B, conflict-free per half-warp
 __host__ __device__ inline int lp_smem_bytes(int lmax, int mode) {
-  return lp_stages(mode) * lp_stage_bytes(lmax, mode) + lmax * 48 /* ul */ + (mode == kModeScalars ? 0 : kTile * kLpRow * 8) + 128;
+  return lp_stages(mode) * lp_stage_bytes(lmax, mode) + (mode == kModeScalars ? 0 : kTile * kLpRow * 8);
 }
 
 // Line-ordered half of S*p (MATVEC), the back-substitution (BACKSUB) and the per-observation
@@ -1490,8 +1490,7 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
   __shared__ double red[kTile / 32];
   __shared__ uint64_t full[kLpStages];
   const int stage_bytes = lp_stage_bytes(a.lmax, MODE);
-  double* ul = reinterpret_cast<double*>(smem + (size_t)kLpStages * stage_bytes);
-  double* s_stg = ul + a.lmax * 6;  // [256][kLpRow]
+  double* s_stg = reinterpret_cast<double*>(smem + (size_t)kLpStages * stage_bytes);  // [256][kLpRow]
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
   const int t = threadIdx.x;
@@ -1554,6 +1553,10 @@ __global__ void __launch_bounds__(kTile, 3) k_line_pass(const LinePassArgs a) {
     const unsigned char* s_ll = s_idx->ll;
     const TileMeta* s_meta = &s_idx->meta;
     const double* s_pts = reinterpret_cast<const double*>(st + kLpOffPts);
+    // u_l of the tile's lines takes the place of their endpoints in the stage: the endpoints are dead after the first
+    // barrier (BACKSUB reads x and writes u at the same index from the same thread), and 3 x this much less shared
+    // memory per SM is what keeps the MATVEC pass under the 164 KB carve-out, i.e. leaves the L1 32 KB larger
+    double* ul = reinterpret_cast<double*>(st + kLpOffPts);
     const double* s_vinv = reinterpret_cast<const double*>(st + off_vinv);
     const double* s_aux = reinterpret_cast<const double*>(st + off_aux);
     const double* s_r = reinterpret_cast<const double*>(st + off_r);
