@@ -816,11 +816,6 @@ __host__ __device__ inline int eval_z_tab_bytes(int nc) { return (nc * kEzRecByt
 __host__ __device__ inline int eval_z_smem_bytes(int lmax, int nsub, int nc_tab) {
   return eval_z_tab_bytes(nc_tab) + nsub * eval_z_sub_bytes(lmax) + 128;
 }
-// C = (t - sin t) / t^3 from t^2 and A = sin t / t (the series of rodrigues_coeffs below t = 0.1)
-__device__ __forceinline__ double coeff_C(double t2, double A) {
-  const double ser = 1.0 / 6 + t2 * (-1.0 / 120 + t2 * (1.0 / 5040 + t2 * (-1.0 / 362880 + t2 * (1.0 / 39916800))));
-  return t2 < 0.01 ? ser : (1.0 - A) / t2;
-}
 // shared -> global bulk copy (16 B aligned, size % 16 == 0), bulk-group completion
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");

@@ -4,6 +4,7 @@ HOST with g++ and checked against the reference-generated fixtures and the oracl
 code on the CPU; this is test infrastructure that lets a change to the kernels' arithmetic be caught without a GPU.
 Tolerances are those of the GPU parity ladder (P1: 1e-9 relative per residual; P2: 1e-12 vs the oracle)."""
 import ctypes as C
+import math
 import os
 import shutil
 import subprocess
@@ -27,6 +28,8 @@ void geo_eval(long m, const double* w, const double* c, const double* X0, const 
   for (long i = 0; i < m; ++i) {
     double A, B, Cc, R[9], G[9];
     rodrigues_coeffs(w + 3 * i, A, B, Cc);
+    // as k_eval_z does: C is not gathered with the camera record but recomputed from |w|^2 and A
+    Cc = coeff_C(w[3 * i] * w[3 * i] + w[3 * i + 1] * w[3 * i + 1] + w[3 * i + 2] * w[3 * i + 2], A);
     build_R(w + 3 * i, A, B, R);
     build_G(w + 3 * i, B, Cc, G);
     double tq[3] = {0, 0, 0};
@@ -45,6 +48,14 @@ void geo_rotation(long n, const double* w, double* R, double* G) {
     rodrigues_coeffs(w + 3 * i, A, B, Cc);
     build_R(w + 3 * i, A, B, R + 9 * i);
     build_G(w + 3 * i, B, Cc, G + 9 * i);
+  }
+}
+// C of the camera record (rodrigues_coeffs) and C as the Jacobian kernel recomputes it
+void geo_coeff_c(long n, const double* w, double* c_rec, double* c_kernel) {
+  for (long i = 0; i < n; ++i) {
+    double A, B;
+    rodrigues_coeffs(w + 3 * i, A, B, c_rec[i]);
+    c_kernel[i] = coeff_C(w[3 * i] * w[3 * i] + w[3 * i + 1] * w[3 * i + 1] + w[3 * i + 2] * w[3 * i + 2], A);
   }
 }
 void geo_rho(long n, int loss, const double* z, double* r0, double* r1, double* r2) {
@@ -127,6 +138,24 @@ def test_rotation_and_so3_jacobian_match_oracle_including_small_angles(geo):
     geo.geo_rotation(C.c_long(len(w)), ptr(w), ptr(R), ptr(G))
     assert np.max(np.abs(R.reshape(-1, 3, 3) - orc.rodrigues(w))) <= 4e-15
     assert np.max(np.abs(G.reshape(-1, 3, 3) - orc.so3_right_jacobian(w))) <= 4e-15
+
+
+def test_recomputed_so3_coefficient_matches_the_camera_record(geo):
+    """k_eval_z keeps 64 B camera records (w, c, A, B) in shared memory and recomputes C = (t - sin t) / t^3 from
+    t^2 and A.  Against the C of the full record and against the Taylor series / closed form evaluated in
+    longdouble, over rotation angles from 1e-9 to beyond pi, both sides of the series switch at t = 0.1 included."""
+    t = np.concatenate([np.logspace(-9, np.log10(3.5), 600), [0.0, 0.0999999, 0.1, 0.1000001, np.pi]])
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=(len(t), 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    w = np.ascontiguousarray(d * t[:, None])
+    c_rec = np.empty(len(t)); c_ker = np.empty(len(t))
+    geo.geo_coeff_c(C.c_long(len(t)), ptr(w), ptr(c_rec), ptr(c_ker))
+    tl = np.linalg.norm(w.astype(np.longdouble), axis=1)
+    exact = np.where(tl < 0.5, sum((-1) ** k * tl ** (2 * k) / np.longdouble(math.factorial(2 * k + 3)) for k in range(12)),
+                     (tl - np.sin(tl)) / np.where(tl > 0, tl, 1) ** 3)
+    # P2's tolerance against the oracle is 1e-12 of the Jacobian's scale; C enters it multiplied by |w|^2 <= 10
+    assert np.max(np.abs(c_ker - c_rec) / c_rec) <= 2e-13
+    assert np.max(np.abs(c_ker - exact.astype(np.float64)) / c_rec) <= 2e-13
 
 
 @pytest.mark.parametrize("loss,code", [("soft_l1", 1), ("huber", 2), ("cauchy", 3), ("arctan", 4)])
