@@ -841,7 +841,8 @@ __global__ void __launch_bounds__(kTile * NSUB, TAB_SMEM ? 1 : 2) k_eval_z(const
   TileMeta* mring = reinterpret_cast<TileMeta*>(gbase + 2 * eval_z_stg_bytes() + kEzOutBytes);
   const int first = blockIdx.x * NSUB + sub, stride = gridDim.x * NSUB;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  // named barriers of the sub-group: 1 + 4 sub + s: stage s consumed;  1 + 4 sub + 2 + b: rows of staging buffer b staged
+  // named barriers of the sub-group, from bar0: + s: stage s consumed;  + 2 + b: rows of staging buffer b staged;
+  // + 4 + b: the two summing warps of the tile in buffer b
   const int bar0 = 1 + sub * 6;
 
   if (t == 0) {
