@@ -486,6 +486,28 @@ def test_many_cameras_take_the_global_gather_variant(LineBA, orc):
     ba.close()
 
 
+@pytest.mark.parametrize("shape", [(40, 3000, 9), (12, 4000, 3), (1500, 3000, 6)])
+def test_jacobian_kernels_agree(LineBA, monkeypatch, shape):
+    """The Jacobian kernel of round 2 (k_eval_z: decoupled load pipeline, sums by two warps, bulk-copied V_l / g_l, C
+    recomputed) against the round-1 kernel it replaces (k_eval<true>, LBA_EVAL_Z=0), with and without the
+    shared-memory camera table and with several batches of lines per tile (3 observations per line).  Same formulas and
+    the same order of every sum; the two instantiations are compiled separately (FMA contraction may differ), so the
+    comparison is to a few ulps of each array's scale, not bitwise."""
+    s = synth(*shape, seed=17)
+    out = {}
+    for z in ("0", "1"):
+        monkeypatch.setenv("LBA_EVAL_Z", z)
+        ba = make_ctx(LineBA, s)
+        r, jc, jl = ba.residuals_jacobian(s.camera_params, s.points_3d)
+        U, gc, V, gl = ba.normal_equations()
+        out[z] = (r, jc, jl, V, gl, U, gc)
+        ba.close()
+    names = ("r", "jc", "jl", "V", "gl", "U", "gc")
+    for name, a0, a1 in zip(names, out["0"], out["1"]):
+        scale = max(np.abs(a0).max(), 1e-300)
+        assert np.max(np.abs(a0 - a1)) <= 1e-13 * scale, name
+
+
 @pytest.mark.parametrize("scene", ["manual3", "toy1_lv2", "synth_noisy"])
 def test_retry_and_evaluation_budget_match_oracle(LineBA, orc, scene):
     """Scenes whose first Gauss-Newton steps overshoot: the rejected trial is retried at the measured length along
